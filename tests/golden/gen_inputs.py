@@ -1,0 +1,77 @@
+"""Seeded synthetic inputs shared by tests/golden/make_golden.py (which runs the real reference)
+and by the tests (which re-create the same inputs for the oracle and the CUDA path).
+
+numpy's PCG64 stream is stable across numpy versions, so a fixture only needs the seed.
+Weights are laid out exactly like the reference state dict:
+quantizers.{i}.in_proj.weight_v [8,D,1], .weight_g [8,1,1], .bias [8],
+quantizers.{i}.out_proj.weight_v [D,8,1], .weight_g [D,1,1], .bias [D], quantizers.{i}.codebook.weight [K,8].
+Unlike the reference's init (g = ||v||, zero biases) g and the biases are randomised so the
+weight-norm fold and both bias paths are exercised.
+"""
+import numpy as np
+
+CD = 8
+
+
+def make_state_dict(seed: int, n_codebooks: int, input_dim: int, codebook_size: int = 1024):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f32 = np.float32
+    sd = {}
+    D, K = input_dim, codebook_size
+    for i in range(n_codebooks):
+        p = f"quantizers.{i}."
+        v_in = (rng.uniform(-1.0, 1.0, (CD, D, 1)) / np.sqrt(D)).astype(f32)
+        g_in = (np.sqrt((v_in.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True))
+                * rng.uniform(0.5, 1.5, (CD, 1, 1))).astype(f32)
+        v_out = (rng.uniform(-1.0, 1.0, (D, CD, 1)) / np.sqrt(CD)).astype(f32)
+        g_out = (np.sqrt((v_out.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True))
+                 * rng.uniform(0.5, 1.5, (D, 1, 1))).astype(f32)
+        sd[p + "in_proj.weight_g"] = g_in
+        sd[p + "in_proj.weight_v"] = v_in
+        sd[p + "in_proj.bias"] = rng.normal(0.0, 0.05, (CD,)).astype(f32)
+        sd[p + "out_proj.weight_g"] = g_out
+        sd[p + "out_proj.weight_v"] = v_out
+        sd[p + "out_proj.bias"] = rng.normal(0.0, 0.05, (D,)).astype(f32)
+        sd[p + "codebook.weight"] = rng.normal(0.0, 1.0, (K, CD)).astype(f32)
+    return sd
+
+
+def make_latents(seed: int, B: int, D: int, T: int, sigma: float = 1.0):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return (rng.normal(0.0, sigma, (B, D, T))).astype(np.float32)
+
+
+def make_imp_map(seed: int, B: int, T: int):
+    """U(0,1) importance map [B,1,T] with a few exact mask-edge values (k / (level*Nq) style) mixed in."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    imp = rng.uniform(0.0, 1.0, (B, 1, T)).astype(np.float32)
+    edges = np.array([0.0, 0.125, 0.25, 0.5, 0.75, 1.0], np.float32)
+    n = min(T, len(edges))
+    imp[0, 0, :n] = edges[:n]
+    return imp
+
+
+def torch_state_dict(sd):
+    import torch
+
+    return {k: torch.from_numpy(np.array(v)) for k, v in sd.items()}
+
+
+# name -> parameters of every committed fixture
+CASES = {
+    # config-1/2 shaped: VBR model, D=1024, Nq=8 (conf/base.yml:9-11), level sweep of configs[1]
+    "vbr_d1024_nq8": dict(kind="vbr", seed=11, D=1024, Nq=8, K=1024, B=2, T=87, sigma=1.0,
+                          levels=[0.25, 0.5, 1.0], imp_seed=21),
+    # per-item tensor level [B,1,1]
+    "vbr_tensor_level": dict(kind="vbr", seed=12, D=1024, Nq=8, K=1024, B=3, T=21, sigma=0.7,
+                             levels=[[0.3, 1.0, 2.5]], imp_seed=22),
+    # CBR class, all stages and early exit (quantize.py:183-184)
+    "cbr_d1024_nq8": dict(kind="cbr", seed=13, D=1024, Nq=8, K=1024, B=2, T=45, sigma=1.0, n_quantizers=[None, 3]),
+    # conf/base_24kbps.yml:9 (Nq=28)
+    "cbr_d1024_nq28": dict(kind="cbr", seed=14, D=1024, Nq=28, K=1024, B=1, T=33, sigma=1.0, n_quantizers=[None]),
+    # class defaults of ResidualVectorQuantize (quantize.py:112-119): input_dim=512, n_codebooks=9
+    "cbr_d512_nq9": dict(kind="cbr", seed=15, D=512, Nq=9, K=1024, B=1, T=40, sigma=1.0, n_quantizers=[None]),
+    # edge shapes: T=1 and T=3, small-magnitude latents (random-init encoder scale)
+    "vbr_t1": dict(kind="vbr", seed=16, D=1024, Nq=8, K=1024, B=3, T=1, sigma=0.007, levels=[1.0], imp_seed=26),
+    "cbr_t3": dict(kind="cbr", seed=17, D=1024, Nq=8, K=1024, B=2, T=3, sigma=0.007, n_quantizers=[None, 1]),
+}
