@@ -1,0 +1,86 @@
+"""Container-only (needs the reference checkout): oracle vs the live reference on larger random cases than the
+committed fixtures, with the near-tie audit, plus state-dict compatibility of the Python mirror."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, ref_import
+from tests import helpers as H
+from tests.golden import gen_inputs as gi
+
+pytestmark = [pytest.mark.reference, pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present")]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_import.load()
+
+
+def test_cbr_random_init_large(ref):
+    """Reference-initialised weights (torch.manual_seed), B=4 x T=431, Nq=8: 13.8k frame-stages."""
+    torch.manual_seed(0)
+    m = ref.ResidualVectorQuantize(input_dim=1024, n_codebooks=8, codebook_size=1024, codebook_dim=8).eval()
+    z = torch.randn(4, 1024, 431)
+    with torch.no_grad():
+        r = m(z)
+    w = c_oracle.OracleWeights.from_state_dict(m.state_dict())
+    o = c_oracle.encode(w, z.numpy(), None, want_z_q_is=False)
+    excused, mask = H.assert_codes_match(w, o, r["codes"].numpy())
+    H.assert_close_frames(o["z_q"], r["z_q"].numpy(), skip=mask, what="z_q")
+    H.assert_close_frames(o["latents"], r["latents"].numpy(), skip=mask, what="latents", rtol=1e-4)
+    assert o["commitment_loss"] == pytest.approx(r["commitment_loss"].item(), rel=1e-4)
+
+
+def test_vbr_with_real_subnet(ref):
+    torch.manual_seed(1)
+    m = ref.VBRResidualVectorQuantize(input_dim=1024, n_codebooks=8, codebook_size=1024, codebook_dim=8, level_min=0.125,
+                                      level_max=6.0, imp2mask_alpha=2.0).eval()
+    z, feat = torch.randn(2, 1024, 87), torch.randn(2, 1024, 87)
+    for level in (0.25, 1.0, 3.0):
+        with torch.no_grad():
+            r = m(z, n_quantizers=None, feat_enc=feat, level=level)
+        w = c_oracle.OracleWeights.from_state_dict(m.state_dict())
+        o = c_oracle.encode(w, z.numpy(), None, r["imp_map"].numpy(), level, want_z_q_is=False)
+        H.assert_codes_match(w, o, r["codes"].numpy())
+        assert np.array_equal(o["mask"], r["mask_imp"].numpy())
+        H.assert_close_frames(o["z_q"], r["z_q"].numpy(), what="z_q")
+        assert ref.cal_bpf_from_mask(r["mask_imp"], [10] * 8) == pytest.approx(float((o["kept"] * 10).sum()) / (2 * 87), rel=1e-6)
+
+
+def test_mirror_state_dict_keys_match_reference(ref):
+    """The Python mirror must load a reference checkpoint unchanged (checkpoint row)."""
+    import vrvq_b200
+
+    torch.manual_seed(2)
+    r = ref.VBRResidualVectorQuantize(input_dim=1024, n_codebooks=8, codebook_size=1024, codebook_dim=8, level_min=0.125, level_max=6.0)
+    ours = vrvq_b200.VBRResidualVectorQuantize(input_dim=1024, n_codebooks=8, codebook_size=1024, codebook_dim=8, level_min=0.125, level_max=6.0)
+    rsd, osd = r.state_dict(), ours.state_dict()
+    assert list(rsd.keys()) == list(osd.keys())
+    assert all(rsd[k].shape == osd[k].shape for k in rsd)
+    ours.load_state_dict(rsd, strict=True)
+    # the PyTorch importance subnet (upstream producer) must agree numerically with the reference's
+    feat = torch.randn(2, 1024, 50)
+    with torch.no_grad():
+        a, b = r.imp_subnet(feat), ours.imp_subnet(feat)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_mirror_encoder_matches_reference(ref):
+    import vrvq_b200
+
+    torch.manual_seed(3)
+    r = ref.DAC_VRVQ(n_codebooks=8, model_type="VBR", level_min=0.125, level_max=6.0).eval()
+    ours = vrvq_b200.DAC_VRVQ(n_codebooks=8, model_type="VBR", level_min=0.125, level_max=6.0).eval()
+    missing, unexpected = [], []
+    sd = {k: v for k, v in r.state_dict().items() if not k.startswith("decoder.")}
+    assert list(sd.keys()) == list(ours.state_dict().keys())
+    ours.load_reference_state_dict(r.state_dict())
+    x = torch.randn(1, 1, 44100) * 0.1
+    with torch.no_grad():
+        xr = r.preprocess(x, 44100)
+        xo = ours.preprocess(x, 44100)
+        assert torch.equal(xr, xo) and xo.shape[-1] == 44544
+        zr, fr = r.encoder(xr, return_feat=True)
+        zo, fo = ours.encoder(xo, return_feat=True)
+    assert zr.shape == (1, 1024, 87)
+    assert torch.allclose(zr, zo, rtol=1e-4, atol=1e-6) and torch.allclose(fr, fo, rtol=1e-4, atol=1e-5)

@@ -1,0 +1,222 @@
+// extern "C" surface of libvrvq.so (see include/vrvq.h).  Host-side logic only: argument checks,
+// weight packing, error strings.  The kernels live in rvq_encode.cu and rvq_aux.cu.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vrvq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return VRVQ_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return VRVQ_ECUDA;
+}
+
+int check_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("no CUDA device: %s (libvrvq has no CPU fallback)", cudaGetErrorString(e));
+        return VRVQ_ENODEVICE;
+    }
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess || major != 10) {
+        cudaGetLastError();
+        set_error("device %d has compute capability %d.x; libvrvq is built for sm_100a only", dev, major);
+        return VRVQ_ENODEVICE;
+    }
+    return VRVQ_OK;
+}
+
+// implemented in rvq_encode.cu / rvq_aux.cu
+int encode_supported(int D, int K, int cd);
+int encode(const vrvq_encode_args *a, void *stream);
+int encode_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem);
+int launch_mask_hard(const float *x, long long x_sb, int B, int T, int nq, float *mask, long long m_sb, long long m_sq, cudaStream_t st);
+int launch_mask_sum(const float *mask, long long m_sb, long long m_sq, int B, int T, int nq, double *sums, cudaStream_t st);
+int launch_remask(const float *zis, long long s_b, long long s_q, long long s_d, const float *imp, long long imp_sb, float level_scaled,
+                  int B, int D, int T, int nq, float *zq, long long zq_sb, long long zq_sd, float *mask, long long m_sb, long long m_sq,
+                  unsigned long long *kept, cudaStream_t st);
+int launch_from_codes(const vrvq_from_codes_args *a, cudaStream_t st);
+int launch_search_latents(const float *blob, int D, int K, const float *lat, long long l_sb, long long l_sc, int B, int T, int n_run,
+                          long long *codes, long long c_sb, long long c_sq, cudaStream_t st);
+
+// F.normalize(codebook) and codebook.pow(2).sum(1) with torch's op order (models/quantize.py:93,99;
+// SURVEY.md A.3/A.4).  This translation unit is compiled with -ffp-contract=off on the host side.
+static void normalize_row(const float *x, float *e, float *c2) {
+    float s = 0.0f;
+    for (int k = 0; k < CD; ++k) {
+        volatile float sq = x[k] * x[k];
+        s = s + sq;
+    }
+    const float n = sqrtf(s);
+    const float den = n > 1e-12f ? n : 1e-12f;
+    float s2 = 0.0f;
+    for (int k = 0; k < CD; ++k) {
+        e[k] = x[k] / den;
+        volatile float sq = e[k] * e[k];
+        s2 = s2 + sq;
+    }
+    *c2 = s2;
+}
+
+}  // namespace vrvq
+
+using namespace vrvq;
+
+extern "C" {
+
+int vrvq_abi_version(void) { return VRVQ_ABI_VERSION; }
+
+const char *vrvq_last_error(void) { return g_err; }
+
+int vrvq_supported(int input_dim, int codebook_size, int codebook_dim) { return encode_supported(input_dim, codebook_size, codebook_dim); }
+
+size_t vrvq_blob_bytes(int n_codebooks, int input_dim, int codebook_size, int codebook_dim) {
+    if (n_codebooks <= 0 || input_dim <= 0 || codebook_size <= 0 || codebook_dim != CD) return 0;
+    const BlobLayout L(input_dim, codebook_size);
+    return sizeof(float) * ((size_t)BLOB_HDR_FLOATS + (size_t)n_codebooks * (size_t)L.stage_floats());
+}
+
+int vrvq_pack_weights(int n_codebooks, int input_dim, int codebook_size, int codebook_dim, const float *w_in, const float *b_in,
+                      const float *w_out, const float *b_out, const float *codebook, void *blob_host, size_t blob_bytes) {
+    if (codebook_dim != CD) {
+        set_error("vrvq_pack_weights: codebook_dim=%d unsupported (only %d)", codebook_dim, CD);
+        return VRVQ_EUNSUPPORTED;
+    }
+    if (n_codebooks <= 0 || input_dim <= 0 || codebook_size <= 0 || (input_dim % 4) != 0 || (codebook_size % 4) != 0) {
+        set_error("vrvq_pack_weights: bad sizes Nq=%d D=%d K=%d (D and K must be positive multiples of 4)", n_codebooks, input_dim,
+                  codebook_size);
+        return VRVQ_EINVAL;
+    }
+    if (!w_in || !b_in || !w_out || !b_out || !codebook || !blob_host) {
+        set_error("vrvq_pack_weights: NULL pointer");
+        return VRVQ_EINVAL;
+    }
+    const size_t need = vrvq_blob_bytes(n_codebooks, input_dim, codebook_size, codebook_dim);
+    if (blob_bytes < need) {
+        set_error("vrvq_pack_weights: blob buffer too small (%zu < %zu)", blob_bytes, need);
+        return VRVQ_EINVAL;
+    }
+    const int D = input_dim, K = codebook_size;
+    const BlobLayout L(D, K);
+    float *blob = static_cast<float *>(blob_host);
+    BlobHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = BLOB_MAGIC;
+    h.version = VRVQ_ABI_VERSION;
+    h.n_codebooks = n_codebooks;
+    h.input_dim = D;
+    h.codebook_size = K;
+    h.stage_floats = L.stage_floats();
+    memcpy(blob, &h, sizeof(h));
+    for (int s = 0; s < n_codebooks; ++s) {
+        float *st = blob + BLOB_HDR_FLOATS + (size_t)s * L.stage_floats();
+        float *p0 = st + L.off_p0(), *p1 = st + L.off_p1(), *p2 = st + L.off_p2(), *raw = st + L.off_raw();
+        const float *wi = w_in + (size_t)s * CD * D;  // [8][D] -> win_t[D][8]
+        for (int d = 0; d < D; ++d)
+            for (int c = 0; c < CD; ++c) p0[d * CD + c] = wi[(size_t)c * D + d];
+        memcpy(p0 + (size_t)D * CD, b_in + (size_t)s * CD, sizeof(float) * CD);
+        const float *cb = codebook + (size_t)s * K * CD;
+        for (int j = 0; j < K; ++j) normalize_row(cb + (size_t)j * CD, p1 + (size_t)j * CD, p1 + (size_t)K * CD + j);
+        memcpy(p2, w_out + (size_t)s * D * CD, sizeof(float) * (size_t)D * CD);
+        memcpy(p2 + (size_t)D * CD, b_out + (size_t)s * D, sizeof(float) * D);
+        memcpy(raw, cb, sizeof(float) * (size_t)K * CD);
+    }
+    return VRVQ_OK;
+}
+
+int vrvq_blob_codebook(const void *blob_host, size_t blob_bytes, int stage, float *cb_norm_out, float *c2_out) {
+    if (!blob_host || blob_bytes < sizeof(BlobHeader)) {
+        set_error("vrvq_blob_codebook: bad blob");
+        return VRVQ_EBLOB;
+    }
+    BlobHeader h;
+    memcpy(&h, blob_host, sizeof(h));
+    if (h.magic != BLOB_MAGIC || stage < 0 || stage >= h.n_codebooks ||
+        blob_bytes < vrvq_blob_bytes(h.n_codebooks, h.input_dim, h.codebook_size, CD)) {
+        set_error("vrvq_blob_codebook: bad blob header or stage");
+        return VRVQ_EBLOB;
+    }
+    const BlobLayout L(h.input_dim, h.codebook_size);
+    const float *p1 = static_cast<const float *>(blob_host) + BLOB_HDR_FLOATS + (size_t)stage * L.stage_floats() + L.off_p1();
+    if (cb_norm_out) memcpy(cb_norm_out, p1, sizeof(float) * (size_t)h.codebook_size * CD);
+    if (c2_out) memcpy(c2_out, p1 + (size_t)h.codebook_size * CD, sizeof(float) * h.codebook_size);
+    return VRVQ_OK;
+}
+
+int vrvq_rvq_encode_f32(const vrvq_encode_args *args, void *stream) { return encode(args, stream); }
+
+int vrvq_rvq_encode_launch_info(const vrvq_encode_args *args, int *grid, int *block, int *smem_bytes) {
+    return encode_launch_info(args, grid, block, smem_bytes);
+}
+
+int vrvq_from_codes_f32(const vrvq_from_codes_args *args, void *stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_from_codes(args, static_cast<cudaStream_t>(stream));
+}
+
+int vrvq_search_latents_f32(const void *blob, int n_codebooks, int input_dim, int codebook_size, const float *latents,
+                            int64_t lat_stride_b, int64_t lat_stride_c, int B, int T, int n_run, int64_t *codes, int64_t codes_stride_b,
+                            int64_t codes_stride_q, void *stream) {
+    if (B < 0 || T < 0 || n_run < 0 || n_run > n_codebooks || input_dim <= 0 || codebook_size <= 0 ||
+        ((long long)B * T * n_run > 0 && (!blob || !latents || !codes))) {
+        set_error("vrvq_search_latents_f32: bad arguments");
+        return VRVQ_EINVAL;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_search_latents(static_cast<const float *>(blob), input_dim, codebook_size, latents, lat_stride_b, lat_stride_c, B, T, n_run,
+                                 reinterpret_cast<long long *>(codes), codes_stride_b, codes_stride_q, static_cast<cudaStream_t>(stream));
+}
+
+int vrvq_generate_mask_hard_f32(const float *x, int64_t x_stride_b, int B, int T, int nq, float *mask, int64_t mask_stride_b,
+                                int64_t mask_stride_q, void *stream) {
+    if (B < 0 || T < 0 || nq < 0 || ((long long)B * T * nq > 0 && (!x || !mask))) {
+        set_error("vrvq_generate_mask_hard_f32: bad arguments");
+        return VRVQ_EINVAL;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_mask_hard(x, x_stride_b, B, T, nq, mask, mask_stride_b, mask_stride_q, static_cast<cudaStream_t>(stream));
+}
+
+int vrvq_mask_sum_f32(const float *mask, int64_t mask_stride_b, int64_t mask_stride_q, int B, int T, int nq, double *sums, void *stream) {
+    if (B < 0 || T < 0 || nq < 0 || ((long long)B * T * nq > 0 && (!mask || !sums))) {
+        set_error("vrvq_mask_sum_f32: bad arguments");
+        return VRVQ_EINVAL;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_mask_sum(mask, mask_stride_b, mask_stride_q, B, T, nq, sums, static_cast<cudaStream_t>(stream));
+}
+
+int vrvq_remask_f32(const float *z_q_is, int64_t s_b, int64_t s_q, int64_t s_d, const float *imp_map, int64_t imp_stride_b,
+                    float level_times_nq, int B, int D, int T, int nq, float *z_q, int64_t zq_stride_b, int64_t zq_stride_d, float *mask,
+                    int64_t mask_stride_b, int64_t mask_stride_q, unsigned long long *kept, void *stream) {
+    if (B < 0 || D < 0 || T < 0 || nq < 1 || ((long long)B * D * T > 0 && (!z_q_is || !imp_map || !z_q))) {
+        set_error("vrvq_remask_f32: bad arguments");
+        return VRVQ_EINVAL;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_remask(z_q_is, s_b, s_q, s_d, imp_map, imp_stride_b, level_times_nq, B, D, T, nq, z_q, zq_stride_b, zq_stride_d, mask,
+                         mask_stride_b, mask_stride_q, kept, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+// Companion kernels of the fused encode: decode-from-codes, mask utilities, level-sweep re-mask.
+// All are streaming, HBM-bound kernels: coalesced along T, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace vrvq {
+
+// ---------------------------------------------------------------------------------------------
+// generate_mask_hard (models/utils.py:55-61): mask[b,k,t] = (x[b,t] - k >= 0)
+// ---------------------------------------------------------------------------------------------
+__global__ void mask_hard_kernel(const float *__restrict__ x, long long x_sb, int B, int T, int nq, float *__restrict__ mask,
+                                 long long m_sb, long long m_sq) {
+    const long long total = (long long)B * nq * T;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % T);
+        const long long r = i / T;
+        const int k = (int)(r % nq);
+        const int b = (int)(r / nq);
+        const float xm = __fsub_rn(x[(long long)b * x_sb + t], (float)k);
+        mask[(long long)b * m_sb + (long long)k * m_sq + t] = (xm >= 0.0f) ? 1.0f : 0.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// numerator of cal_bpf_from_mask (models/utils.py:64-73): sums[k] += sum_{b,t} mask[b,k,t]  (binary64)
+// grid = (blocks_per_row, nq, B)
+// ---------------------------------------------------------------------------------------------
+__global__ void mask_sum_kernel(const float *__restrict__ mask, long long m_sb, long long m_sq, int T, double *__restrict__ sums) {
+    const int k = blockIdx.y, b = blockIdx.z;
+    const float *row = mask + (long long)b * m_sb + (long long)k * m_sq;
+    double acc = 0.0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) acc += (double)row[t];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    __shared__ double wsum[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+        acc = (lane < (int)(blockDim.x >> 5)) ? wsum[lane] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0 && acc != 0.0) atomicAdd(&sums[k], acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Level-sweep re-mask (scripts/inference.py:95-100): z_q[b,d,t] = sum_k z_q_is[b,k,d,t] * mask[b,k,t]
+// with mask from imp_map * level_scaled.  One thread per (b,d,t); the Nq reads per output are each
+// coalesced along t.  grid.x covers t in chunks, grid.y = d-blocks, grid.z = b.
+// ---------------------------------------------------------------------------------------------
+constexpr int RM_DPB = 8;  // channels per CTA row-group
+__global__ void __launch_bounds__(256) remask_kernel(const float *__restrict__ zis, long long s_b, long long s_q, long long s_d,
+                                                     const float *__restrict__ imp, long long imp_sb, float level_scaled, int D, int T,
+                                                     int nq, float *__restrict__ zq, long long zq_sb, long long zq_sd,
+                                                     float *__restrict__ mask, long long m_sb, long long m_sq,
+                                                     unsigned long long *__restrict__ kept) {
+    const int b = blockIdx.z;
+    const int t = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int dr = threadIdx.x >> 5;  // 0..7
+    int nk = 0;
+    if (t < T) {
+        const float x = __fmul_rn(imp[(long long)b * imp_sb + t], level_scaled);
+        for (int k = 0; k < nq; ++k) nk += (__fsub_rn(x, (float)k) >= 0.0f) ? 1 : 0;
+    }
+    if (blockIdx.y == 0 && dr == 0) {  // one warp per (b, t-chunk) owns the mask / kept outputs
+        for (int k = 0; k < nq; ++k) {
+            const bool on = nk > k;
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if ((threadIdx.x & 31) == 0 && kept != nullptr && bal) atomicAdd(&kept[k], (unsigned long long)__popc(bal));
+            if (mask != nullptr && t < T) mask[(long long)b * m_sb + (long long)k * m_sq + t] = on ? 1.0f : 0.0f;
+        }
+    }
+    if (t >= T) return;
+    for (int d = blockIdx.y * RM_DPB + dr; d < D; d += gridDim.y * RM_DPB) {
+        const float *src = zis + (long long)b * s_b + (long long)d * s_d + t;
+        float acc = 0.0f;
+        for (int k = 0; k < nq; ++k) {
+            const float v = __ldcs(src + (long long)k * s_q);
+            acc = __fmaf_rn(k < nk ? 1.0f : 0.0f, v, acc);  // reference multiplies by the 0/1 mask, then sums over k
+        }
+        __stcs(zq + (long long)b * zq_sb + (long long)d * zq_sd + t, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// from_codes (models/quantize.py:217-249): z_q = sum_i (W_out,i codebook_i[codes_i] + b_out,i)
+// Tile = 32 frames of one batch item; 256 threads; thread (lane = frame, warp = channel slice).
+// The gathered rows go to shared memory once per stage; W_out rows are read straight from L2/L1
+// (8 floats per channel, warp-uniform address = one broadcast transaction).
+// ---------------------------------------------------------------------------------------------
+struct FromCodesParams {
+    const float *blob;
+    const long long *codes;
+    long long c_sb, c_sq;
+    const float *mask;
+    long long m_sb, m_sq;
+    float *z_q;
+    long long zq_sb, zq_sd;
+    float *z_p;
+    long long zp_sb, zp_sc;
+    float *z_q_is;
+    long long zqis_sb, zqis_sq, zqis_sd;
+    int *error_flag;
+    int B, T, D, K, n_run, tiles_per_b, stage_floats, off_p2, off_raw;
+};
+
+constexpr int FC_NT = 256;
+constexpr int FC_DCH = 128;  // channels handled per CTA (grid.y covers D / FC_DCH)
+__global__ void __launch_bounds__(FC_NT) from_codes_kernel(const FromCodesParams p) {
+    __shared__ float qs[32][CD][33];  // [stage (<=32)][k][frame], padded
+    __shared__ float ms[32][33];
+    const int tile = blockIdx.x;
+    const int b = tile / p.tiles_per_b, t0 = (tile % p.tiles_per_b) * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t = t0 + lane;
+    const bool valid = t < p.T;
+    const float *stages = p.blob + BLOB_HDR_FLOATS;
+    // gather: warp w handles stages w, w+8, ...
+    for (int s = w; s < p.n_run; s += FC_NT / 32) {
+        long long idx = valid ? p.codes[(long long)b * p.c_sb + (long long)s * p.c_sq + t] : 0;
+        if (idx < 0 || idx >= p.K) {
+            if (p.error_flag) atomicExch(p.error_flag, 1);
+            idx = 0;
+        }
+        const float *raw = stages + (size_t)s * p.stage_floats + p.off_raw + (size_t)idx * CD;
+        const float4 ra = __ldg(reinterpret_cast<const float4 *>(raw));
+        const float4 rb = __ldg(reinterpret_cast<const float4 *>(raw + 4));
+        const float cr[CD] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+        for (int k = 0; k < CD; ++k) {
+            qs[s][k][lane] = cr[k];
+            if (blockIdx.y == 0 && p.z_p != nullptr && valid)
+                p.z_p[(long long)b * p.zp_sb + (long long)(s * CD + k) * p.zp_sc + t] = cr[k];
+        }
+        ms[s][lane] = (p.mask != nullptr && valid) ? p.mask[(long long)b * p.m_sb + (long long)s * p.m_sq + t] : 1.0f;
+    }
+    __syncthreads();
+    const int d_begin = blockIdx.y * FC_DCH;
+    for (int dd = w; dd < FC_DCH; dd += FC_NT / 32) {
+        const int d = d_begin + dd;
+        if (d >= p.D) break;
+        float acc = 0.0f;
+        for (int s = 0; s < p.n_run; ++s) {
+            const float *wo = stages + (size_t)s * p.stage_floats + p.off_p2 + (size_t)d * CD;
+            const float4 wa = __ldg(reinterpret_cast<const float4 *>(wo));
+            const float4 wb = __ldg(reinterpret_cast<const float4 *>(wo + 4));
+            float v = __ldg(stages + (size_t)s * p.stage_floats + p.off_p2 + (size_t)p.D * CD + d);
+            v = __fmaf_rn(wa.x, qs[s][0][lane], v);
+            v = __fmaf_rn(wa.y, qs[s][1][lane], v);
+            v = __fmaf_rn(wa.z, qs[s][2][lane], v);
+            v = __fmaf_rn(wa.w, qs[s][3][lane], v);
+            v = __fmaf_rn(wb.x, qs[s][4][lane], v);
+            v = __fmaf_rn(wb.y, qs[s][5][lane], v);
+            v = __fmaf_rn(wb.z, qs[s][6][lane], v);
+            v = __fmaf_rn(wb.w, qs[s][7][lane], v);
+            if (p.z_q_is != nullptr && valid)
+                __stcs(p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + (long long)d * p.zqis_sd + t, v);
+            acc = __fmaf_rn(ms[s][lane], v, acc);
+        }
+        if (valid) __stcs(p.z_q + (long long)b * p.zq_sb + (long long)d * p.zq_sd + t, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// search_latents (models/quantize.py:87-101 on given latents): grid = (frame tiles, stages); 256 threads;
+// lane = frame, warp w scans codes [w*K/8, (w+1)*K/8) in ascending order (warp-uniform codebook reads),
+// then the 8 partial minima are merged with the first-index tie rule.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) search_latents_kernel(const float *__restrict__ blob, int stage_floats, int off_p1, int K,
+                                                             const float *__restrict__ lat, long long l_sb, long long l_sc, int T,
+                                                             int tiles_per_b, long long *__restrict__ codes, long long c_sb,
+                                                             long long c_sq) {
+    __shared__ float sb[8][32];
+    __shared__ int si[8][32];
+    const int s = blockIdx.y;
+    const int b = blockIdx.x / tiles_per_b, t0 = (blockIdx.x % tiles_per_b) * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t = t0 + lane;
+    const bool valid = t < T;
+    float x[CD];
+#pragma unroll
+    for (int k = 0; k < CD; ++k) x[k] = valid ? lat[(long long)b * l_sb + (long long)(s * CD + k) * l_sc + t] : 0.0f;
+    float ss = __fmul_rn(x[0], x[0]);
+#pragma unroll
+    for (int k = 1; k < CD; ++k) ss = __fadd_rn(ss, __fmul_rn(x[k], x[k]));
+    const float den = fmaxf(__fsqrt_rn(ss), 1e-12f);
+    float e2x[CD], e2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < CD; ++k) {
+        const float e = __fdiv_rn(x[k], den);
+        const float sq = __fmul_rn(e, e);
+        e2 = (k == 0) ? sq : __fadd_rn(e2, sq);
+        e2x[k] = __fmul_rn(2.0f, e);
+    }
+    const float *cbn = blob + BLOB_HDR_FLOATS + (size_t)s * stage_floats + off_p1;
+    const float *c2 = cbn + (size_t)K * CD;
+    float best = __int_as_float(0x7f800000);
+    int bi = 0;
+    const int per = K / 8;
+    for (int j = w * per; j < (w + 1) * per; ++j) {
+        const float4 ca = __ldg(reinterpret_cast<const float4 *>(cbn + (size_t)j * CD));
+        const float4 cb = __ldg(reinterpret_cast<const float4 *>(cbn + (size_t)j * CD + 4));
+        float d = __fmul_rn(e2x[0], ca.x);
+        d = __fmaf_rn(e2x[1], ca.y, d);
+        d = __fmaf_rn(e2x[2], ca.z, d);
+        d = __fmaf_rn(e2x[3], ca.w, d);
+        d = __fmaf_rn(e2x[4], cb.x, d);
+        d = __fmaf_rn(e2x[5], cb.y, d);
+        d = __fmaf_rn(e2x[6], cb.z, d);
+        d = __fmaf_rn(e2x[7], cb.w, d);
+        const float dist = __fadd_rn(__fsub_rn(e2, d), __ldg(c2 + j));
+        if (dist < best) {
+            best = dist;
+            bi = j;
+        }
+    }
+    sb[w][lane] = best;
+    si[w][lane] = bi;
+    __syncthreads();
+    if (w == 0 && valid) {
+        for (int ww = 1; ww < 8; ++ww) {
+            const float ob = sb[ww][lane];
+            const int oi = si[ww][lane];
+            if (ob < best || (ob == best && oi < bi)) {
+                best = ob;
+                bi = oi;
+            }
+        }
+        codes[(long long)b * c_sb + (long long)s * c_sq + t] = (long long)bi;
+    }
+}
+
+// ---- host launchers ----------------------------------------------------------------------------
+static int sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
+int launch_mask_hard(const float *x, long long x_sb, int B, int T, int nq, float *mask, long long m_sb, long long m_sq, cudaStream_t st) {
+    const long long total = (long long)B * nq * T;
+    if (total == 0) return VRVQ_OK;
+    const int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    mask_hard_kernel<<<(int)blocks, threads, 0, st>>>(x, x_sb, B, T, nq, mask, m_sb, m_sq);
+    return check_cuda(cudaGetLastError(), "mask_hard_kernel launch");
+}
+
+int launch_mask_sum(const float *mask, long long m_sb, long long m_sq, int B, int T, int nq, double *sums, cudaStream_t st) {
+    if ((long long)B * nq * T == 0) return VRVQ_OK;
+    const int threads = 256;
+    int bx = (T + threads * 4 - 1) / (threads * 4);
+    if (bx < 1) bx = 1;
+    if (nq > 65535 || B > 65535) {
+        set_error("vrvq_mask_sum_f32: nq and B must be <= 65535");
+        return VRVQ_EUNSUPPORTED;
+    }
+    mask_sum_kernel<<<dim3(bx, nq, B), threads, 0, st>>>(mask, m_sb, m_sq, T, sums);
+    return check_cuda(cudaGetLastError(), "mask_sum_kernel launch");
+}
+
+int launch_remask(const float *zis, long long s_b, long long s_q, long long s_d, const float *imp, long long imp_sb, float level_scaled,
+                  int B, int D, int T, int nq, float *zq, long long zq_sb, long long zq_sd, float *mask, long long m_sb, long long m_sq,
+                  unsigned long long *kept, cudaStream_t st) {
+    if ((long long)B * D * T == 0) return VRVQ_OK;
+    if (B > 65535) {
+        set_error("vrvq_remask_f32: B must be <= 65535");
+        return VRVQ_EUNSUPPORTED;
+    }
+    const int tx = (T + 31) / 32;
+    int dy = (D + RM_DPB - 1) / RM_DPB;
+    if (dy > 65535) dy = 65535;
+    remask_kernel<<<dim3(tx, dy, B), 256, 0, st>>>(zis, s_b, s_q, s_d, imp, imp_sb, level_scaled, D, T, nq, zq, zq_sb, zq_sd, mask, m_sb,
+                                                   m_sq, kept);
+    return check_cuda(cudaGetLastError(), "remask_kernel launch");
+}
+
+int launch_search_latents(const float *blob, int D, int K, const float *lat, long long l_sb, long long l_sc, int B, int T, int n_run,
+                          long long *codes, long long c_sb, long long c_sq, cudaStream_t st) {
+    if ((long long)B * T == 0 || n_run == 0) return VRVQ_OK;
+    if (K % 8 != 0 || n_run > 65535) {
+        set_error("vrvq_search_latents_f32: codebook_size must be a multiple of 8");
+        return VRVQ_EUNSUPPORTED;
+    }
+    const BlobLayout L(D, K);
+    const int tpb = (T + 31) / 32;
+    const long long tiles = (long long)tpb * B;
+    if (tiles > 0x7fffffffLL) {
+        set_error("vrvq_search_latents_f32: too many tiles");
+        return VRVQ_EUNSUPPORTED;
+    }
+    search_latents_kernel<<<dim3((unsigned)tiles, n_run), 256, 0, st>>>(blob, L.stage_floats(), L.off_p1(), K, lat, l_sb, l_sc, T, tpb,
+                                                                        codes, c_sb, c_sq);
+    return check_cuda(cudaGetLastError(), "search_latents_kernel launch");
+}
+
+int launch_from_codes(const vrvq_from_codes_args *a, cudaStream_t st) {
+    if (a == nullptr || a->struct_size != sizeof(vrvq_from_codes_args)) {
+        set_error("vrvq_from_codes_f32: args is NULL or struct_size mismatch");
+        return VRVQ_EINVAL;
+    }
+    if (a->B < 0 || a->T < 0 || a->n_run < 1 || a->n_run > a->n_codebooks || a->n_run > 32) {
+        set_error("vrvq_from_codes_f32: bad sizes B=%d T=%d n_run=%d n_codebooks=%d", a->B, a->T, a->n_run, a->n_codebooks);
+        return a->n_run > 32 ? VRVQ_EUNSUPPORTED : VRVQ_EINVAL;
+    }
+    if (a->blob == nullptr || a->codes == nullptr || a->z_q == nullptr) {
+        set_error("vrvq_from_codes_f32: blob, codes and z_q must be non-NULL");
+        return VRVQ_EINVAL;
+    }
+    if (a->input_dim <= 0 || a->codebook_size <= 0) {
+        set_error("vrvq_from_codes_f32: bad input_dim/codebook_size");
+        return VRVQ_EINVAL;
+    }
+    if ((long long)a->B * a->T == 0) return VRVQ_OK;
+    const BlobLayout L(a->input_dim, a->codebook_size);
+    FromCodesParams p{};
+    p.blob = static_cast<const float *>(a->blob);
+    p.codes = reinterpret_cast<const long long *>(a->codes); p.c_sb = a->codes_stride_b; p.c_sq = a->codes_stride_q;
+    p.mask = a->mask; p.m_sb = a->mask_stride_b; p.m_sq = a->mask_stride_q;
+    p.z_q = a->z_q; p.zq_sb = a->z_q_stride_b; p.zq_sd = a->z_q_stride_d;
+    p.z_p = a->z_p; p.zp_sb = a->z_p_stride_b; p.zp_sc = a->z_p_stride_c;
+    p.z_q_is = a->z_q_is; p.zqis_sb = a->z_q_is_stride_b; p.zqis_sq = a->z_q_is_stride_q; p.zqis_sd = a->z_q_is_stride_d;
+    p.error_flag = a->error_flag;
+    p.B = a->B; p.T = a->T; p.D = a->input_dim; p.K = a->codebook_size; p.n_run = a->n_run;
+    p.tiles_per_b = (a->T + 31) / 32;
+    p.stage_floats = L.stage_floats(); p.off_p2 = L.off_p2(); p.off_raw = L.off_raw();
+    const long long tiles = (long long)p.tiles_per_b * a->B;
+    if (tiles > 0x7fffffffLL) {
+        set_error("vrvq_from_codes_f32: too many tiles");
+        return VRVQ_EUNSUPPORTED;
+    }
+    const int gy = (a->input_dim + FC_DCH - 1) / FC_DCH;
+    from_codes_kernel<<<dim3((unsigned)tiles, gy), FC_NT, 0, st>>>(p);
+    return check_cuda(cudaGetLastError(), "from_codes_kernel launch");
+}
+
+}  // namespace vrvq
