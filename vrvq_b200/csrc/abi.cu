@@ -98,7 +98,7 @@ int vrvq_pack_weights(int n_codebooks, int input_dim, int codebook_size, int cod
         set_error("vrvq_pack_weights: codebook_dim=%d unsupported (only %d)", codebook_dim, CD);
         return VRVQ_EUNSUPPORTED;
     }
-    if (n_codebooks <= 0 || input_dim <= 0 || codebook_size <= 0 || (input_dim % 4) != 0 || (codebook_size % 4) != 0) {
+    if (n_codebooks <= 0 || input_dim <= 0 || codebook_size <= 0 || (input_dim % 4) != 0 || (codebook_size % 8) != 0) {
         set_error("vrvq_pack_weights: bad sizes Nq=%d D=%d K=%d (D and K must be positive multiples of 4)", n_codebooks, input_dim,
                   codebook_size);
         return VRVQ_EINVAL;
@@ -132,7 +132,11 @@ int vrvq_pack_weights(int n_codebooks, int input_dim, int codebook_size, int cod
             for (int c = 0; c < CD; ++c) p0[d * CD + c] = wi[(size_t)c * D + d];
         memcpy(p0 + (size_t)D * CD, b_in + (size_t)s * CD, sizeof(float) * CD);
         const float *cb = codebook + (size_t)s * K * CD;
-        for (int j = 0; j < K; ++j) normalize_row(cb + (size_t)j * CD, p1 + (size_t)j * CD, p1 + (size_t)K * CD + j);
+        for (int j = 0; j < K; ++j) {  // P1 is pair-interleaved: element k of code j lives at [(j/2)*16 + 2k + (j&1)]
+            float e[CD];
+            normalize_row(cb + (size_t)j * CD, e, p1 + (size_t)K * CD + j);
+            for (int k = 0; k < CD; ++k) p1[(size_t)(j >> 1) * 2 * CD + 2 * k + (j & 1)] = e[k];
+        }
         memcpy(p2, w_out + (size_t)s * D * CD, sizeof(float) * (size_t)D * CD);
         memcpy(p2 + (size_t)D * CD, b_out + (size_t)s * D, sizeof(float) * D);
         memcpy(raw, cb, sizeof(float) * (size_t)K * CD);
@@ -154,7 +158,9 @@ int vrvq_blob_codebook(const void *blob_host, size_t blob_bytes, int stage, floa
     }
     const BlobLayout L(h.input_dim, h.codebook_size);
     const float *p1 = static_cast<const float *>(blob_host) + BLOB_HDR_FLOATS + (size_t)stage * L.stage_floats() + L.off_p1();
-    if (cb_norm_out) memcpy(cb_norm_out, p1, sizeof(float) * (size_t)h.codebook_size * CD);
+    if (cb_norm_out)
+        for (int j = 0; j < h.codebook_size; ++j)
+            for (int k = 0; k < CD; ++k) cb_norm_out[(size_t)j * CD + k] = p1[(size_t)(j >> 1) * 2 * CD + 2 * k + (j & 1)];
     if (c2_out) memcpy(c2_out, p1 + (size_t)h.codebook_size * CD, sizeof(float) * h.codebook_size);
     return VRVQ_OK;
 }

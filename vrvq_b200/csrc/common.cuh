@@ -15,7 +15,7 @@ constexpr int BLOB_HDR_FLOATS = 16;
 // header (16 x 4 B): magic, version, Nq, D, K, stage_stride_floats, 0...
 // per stage, four 16-byte aligned sections (float counts):
 //   P0 in_proj : win_t[D][8] (d-major, the 8 output channels contiguous), b_in[8]
-//   P1 search  : cbn[K][8] normalised codebook rows, c2[K]
+//   P1 search  : cbn[K/2][8][2] normalised codebook rows, interleaved by pairs of adjacent codes, c2[K]
 //   P2 out_proj: wout[D][8], bout[D]
 //   RAW        : cbraw[K][8] un-normalised codebook rows (gathered per frame)
 // P0/P1/P2 are the three pieces the encode kernel streams into shared memory with cp.async.bulk.
@@ -87,6 +87,35 @@ __device__ __forceinline__ void cp_async(void *dst_smem, const void *src_gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- tensor memory (TMEM) as per-thread scratch ----------------------------------------------------
+// The 256 KB of TMEM per SM are otherwise unused by this kernel (no tcgen05.mma); each thread parks its
+// z_q accumulators in its own TMEM lane (32x32b shape: thread i of warp w owns lane 32*(w%4)+i) and moves
+// them with tcgen05.ld / tcgen05.st (SASS: LDTM / STTM), which frees half of the register file.
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the allocating warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 
 // streaming (evict-first) global stores for write-once outputs
 __device__ __forceinline__ void st_cs(float *p, float v) { __stcs(p, v); }

@@ -196,22 +196,27 @@ __global__ void __launch_bounds__(256) search_latents_kernel(const float *__rest
     const float *c2 = cbn + (size_t)K * CD;
     float best = __int_as_float(0x7f800000);
     int bi = 0;
-    const int per = K / 8;
-    for (int j = w * per; j < (w + 1) * per; ++j) {
-        const float4 ca = __ldg(reinterpret_cast<const float4 *>(cbn + (size_t)j * CD));
-        const float4 cb = __ldg(reinterpret_cast<const float4 *>(cbn + (size_t)j * CD + 4));
-        float d = __fmul_rn(e2x[0], ca.x);
-        d = __fmaf_rn(e2x[1], ca.y, d);
-        d = __fmaf_rn(e2x[2], ca.z, d);
-        d = __fmaf_rn(e2x[3], ca.w, d);
-        d = __fmaf_rn(e2x[4], cb.x, d);
-        d = __fmaf_rn(e2x[5], cb.y, d);
-        d = __fmaf_rn(e2x[6], cb.z, d);
-        d = __fmaf_rn(e2x[7], cb.w, d);
-        const float dist = __fadd_rn(__fsub_rn(e2, d), __ldg(c2 + j));
-        if (dist < best) {
-            best = dist;
+    const int per = K / 8;  // codes per warp (even); the blob stores code pairs interleaved: [(j/2)][k][2]
+    for (int j = w * per; j < (w + 1) * per; j += 2) {
+        const float4 *cp = reinterpret_cast<const float4 *>(cbn + (size_t)(j >> 1) * 2 * CD);
+        const float4 c01 = __ldg(cp), c23 = __ldg(cp + 1), c45 = __ldg(cp + 2), c67 = __ldg(cp + 3);
+        float d0 = __fmul_rn(e2x[0], c01.x), d1 = __fmul_rn(e2x[0], c01.y);
+        d0 = __fmaf_rn(e2x[1], c01.z, d0); d1 = __fmaf_rn(e2x[1], c01.w, d1);
+        d0 = __fmaf_rn(e2x[2], c23.x, d0); d1 = __fmaf_rn(e2x[2], c23.y, d1);
+        d0 = __fmaf_rn(e2x[3], c23.z, d0); d1 = __fmaf_rn(e2x[3], c23.w, d1);
+        d0 = __fmaf_rn(e2x[4], c45.x, d0); d1 = __fmaf_rn(e2x[4], c45.y, d1);
+        d0 = __fmaf_rn(e2x[5], c45.z, d0); d1 = __fmaf_rn(e2x[5], c45.w, d1);
+        d0 = __fmaf_rn(e2x[6], c67.x, d0); d1 = __fmaf_rn(e2x[6], c67.y, d1);
+        d0 = __fmaf_rn(e2x[7], c67.z, d0); d1 = __fmaf_rn(e2x[7], c67.w, d1);
+        const float dist0 = __fadd_rn(__fsub_rn(e2, d0), __ldg(c2 + j));
+        const float dist1 = __fadd_rn(__fsub_rn(e2, d1), __ldg(c2 + j + 1));
+        if (dist0 < best) {
+            best = dist0;
             bi = j;
+        }
+        if (dist1 < best) {
+            best = dist1;
+            bi = j + 1;
         }
     }
     sb[w][lane] = best;
@@ -280,8 +285,8 @@ int launch_remask(const float *zis, long long s_b, long long s_q, long long s_d,
 int launch_search_latents(const float *blob, int D, int K, const float *lat, long long l_sb, long long l_sc, int B, int T, int n_run,
                           long long *codes, long long c_sb, long long c_sq, cudaStream_t st) {
     if ((long long)B * T == 0 || n_run == 0) return VRVQ_OK;
-    if (K % 8 != 0 || n_run > 65535) {
-        set_error("vrvq_search_latents_f32: codebook_size must be a multiple of 8");
+    if (K % 16 != 0 || n_run > 65535) {
+        set_error("vrvq_search_latents_f32: codebook_size must be a multiple of 16");
         return VRVQ_EUNSUPPORTED;
     }
     const BlobLayout L(D, K);

@@ -2,7 +2,9 @@
 //
 // One persistent CTA per SM walks tiles of TF=32 consecutive latent frames of one batch item.
 // Per tile the [D x 32] residual lives in shared memory for all stages, the z_q accumulators live
-// in registers, and the per-stage weights (in_proj / codebook / out_proj pieces, ~36 KB each) are
+// in tensor memory (each thread parks its 2 x D/32 partial sums in its own TMEM lane and streams them
+// through tcgen05.ld/st once per stage, which keeps the register file free for pipelined operands),
+// and the per-stage weights (in_proj / codebook / out_proj pieces, ~36 KB each) are
 // streamed L2 -> shared memory through a two-slot ring filled by cp.async.bulk (TMA unit) and
 // tracked with mbarriers, one piece ahead of the math.  The latent is read from HBM exactly once;
 // codes, latents, mask, z_q and (optionally) z_q_is are written exactly once.
@@ -17,8 +19,15 @@
 // The hard importance mask (models/utils.py:55-61), the masked loss sums (quantize.py:422-423) and
 // the per-stage kept-frame counts (numerator of models/utils.py:64-73) are produced in the same pass.
 //
-// Arithmetic that must be reproduced bit-for-bit uses explicit __f*_rn intrinsics; the file is
-// compiled with --fmad=false so nothing else is contracted behind our back.
+// Arithmetic that must be reproduced bit-for-bit uses explicit __f*_rn intrinsics (packed
+// fma.rn.f32x2 where two independent IEEE FMAs share an instruction); the file is compiled with
+// --fmad=false so nothing else is contracted behind our back.
+//
+// Shared-memory cost model used for the thread mappings (measured with ncu on B200, profiles/r1a_*):
+// an LDS.128 whose lanes read distinct 16-byte chunks costs 4 wavefronts (512 B), identical quarter-warps
+// are NOT merged; a broadcast LDS.128 costs one wavefront per distinct address; an LDS.64 with 4 distinct
+// 8-byte addresses costs 1.  So every quarter-warp reads a different residual row, and broadcast operands
+// are fetched with as few distinct addresses per instruction as the tiling allows.
 #include "common.cuh"
 
 namespace vrvq {
@@ -68,11 +77,11 @@ struct EncodeSmem {
     static constexpr int OFF_PART = OFF_WB1 + WB_FLOATS;
     static constexpr int OFF_ZE = OFF_PART + PART_FLOATS;
     static constexpr int OFF_ES = OFF_ZE + CD * TF;
-    static constexpr int OFF_QS = OFF_ES + CD * TF;
-    static constexpr int OFF_E2 = OFF_QS + CD * TF;
+    static constexpr int OFF_E2 = OFF_ES + CD * TF;
     static constexpr int OFF_NKEEP = OFF_E2 + TF;
     static constexpr int OFF_BARS = OFF_NKEEP + TF;  // 2 x uint64
-    static constexpr int TOTAL_FLOATS = OFF_BARS + 4;
+    static constexpr int OFF_TMEM = OFF_BARS + 4;    // TMEM base address written by tcgen05.alloc
+    static constexpr int TOTAL_FLOATS = OFF_TMEM + 4;
     static constexpr int BYTES = TOTAL_FLOATS * 4;
     static_assert(OFF_BARS % 2 == 0, "mbarriers need 8-byte alignment");
     static_assert(OFF_WB0 % 4 == 0 && OFF_WB1 % 4 == 0, "bulk copy destinations need 16-byte alignment");
@@ -83,6 +92,7 @@ struct EncodeSmem {
 template <int D, int VEC>
 __device__ __forceinline__ void load_tile(float *R, const float *zb, long long z_sd, int fv, int tid) {
     constexpr int CPR = TF / VEC;  // chunks per row
+#pragma unroll 4
     for (int c = tid; c < D * CPR; c += NT) {
         const int d = c / CPR, q = c % CPR;
         float *dst = R + d * TF + q * VEC;
@@ -95,13 +105,89 @@ __device__ __forceinline__ void load_tile(float *R, const float *zb, long long z
     }
 }
 
-template <int D, int K>
+__device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
+
+// out_proj + residual update + masked accumulate for one thread: channels dbase + 2i (i < NI), frames f0, f0+1.
+// FIRST / LAST and the store shapes are compile-time, so the unrolled body has no branches and the scheduler can
+// overlap the shared-memory loads of the next channels with the FMA chains of the current ones.
+// The z_q accumulators stream through TMEM in groups of 8 (4 channels x 2 frames): load (unless FIRST), fma with the
+// 0/1 mask, store back (unless LAST, where the finished sums go straight to global memory).
+template <int NI, bool FIRST, bool LAST, bool ZQIS, int VEC_ST>
+__device__ __forceinline__ void out_proj_thread(const float *__restrict__ wp, const float *__restrict__ bp, float *__restrict__ rp,
+                                                const float (&q0)[CD], const float (&q1)[CD], float m0, float m1, uint32_t tacc,
+                                                float *zo, long long zstep, float *zq, long long zqstep, bool v0ok, bool v1ok) {
+    static_assert(NI % 4 == 0, "channels per thread must be a multiple of 4");
+#pragma unroll
+    for (int g = 0; g < NI / 4; ++g) {
+        uint32_t a8[8];
+        if (!FIRST) tmem_ld8(tacc + 8 * g, a8);
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = 4 * g + u;
+            const float4 wa = *reinterpret_cast<const float4 *>(wp + i * 2 * CD);
+            const float4 wb = *reinterpret_cast<const float4 *>(wp + i * 2 * CD + 4);
+            float v0 = bp[2 * i], v1 = v0;
+            v0 = __fmaf_rn(wa.x, q0[0], v0); v1 = __fmaf_rn(wa.x, q1[0], v1);
+            v0 = __fmaf_rn(wa.y, q0[1], v0); v1 = __fmaf_rn(wa.y, q1[1], v1);
+            v0 = __fmaf_rn(wa.z, q0[2], v0); v1 = __fmaf_rn(wa.z, q1[2], v1);
+            v0 = __fmaf_rn(wa.w, q0[3], v0); v1 = __fmaf_rn(wa.w, q1[3], v1);
+            v0 = __fmaf_rn(wb.x, q0[4], v0); v1 = __fmaf_rn(wb.x, q1[4], v1);
+            v0 = __fmaf_rn(wb.y, q0[5], v0); v1 = __fmaf_rn(wb.y, q1[5], v1);
+            v0 = __fmaf_rn(wb.z, q0[6], v0); v1 = __fmaf_rn(wb.z, q1[6], v1);
+            v0 = __fmaf_rn(wb.w, q0[7], v0); v1 = __fmaf_rn(wb.w, q1[7], v1);
+            if (!LAST) {
+                float2 *rr = reinterpret_cast<float2 *>(rp + i * 2 * TF);
+                float2 r = *rr;
+                r.x = __fsub_rn(r.x, v0);
+                r.y = __fsub_rn(r.y, v1);
+                *rr = r;
+            }
+            if (ZQIS) {
+                if (VEC_ST == 2) {
+                    if (v0ok) st_cs2(zo, v0, v1);  // fv is even whenever VEC_ST == 2
+                } else {
+                    if (v0ok) st_cs(zo, v0);
+                    if (v1ok) st_cs(zo + 1, v1);
+                }
+                zo += zstep;
+            }
+            v[2 * u] = v0;
+            v[2 * u + 1] = v1;
+        }
+        if (!FIRST) tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // z_q += mask * z_q_i  (quantize.py:194 / :421), ascending stage order from 0
+            const float a0 = FIRST ? 0.0f : __uint_as_float(a8[2 * u]);
+            const float a1 = FIRST ? 0.0f : __uint_as_float(a8[2 * u + 1]);
+            a8[2 * u] = __float_as_uint(__fmaf_rn(m0, v[2 * u], a0));
+            a8[2 * u + 1] = __float_as_uint(__fmaf_rn(m1, v[2 * u + 1], a1));
+        }
+        if (!LAST) {
+            tmem_st8(tacc + 8 * g, a8);
+        } else if (zq != nullptr) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (VEC_ST == 2) {
+                    if (v0ok) st_cs2(zq, __uint_as_float(a8[2 * u]), __uint_as_float(a8[2 * u + 1]));
+                } else {
+                    if (v0ok) st_cs(zq, __uint_as_float(a8[2 * u]));
+                    if (v1ok) st_cs(zq + 1, __uint_as_float(a8[2 * u + 1]));
+                }
+                zq += zqstep;
+            }
+        }
+    }
+    if (!LAST) tmem_wait_st();
+}
+
+template <int D, int K, int VEC_ST, bool ZQIS>
 __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p) {
     using S = EncodeSmem<D, K>;
     constexpr BlobLayout L = BlobLayout(D, K);
     constexpr int DW = D / NW;  // channels per warp
-    static_assert(D % (NW * 2) == 0, "D must be a multiple of 32");
-    static_assert(K % 32 == 0, "codebook size must be a multiple of 32");
+    static_assert(D % (NW * 4) == 0, "D must be a multiple of 64");
+    static_assert(K % 64 == 0, "codebook size must be a multiple of 64");
 
     extern __shared__ __align__(128) float smem[];
     float *R = smem + S::OFF_R;
@@ -112,10 +198,12 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
     int *sidx = reinterpret_cast<int *>(part + NW * TF);
     float *ze = smem + S::OFF_ZE;  // [CD][TF] pre-normalisation latents
     float *es = smem + S::OFF_ES;  // [CD][TF] 2*e
-    float *qs = smem + S::OFF_QS;  // [CD][TF] straight-through values
     float *e2s = smem + S::OFF_E2;
     int *nkeep = reinterpret_cast<int *>(smem + S::OFF_NKEEP);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::OFF_BARS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::OFF_TMEM);
+    constexpr uint32_t TMEM_COLS = (NW / 4) * DW;  // accumulator columns: DW per thread, 4 lane quadrants
+    static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two in [32, 512]");
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int n_run = p.n_run;
@@ -158,7 +246,16 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
         mbar_init(&bars[1], 1);
         fence_mbar_init();
     }
+    if (w == 0) {  // one warp owns the TMEM allocation for the CTA's lifetime
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tmem_fence_before_sync();
     __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    // this thread's accumulator strip: its own lane of quadrant w%4, DW columns starting at (w/4)*DW
+    const uint32_t tacc = tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)((w >> 2) * DW);
     if (tid == 0) issue_piece(0);
 
     auto tile_coords = [&](int it, int &b, int &t0, int &fv) {
@@ -181,21 +278,17 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
     };
     start_tile_load(0);
 
-    // thread coordinates of the three phase mappings
-    const int l4 = lane & 7, g4 = lane >> 3;    // in_proj : 4 frames x channel pair g4
-    const int l2 = lane & 15, g2 = lane >> 4;   // search / out_proj : 2 frames x (codes | channels) g2
+    // thread coordinates of the phase mappings
+    const int l4 = lane & 7, g4 = lane >> 3;   // in_proj : frames 4*l4..+3, quarter-warp g4 = K sub-slice
+    const int l2 = lane & 15, g2 = lane >> 4;  // search / out_proj : frames 2*l2, 2*l2+1; half-warp g2
     const int f0 = 2 * l2;
 
-    float acc[DW / 2][2];  // z_q accumulators: channels w*DW + 2i + g2, frames f0, f0+1
-    double loss_acc = 0.0; // lane 0 of warp 0
+    double loss_acc = 0.0;               // lane 0 of warp 0
     unsigned long long kept_acc = 0ull;  // lane k of warp 0 counts stage k
 
     for (int it = 0; it < n_my_tiles; ++it) {
         int b, t0, fv;
         tile_coords(it, b, t0, fv);
-
-#pragma unroll
-        for (int i = 0; i < DW / 2; ++i) acc[i][0] = acc[i][1] = 0.0f;
 
         // ---- per-frame keep counts: mask[k] = (imp*level*Nq - k >= 0)   (quantize.py:389, utils.py:59-60)
         if (w == 0) {
@@ -224,26 +317,53 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
         for (int s = 0; s < n_run; ++s) {
             const bool last = (s == n_run - 1);
             // ================= in_proj: z_e[c][f] = sum_d W_in[c][d] r[d][f] =================
+            // Thread tile 8 channels x 4 frames; the four quarter-warps take four consecutive residual rows per step
+            // (so one LDS.128 delivers 512 useful bytes), i.e. K is split 4 ways inside the warp and NW ways across warps.
             {
                 const float *W = acquire();
-                float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
-                const float *Wp = W + (w * DW) * CD + 2 * g4;
-                const float *Rp = R + (w * DW) * TF + 4 * l4;
-#pragma unroll 8
-                for (int i = 0; i < DW; ++i) {
-                    const float2 wv = *reinterpret_cast<const float2 *>(Wp + i * CD);
-                    const float4 rv = *reinterpret_cast<const float4 *>(Rp + i * TF);
-                    a0[0] = fmaf(wv.x, rv.x, a0[0]);
-                    a0[1] = fmaf(wv.x, rv.y, a0[1]);
-                    a0[2] = fmaf(wv.x, rv.z, a0[2]);
-                    a0[3] = fmaf(wv.x, rv.w, a0[3]);
-                    a1[0] = fmaf(wv.y, rv.x, a1[0]);
-                    a1[1] = fmaf(wv.y, rv.y, a1[1]);
-                    a1[2] = fmaf(wv.y, rv.z, a1[2]);
-                    a1[3] = fmaf(wv.y, rv.w, a1[3]);
+                float a[CD][4];
+#pragma unroll
+                for (int c = 0; c < CD; ++c) a[c][0] = a[c][1] = a[c][2] = a[c][3] = 0.0f;
+                const float *Wp = W + (w * DW + g4) * CD;
+                const float *Rp = R + (w * DW + g4) * TF + 4 * l4;
+#pragma unroll 4
+                for (int i = 0; i < DW / 4; ++i) {
+                    const float4 rv = *reinterpret_cast<const float4 *>(Rp + i * 4 * TF);
+                    const float4 wa = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD);
+                    const float4 wb = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD + 4);
+                    const float wv[CD] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int c = 0; c < CD; ++c) {
+                        a[c][0] = fmaf(wv[c], rv.x, a[c][0]);
+                        a[c][1] = fmaf(wv[c], rv.y, a[c][1]);
+                        a[c][2] = fmaf(wv[c], rv.z, a[c][2]);
+                        a[c][3] = fmaf(wv[c], rv.w, a[c][3]);
+                    }
                 }
-                *reinterpret_cast<float4 *>(&part[(w * CD + 2 * g4) * TF + 4 * l4]) = make_float4(a0[0], a0[1], a0[2], a0[3]);
-                *reinterpret_cast<float4 *>(&part[(w * CD + 2 * g4 + 1) * TF + 4 * l4]) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+                // reduce-scatter over the four K sub-slices: after lane^16 a thread keeps 4 channels, after lane^8 two.
+                float h[4][4];
+                const bool up16 = (g4 & 2) != 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        const float keep = up16 ? a[c + 4][f] : a[c][f];
+                        const float send = up16 ? a[c][f] : a[c + 4][f];
+                        h[c][f] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                    }
+                float q2[2][4];
+                const bool up8 = (g4 & 1) != 0;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        const float keep = up8 ? h[c + 2][f] : h[c][f];
+                        const float send = up8 ? h[c][f] : h[c + 2][f];
+                        q2[c][f] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                    }
+                const int c0 = 4 * (g4 >> 1) + 2 * (g4 & 1);
+                *reinterpret_cast<float4 *>(&part[(w * CD + c0) * TF + 4 * l4]) = make_float4(q2[0][0], q2[0][1], q2[0][2], q2[0][3]);
+                *reinterpret_cast<float4 *>(&part[(w * CD + c0 + 1) * TF + 4 * l4]) = make_float4(q2[1][0], q2[1][1], q2[1][2], q2[1][3]);
                 __syncthreads();
                 // the residual is dead after the last stage's in_proj: start fetching the next tile
                 if (last && it + 1 < n_my_tiles) start_tile_load(it + 1);
@@ -285,52 +405,47 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                 __syncthreads();
             }
             // ================= search over the normalised codebook =================
+            // Lane = frame; warp w scans code pairs [w*K/32, (w+1)*K/32) in ascending order with warp-uniform
+            // (broadcast) codebook reads.  The codebook piece is pair-interleaved ([pair][k][2]) so that one
+            // fma.rn.f32x2 advances the dot products of two adjacent codes.
             {
                 const float *CB = acquire();
                 const float *c2 = CB + K * CD;
-                float ex0[CD], ex1[CD];
+                float2 ea[CD];  // (2e_k, 2e_k) of frame `lane`
 #pragma unroll
-                for (int k = 0; k < CD; ++k) {
-                    const float2 t = *reinterpret_cast<const float2 *>(&es[k * TF + f0]);
-                    ex0[k] = t.x;
-                    ex1[k] = t.y;
-                }
-                const float2 e2v = *reinterpret_cast<const float2 *>(&e2s[f0]);
-                float best0 = __int_as_float(0x7f800000), best1 = best0;
-                int bi0 = 0, bi1 = 0;
+                for (int k = 0; k < CD; ++k) ea[k] = dup2(es[k * TF + lane]);
+                const float2 e2a = dup2(e2s[lane]);
+                float best = __int_as_float(0x7f800000);
+                int bi = 0;
+                constexpr int PPW = K / 2 / NW;  // code pairs per warp
+                const float4 *cp = reinterpret_cast<const float4 *>(CB + (w * PPW) * 2 * CD);
+                const float2 *ccp = reinterpret_cast<const float2 *>(c2 + 2 * w * PPW);
 #pragma unroll 4
-                for (int i = 0; i < K / 32; ++i) {
-                    const int j = 32 * i + 2 * w + g2;  // ascending per thread: strict '<' keeps the first minimum
-                    const float4 ca = *reinterpret_cast<const float4 *>(CB + j * CD);
-                    const float4 cb = *reinterpret_cast<const float4 *>(CB + j * CD + 4);
-                    const float cc = c2[j];
-                    float d0 = __fmul_rn(ex0[0], ca.x), d1 = __fmul_rn(ex1[0], ca.x);
-                    d0 = __fmaf_rn(ex0[1], ca.y, d0); d1 = __fmaf_rn(ex1[1], ca.y, d1);
-                    d0 = __fmaf_rn(ex0[2], ca.z, d0); d1 = __fmaf_rn(ex1[2], ca.z, d1);
-                    d0 = __fmaf_rn(ex0[3], ca.w, d0); d1 = __fmaf_rn(ex1[3], ca.w, d1);
-                    d0 = __fmaf_rn(ex0[4], cb.x, d0); d1 = __fmaf_rn(ex1[4], cb.x, d1);
-                    d0 = __fmaf_rn(ex0[5], cb.y, d0); d1 = __fmaf_rn(ex1[5], cb.y, d1);
-                    d0 = __fmaf_rn(ex0[6], cb.z, d0); d1 = __fmaf_rn(ex1[6], cb.z, d1);
-                    d0 = __fmaf_rn(ex0[7], cb.w, d0); d1 = __fmaf_rn(ex1[7], cb.w, d1);
-                    const float dist0 = __fadd_rn(__fsub_rn(e2v.x, d0), cc);
-                    const float dist1 = __fadd_rn(__fsub_rn(e2v.y, d1), cc);
-                    if (dist0 < best0) { best0 = dist0; bi0 = j; }
-                    if (dist1 < best1) { best1 = dist1; bi1 = j; }
+                for (int i = 0; i < PPW; ++i) {
+                    const float4 c01 = cp[4 * i], c23 = cp[4 * i + 1], c45 = cp[4 * i + 2], c67 = cp[4 * i + 3];
+                    const float2 cc = ccp[i];
+                    float2 da = __fmul2_rn(ea[0], make_float2(c01.x, c01.y));
+                    da = __ffma2_rn(ea[1], make_float2(c01.z, c01.w), da);
+                    da = __ffma2_rn(ea[2], make_float2(c23.x, c23.y), da);
+                    da = __ffma2_rn(ea[3], make_float2(c23.z, c23.w), da);
+                    da = __ffma2_rn(ea[4], make_float2(c45.x, c45.y), da);
+                    da = __ffma2_rn(ea[5], make_float2(c45.z, c45.w), da);
+                    da = __ffma2_rn(ea[6], make_float2(c67.x, c67.y), da);
+                    da = __ffma2_rn(ea[7], make_float2(c67.z, c67.w), da);
+                    // dist = fl(fl(e2 - dot) + c2)
+                    const float2 ta = __fadd2_rn(__fadd2_rn(e2a, make_float2(-da.x, -da.y)), cc);
+                    const int j = 2 * (w * PPW + i);
+                    if (ta.x < best) { best = ta.x; bi = j; }
+                    if (ta.y < best) { best = ta.y; bi = j + 1; }
                 }
-                {   // merge the two code groups of the warp (lane ^ 16)
-                    const float ob0 = __shfl_xor_sync(0xffffffffu, best0, 16), ob1 = __shfl_xor_sync(0xffffffffu, best1, 16);
-                    const int oi0 = __shfl_xor_sync(0xffffffffu, bi0, 16), oi1 = __shfl_xor_sync(0xffffffffu, bi1, 16);
-                    if (ob0 < best0 || (ob0 == best0 && oi0 < bi0)) { best0 = ob0; bi0 = oi0; }
-                    if (ob1 < best1 || (ob1 == best1 && oi1 < bi1)) { best1 = ob1; bi1 = oi1; }
-                }
-                if (g2 == 0) {
-                    *reinterpret_cast<float2 *>(&sbest[w * TF + f0]) = make_float2(best0, best1);
-                    *reinterpret_cast<int2 *>(&sidx[w * TF + f0]) = make_int2(bi0, bi1);
-                }
+                sbest[w * TF + lane] = best;
+                sidx[w * TF + lane] = bi;
                 __syncthreads();
             }
-            // ================= argmin merge, gather, loss, straight-through (one warp) =================
-            if (w == 0) {
+            // ===== argmin merge, gather, loss, straight-through: every warp redundantly, lane = frame (no extra barrier) =====
+            float qv[CD];
+            const float *WO;
+            {
                 float best = sbest[lane];
                 int bi = sidx[lane];
 #pragma unroll
@@ -342,6 +457,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                 const float *raw = stages + (size_t)s * L.stage_floats() + L.off_raw() + (size_t)bi * CD;
                 const float4 ra = __ldg(reinterpret_cast<const float4 *>(raw));
                 const float4 rb = __ldg(reinterpret_cast<const float4 *>(raw + 4));
+                WO = acquire();  // out_proj weights: the mbarrier wait overlaps the L2 gather latency
                 const float cr[CD] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                 float ls = 0.0f;
 #pragma unroll
@@ -350,111 +466,89 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                     const float diff = __fsub_rn(x, cr[k]);  // quantize.py:69-71
                     const float sq = __fmul_rn(diff, diff);
                     ls = (k == 0) ? sq : __fadd_rn(ls, sq);
-                    qs[k * TF + lane] = __fadd_rn(x, __fsub_rn(cr[k], x));  // quantize.py:73-75
+                    qv[k] = __fadd_rn(x, __fsub_rn(cr[k], x));  // quantize.py:73-75
                 }
-                const float loss = __fdiv_rn(ls, (float)CD);
-                const bool valid = lane < fv;
-                if (valid) {
-                    p.codes[(long long)b * p.codes_sb + (long long)s * p.codes_sq + t0 + lane] = (long long)bi;
-                    if (p.loss_pf != nullptr)
-                        p.loss_pf[(long long)b * p.loss_sb + (long long)s * p.loss_sq + t0 + lane] = loss;
-                }
-                double ml = (valid && nkeep[lane] > s) ? (double)loss : 0.0;
+                if (w == 0) {
+                    const float loss = __fdiv_rn(ls, (float)CD);
+                    const bool valid = lane < fv;
+                    if (valid) {
+                        p.codes[(long long)b * p.codes_sb + (long long)s * p.codes_sq + t0 + lane] = (long long)bi;
+                        if (p.loss_pf != nullptr)
+                            p.loss_pf[(long long)b * p.loss_sb + (long long)s * p.loss_sq + t0 + lane] = loss;
+                    }
+                    double ml = (valid && nkeep[lane] > s) ? (double)loss : 0.0;
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) ml += __shfl_xor_sync(0xffffffffu, ml, off);
-                loss_acc += ml;
+                    for (int off = 16; off > 0; off >>= 1) ml += __shfl_xor_sync(0xffffffffu, ml, off);
+                    loss_acc += ml;
+                }
             }
-            __syncthreads();
             // ================= out_proj + residual update + masked accumulate =================
             {
-                const float *WO = acquire();
                 const float *bo = WO + D * CD;
                 float q0[CD], q1[CD];
 #pragma unroll
                 for (int k = 0; k < CD; ++k) {
-                    const float2 t = *reinterpret_cast<const float2 *>(&qs[k * TF + f0]);
-                    q0[k] = t.x;
-                    q1[k] = t.y;
+                    q0[k] = __shfl_sync(0xffffffffu, qv[k], f0);
+                    q1[k] = __shfl_sync(0xffffffffu, qv[k], f0 + 1);
                 }
                 const int2 nk = *reinterpret_cast<const int2 *>(&nkeep[f0]);
                 const float m0 = nk.x > s ? 1.0f : 0.0f, m1 = nk.y > s ? 1.0f : 0.0f;
                 const bool v0ok = f0 < fv, v1ok = f0 + 1 < fv;
                 const int dbase = w * DW + g2;
-                float *zis = nullptr;
-                if (p.z_q_is != nullptr)
-                    zis = p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + (long long)dbase * p.zqis_sd + t0 + f0;
-#pragma unroll
-                for (int i = 0; i < DW / 2; ++i) {
-                    const int d = dbase + 2 * i;
-                    const float4 wa = *reinterpret_cast<const float4 *>(WO + d * CD);
-                    const float4 wb = *reinterpret_cast<const float4 *>(WO + d * CD + 4);
-                    float v0 = bo[d], v1 = v0;
-                    v0 = __fmaf_rn(wa.x, q0[0], v0); v1 = __fmaf_rn(wa.x, q1[0], v1);
-                    v0 = __fmaf_rn(wa.y, q0[1], v0); v1 = __fmaf_rn(wa.y, q1[1], v1);
-                    v0 = __fmaf_rn(wa.z, q0[2], v0); v1 = __fmaf_rn(wa.z, q1[2], v1);
-                    v0 = __fmaf_rn(wa.w, q0[3], v0); v1 = __fmaf_rn(wa.w, q1[3], v1);
-                    v0 = __fmaf_rn(wb.x, q0[4], v0); v1 = __fmaf_rn(wb.x, q1[4], v1);
-                    v0 = __fmaf_rn(wb.y, q0[5], v0); v1 = __fmaf_rn(wb.y, q1[5], v1);
-                    v0 = __fmaf_rn(wb.z, q0[6], v0); v1 = __fmaf_rn(wb.z, q1[6], v1);
-                    v0 = __fmaf_rn(wb.w, q0[7], v0); v1 = __fmaf_rn(wb.w, q1[7], v1);
-                    if (!last) {
-                        float2 *rp = reinterpret_cast<float2 *>(&R[d * TF + f0]);
-                        float2 r = *rp;
-                        r.x = __fsub_rn(r.x, v0);
-                        r.y = __fsub_rn(r.y, v1);
-                        *rp = r;
-                    }
-                    acc[i][0] = __fmaf_rn(m0, v0, acc[i][0]);
-                    acc[i][1] = __fmaf_rn(m1, v1, acc[i][1]);
-                    if (zis != nullptr) {
-                        float *o = zis + (long long)(2 * i) * p.zqis_sd;
-                        if (p.vec_st == 2) {
-                            if (v0ok) st_cs2(o, v0, v1);  // fv is even whenever vec_st == 2
-                        } else {
-                            if (v0ok) st_cs(o, v0);
-                            if (v1ok) st_cs(o + 1, v1);
-                        }
-                    }
-                }
-                __syncthreads();  // residual updated; qs and the weight slot are free again
+                float *zo = nullptr;
+                if (ZQIS) zo = p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + (long long)dbase * p.zqis_sd + t0 + f0;
+                const long long zstep = 2 * p.zqis_sd;
+                const float *wp = WO + dbase * CD;
+                const float *bp = bo + dbase;
+                float *rp = R + dbase * TF + f0;
+                float *zq = nullptr;
+                if (p.z_q != nullptr) zq = p.z_q + (long long)b * p.zq_sb + (long long)dbase * p.zq_sd + t0 + f0;
+                const long long zqstep = 2 * p.zq_sd;
+                const bool first = (s == 0);
+                if (first && last)
+                    out_proj_thread<DW / 2, true, true, ZQIS, VEC_ST>(wp, bp, rp, q0, q1, m0, m1, tacc, zo, zstep, zq, zqstep, v0ok, v1ok);
+                else if (first)
+                    out_proj_thread<DW / 2, true, false, ZQIS, VEC_ST>(wp, bp, rp, q0, q1, m0, m1, tacc, zo, zstep, zq, zqstep, v0ok, v1ok);
+                else if (last)
+                    out_proj_thread<DW / 2, false, true, ZQIS, VEC_ST>(wp, bp, rp, q0, q1, m0, m1, tacc, zo, zstep, zq, zqstep, v0ok, v1ok);
+                else
+                    out_proj_thread<DW / 2, false, false, ZQIS, VEC_ST>(wp, bp, rp, q0, q1, m0, m1, tacc, zo, zstep, zq, zqstep, v0ok, v1ok);
+                __syncthreads();  // residual updated; sbest/ze and the weight slot are free again
             }
         }  // stages
 
-        if (p.z_q != nullptr) {
-            const bool v0ok = f0 < fv, v1ok = f0 + 1 < fv;
-            float *zo = p.z_q + (long long)b * p.zq_sb + (long long)(w * DW + g2) * p.zq_sd + t0 + f0;
-#pragma unroll
-            for (int i = 0; i < DW / 2; ++i) {
-                float *o = zo + (long long)(2 * i) * p.zq_sd;
-                if (p.vec_st == 2) {
-                    if (v0ok) st_cs2(o, acc[i][0], acc[i][1]);
-                } else {
-                    if (v0ok) st_cs(o, acc[i][0]);
-                    if (v1ok) st_cs(o + 1, acc[i][1]);
-                }
-            }
-        }
     }  // tiles
 
+    tmem_fence_before_sync();
+    __syncthreads();
     if (w == 0) {
+        tmem_fence_after_sync();
+        tmem_dealloc(tmem_base, TMEM_COLS);
         if (lane == 0 && p.loss_sum != nullptr) atomicAdd(p.loss_sum, loss_acc);
         if (lane < n_run && p.kept != nullptr && kept_acc != 0ull) atomicAdd(&p.kept[lane], kept_acc);
     }
 }
 
 // ---- host launcher ---------------------------------------------------------------------------
-template <int D, int K>
-static int launch_encode(const EncodeParams &p, int grid, cudaStream_t stream) {
+template <int D, int K, int VEC_ST, bool ZQIS>
+static int launch_one(const EncodeParams &p, int grid, cudaStream_t stream) {
     using S = EncodeSmem<D, K>;
     static bool attr_done = false;  // benign race: the attribute is idempotent
     if (!attr_done) {
-        int rc = check_cuda(cudaFuncSetAttribute(rvq_encode_kernel<D, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES),
+        int rc = check_cuda(cudaFuncSetAttribute(rvq_encode_kernel<D, K, VEC_ST, ZQIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES),
                             "cudaFuncSetAttribute(rvq_encode_kernel)");
         if (rc) return rc;
         attr_done = true;
     }
-    rvq_encode_kernel<D, K><<<grid, NT, S::BYTES, stream>>>(p);
+    rvq_encode_kernel<D, K, VEC_ST, ZQIS><<<grid, NT, S::BYTES, stream>>>(p);
     return check_cuda(cudaGetLastError(), "rvq_encode_kernel launch");
+}
+
+template <int D, int K>
+static int launch_encode(const EncodeParams &p, int grid, cudaStream_t stream) {
+    const bool zqis = p.z_q_is != nullptr;
+    if (p.vec_st == 2) return zqis ? launch_one<D, K, 2, true>(p, grid, stream) : launch_one<D, K, 2, false>(p, grid, stream);
+    return zqis ? launch_one<D, K, 1, true>(p, grid, stream) : launch_one<D, K, 1, false>(p, grid, stream);
 }
 
 template <int D, int K>
