@@ -8,7 +8,7 @@ from tests.golden import gen_inputs as gi
 zqis = "--no-zqis" not in sys.argv
 sd = gi.torch_state_dict(gi.make_state_dict(0, 8, 1024))
 pw = ops.PackedWeights.from_state_dict(sd, "cuda")
-B, T = 16, 862
+B, T = 16, int(os.environ.get("PROF_T", "862"))
 zs = [torch.randn(B, 1024, T, device="cuda") for _ in range(2)]
 imp = torch.rand(B, 1, T, device="cuda")
 out = ops.EncodeOutputs(B, 1024, T, 8, "cuda", z_q=True, z_q_is=zqis, latents=True, mask=True)

@@ -27,6 +27,10 @@ def run(B, T, Nq, zqis, iters=20):
     print(f"B={B} T={T} Nq={Nq} zqis={zqis}: median {med*1e3:.1f} us  min {ts[0]*1e3:.1f} us  {frames/med/1e3:.2f} Mframes/s  {frames*bpf/med/1e6:.1f} GB/s algorithmic", flush=True)
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        B, T, Nq, zq = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4] == "1"
+        run(B, T, Nq, zq)
+        sys.exit(0)
     run(16, 862, 8, True)
     run(16, 862, 8, False)
     run(64, 862, 28, False)

@@ -1,13 +1,15 @@
 // Fused residual-vector-quantisation encode for B200 (sm_100a).
 //
 // One persistent CTA per SM walks tiles of TF=32 consecutive latent frames of one batch item.
-// Per tile the [D x 32] residual lives in shared memory for all stages, the z_q accumulators live
-// in tensor memory (each thread parks its 2 x D/32 partial sums in its own TMEM lane and streams them
-// through tcgen05.ld/st once per stage, which keeps the register file free for pipelined operands),
-// and the per-stage weights (in_proj / codebook / out_proj pieces, ~36 KB each) are
-// streamed L2 -> shared memory through a two-slot ring filled by cp.async.bulk (TMA unit) and
-// tracked with mbarriers, one piece ahead of the math.  The latent is read from HBM exactly once;
-// codes, latents, mask, z_q and (optionally) z_q_is are written exactly once.
+// Thread (warp w, quarter-warp g4, l4) owns the 4 frames 4*l4..4*l4+3 of the D/64 channels
+// d = w*D/16 + 4i + g4 for the whole tile.  Its slice of the residual and of the z_q accumulators is
+// thread-private, so both live in TENSOR MEMORY: 2 x D/16 columns of the thread's own TMEM lane, moved
+// with tcgen05.ld / tcgen05.st (~800 B/clk/SM measured) instead of through shared memory (64 B/clk for
+// lane-distinct LDS.128, profiles/r1_micro_tmem_lds.txt) or the register file (which stays free for
+// pipelined operands).  Shared memory holds only: the staging buffer the next tile's latent is
+// prefetched into (cp.async), the two-slot ring of per-stage weight pieces (cp.async.bulk + mbarrier,
+// one piece ahead of the math) and small per-stage exchange buffers.  The latent is read from HBM
+// exactly once; codes, latents, mask, z_q and (optionally) z_q_is are written exactly once.
 //
 // Stage i, per frame (reference: models/quantize.py:42-103, loop :182-202 / :353-365):
 //   in_proj   z_e = W_in r + b_in                      (quantize.py:66)     CUDA cores, fp32 FMA
@@ -22,12 +24,8 @@
 // Arithmetic that must be reproduced bit-for-bit uses explicit __f*_rn intrinsics (packed
 // fma.rn.f32x2 where two independent IEEE FMAs share an instruction); the file is compiled with
 // --fmad=false so nothing else is contracted behind our back.
-//
-// Shared-memory cost model used for the thread mappings (measured with ncu on B200, profiles/r1a_*):
-// an LDS.128 whose lanes read distinct 16-byte chunks costs 4 wavefronts (512 B), identical quarter-warps
-// are NOT merged; a broadcast LDS.128 costs one wavefront per distinct address; an LDS.64 with 4 distinct
-// 8-byte addresses costs 1.  So every quarter-warp reads a different residual row, and broadcast operands
-// are fetched with as few distinct addresses per instruction as the tiling allows.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vrvq {
@@ -61,14 +59,14 @@ struct EncodeParams {
     unsigned long long *kept;
     int B, T, Nq, n_run, tiles_per_b, n_tiles;
     int vec_ld;  // 4 / 2 / 1 floats per global load of z
-    int vec_st;  // 2 / 1 floats per global store of z_q, z_q_is
+    int vec_st;  // 4 / 2 / 1 floats per global store of z_q, z_q_is
 };
 
 template <int D, int K>
 struct EncodeSmem {
     static constexpr BlobLayout L = BlobLayout(D, K);
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
-    static constexpr int R_FLOATS = D * TF;
+    static constexpr int R_FLOATS = D * TF;  // staging buffer for the next tile's latent
     static constexpr int WB_FLOATS = (cmax(cmax(L.p0_floats(), L.p1_floats()), L.p2_floats()) + 3) / 4 * 4;
     static constexpr int PART_FLOATS = NW * CD * TF;
     static constexpr int OFF_R = 0;
@@ -88,7 +86,7 @@ struct EncodeSmem {
     static_assert(BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 
-// global -> shared load of one [D x TF] latent tile; frames >= fv are zero-filled.
+// global -> shared prefetch of one [D x TF] latent tile; frames >= fv are zero-filled.
 template <int D, int VEC>
 __device__ __forceinline__ void load_tile(float *R, const float *zb, long long z_sd, int fv, int tid) {
     constexpr int CPR = TF / VEC;  // chunks per row
@@ -107,75 +105,124 @@ __device__ __forceinline__ void load_tile(float *R, const float *zb, long long z
 
 __device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
 
-// out_proj + residual update + masked accumulate for one thread: channels dbase + 2i (i < NI), frames f0, f0+1.
-// FIRST / LAST and the store shapes are compile-time, so the unrolled body has no branches and the scheduler can
-// overlap the shared-memory loads of the next channels with the FMA chains of the current ones.
-// The z_q accumulators stream through TMEM in groups of 8 (4 channels x 2 frames): load (unless FIRST), fma with the
-// 0/1 mask, store back (unless LAST, where the finished sums go straight to global memory).
-template <int NI, bool FIRST, bool LAST, bool ZQIS, int VEC_ST>
-__device__ __forceinline__ void out_proj_thread(const float *__restrict__ wp, const float *__restrict__ bp, float *__restrict__ rp,
-                                                const float (&q0)[CD], const float (&q1)[CD], float m0, float m1, uint32_t tacc,
-                                                float *zo, long long zstep, float *zq, long long zqstep, bool v0ok, bool v1ok) {
-    static_assert(NI % 4 == 0, "channels per thread must be a multiple of 4");
+// Which 4 of the tile's 32 frames a thread owns depends on the widest store every output row allows, so that each
+// warp-level store instruction writes contiguous bytes (full 32-byte sectors) whatever the row alignment is:
+//   V = 4 (rows 16-byte aligned): frames 4*l4 + j                   -> one STG.128, 8 lanes x 16 B contiguous
+//   V = 2 (rows  8-byte aligned): frames 2*l4 + (j&1) + 16*(j>>1)   -> two STG.64, each 8 lanes x 8 B contiguous
+//   V = 1 (rows  4-byte aligned): frames l4 + 8*j                   -> four STG.32, each 8 lanes x 4 B contiguous
+// (Measured on B200: with frames 4*l4+j and split stores, T=862 ran 25% slower than T=864; profiles/r1d_*.)
+template <int V>
+__device__ __forceinline__ int frame_of(int l4, int j) {
+    return V == 4 ? 4 * l4 + j : V == 2 ? 2 * l4 + (j & 1) + 16 * (j >> 1) : l4 + 8 * j;
+}
+
+// The thread's 4 frames of one 32-frame row in shared memory (row = pointer to frame 0).
+template <int V>
+__device__ __forceinline__ void row_load4(const float *row, int l4, float (&x)[4]) {
+    if (V == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(row + 4 * l4);
+        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else if (V == 2) {
+        const float2 a = *reinterpret_cast<const float2 *>(row + 2 * l4);
+        const float2 b = *reinterpret_cast<const float2 *>(row + 16 + 2 * l4);
+        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+    } else {
 #pragma unroll
-    for (int g = 0; g < NI / 4; ++g) {
-        uint32_t a8[8];
-        if (!FIRST) tmem_ld8(tacc + 8 * g, a8);
+        for (int j = 0; j < 4; ++j) x[j] = row[l4 + 8 * j];
+    }
+}
+template <int V>
+__device__ __forceinline__ void row_store4(float *row, int l4, float a, float b, float c, float d) {
+    if (V == 4) {
+        *reinterpret_cast<float4 *>(row + 4 * l4) = make_float4(a, b, c, d);
+    } else if (V == 2) {
+        *reinterpret_cast<float2 *>(row + 2 * l4) = make_float2(a, b);
+        *reinterpret_cast<float2 *>(row + 16 + 2 * l4) = make_float2(c, d);
+    } else {
+        row[l4] = a; row[l4 + 8] = b; row[l4 + 16] = c; row[l4 + 24] = d;
+    }
+}
+// The same 4 frames to global memory (write-once, streaming); o points at frame 0 of the row, fv = valid frames.
+template <int V>
+__device__ __forceinline__ void store4(float *o, int l4, float a, float b, float c, float d, int fv) {
+    if (V == 4) {
+        if (4 * l4 < fv) st_cs4(o + 4 * l4, make_float4(a, b, c, d));  // fv is a multiple of 4 whenever V == 4
+    } else if (V == 2) {
+        if (2 * l4 < fv) st_cs2(o + 2 * l4, a, b);  // fv is even whenever V == 2
+        if (16 + 2 * l4 < fv) st_cs2(o + 16 + 2 * l4, c, d);
+    } else {
+        if (l4 < fv) st_cs(o + l4, a);
+        if (l4 + 8 < fv) st_cs(o + l4 + 8, b);
+        if (l4 + 16 < fv) st_cs(o + l4 + 16, c);
+        if (l4 + 24 < fv) st_cs(o + l4 + 24, d);
+    }
+}
+
+// One 1x8 by 8x4 FMA block: a[c][f] += w[c] * r[f]
+__device__ __forceinline__ void fma_8x4(float (&a)[CD][4], const float4 &wa, const float4 &wb, float r0, float r1, float r2, float r3) {
+    const float wv[CD] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+    for (int c = 0; c < CD; ++c) {
+        a[c][0] = fmaf(wv[c], r0, a[c][0]);
+        a[c][1] = fmaf(wv[c], r1, a[c][1]);
+        a[c][2] = fmaf(wv[c], r2, a[c][2]);
+        a[c][3] = fmaf(wv[c], r3, a[c][3]);
+    }
+}
+
+// out_proj + residual update + masked accumulate for one thread: NCH channels (stride 4 in d) x 4 frames.
+// FIRST / LAST and the store shapes are compile-time, so the unrolled body is branch-free.  Residual and z_q
+// accumulators stream through TMEM in groups of 8 columns (2 channels x 4 frames).
+template <int NCH, bool FIRST, bool LAST, bool ZQIS, int VEC_ST>
+__device__ __forceinline__ void out_proj_thread(const float *__restrict__ wp, const float *__restrict__ bp, const float (&q)[CD][4],
+                                                const float (&m)[4], uint32_t tR, uint32_t tA, float *zo, long long zstep, float *zq,
+                                                long long zqstep, int l4, int fv) {
+    static_assert(NCH % 2 == 0, "channels per thread must be even");
+#pragma unroll
+    for (int g = 0; g < NCH / 2; ++g) {
+        uint32_t r8[8], a8[8];
+        if (!LAST) tmem_ld8(tR + 8 * g, r8);
+        if (!FIRST) tmem_ld8(tA + 8 * g, a8);
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = 4 * g + u;
-            const float4 wa = *reinterpret_cast<const float4 *>(wp + i * 2 * CD);
-            const float4 wb = *reinterpret_cast<const float4 *>(wp + i * 2 * CD + 4);
-            float v0 = bp[2 * i], v1 = v0;
-            v0 = __fmaf_rn(wa.x, q0[0], v0); v1 = __fmaf_rn(wa.x, q1[0], v1);
-            v0 = __fmaf_rn(wa.y, q0[1], v0); v1 = __fmaf_rn(wa.y, q1[1], v1);
-            v0 = __fmaf_rn(wa.z, q0[2], v0); v1 = __fmaf_rn(wa.z, q1[2], v1);
-            v0 = __fmaf_rn(wa.w, q0[3], v0); v1 = __fmaf_rn(wa.w, q1[3], v1);
-            v0 = __fmaf_rn(wb.x, q0[4], v0); v1 = __fmaf_rn(wb.x, q1[4], v1);
-            v0 = __fmaf_rn(wb.y, q0[5], v0); v1 = __fmaf_rn(wb.y, q1[5], v1);
-            v0 = __fmaf_rn(wb.z, q0[6], v0); v1 = __fmaf_rn(wb.z, q1[6], v1);
-            v0 = __fmaf_rn(wb.w, q0[7], v0); v1 = __fmaf_rn(wb.w, q1[7], v1);
-            if (!LAST) {
-                float2 *rr = reinterpret_cast<float2 *>(rp + i * 2 * TF);
-                float2 r = *rr;
-                r.x = __fsub_rn(r.x, v0);
-                r.y = __fsub_rn(r.y, v1);
-                *rr = r;
+        for (int u = 0; u < 2; ++u) {
+            const int i = 2 * g + u;
+            const float4 wa = *reinterpret_cast<const float4 *>(wp + i * 4 * CD);
+            const float4 wb = *reinterpret_cast<const float4 *>(wp + i * 4 * CD + 4);
+            const float wv[CD] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const float bias = bp[4 * i];
+            float x[4] = {bias, bias, bias, bias};
+#pragma unroll
+            for (int k = 0; k < CD; ++k) {  // bias-initialised ascending-k chain, 4 independent frames
+                x[0] = __fmaf_rn(wv[k], q[k][0], x[0]);
+                x[1] = __fmaf_rn(wv[k], q[k][1], x[1]);
+                x[2] = __fmaf_rn(wv[k], q[k][2], x[2]);
+                x[3] = __fmaf_rn(wv[k], q[k][3], x[3]);
             }
             if (ZQIS) {
-                if (VEC_ST == 2) {
-                    if (v0ok) st_cs2(zo, v0, v1);  // fv is even whenever VEC_ST == 2
-                } else {
-                    if (v0ok) st_cs(zo, v0);
-                    if (v1ok) st_cs(zo + 1, v1);
-                }
+                store4<VEC_ST>(zo, l4, x[0], x[1], x[2], x[3], fv);
                 zo += zstep;
             }
-            v[2 * u] = v0;
-            v[2 * u + 1] = v1;
+            v[4 * u] = x[0]; v[4 * u + 1] = x[1]; v[4 * u + 2] = x[2]; v[4 * u + 3] = x[3];
         }
-        if (!FIRST) tmem_wait_ld();
+        if (!LAST) tmem_wait_ld(r8);
+        if (!FIRST) tmem_wait_ld(a8);
+        if (!LAST) {  // r <- r - z_q_i  (quantize.py:195 / :360)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {  // z_q += mask * z_q_i  (quantize.py:194 / :421), ascending stage order from 0
-            const float a0 = FIRST ? 0.0f : __uint_as_float(a8[2 * u]);
-            const float a1 = FIRST ? 0.0f : __uint_as_float(a8[2 * u + 1]);
-            a8[2 * u] = __float_as_uint(__fmaf_rn(m0, v[2 * u], a0));
-            a8[2 * u + 1] = __float_as_uint(__fmaf_rn(m1, v[2 * u + 1], a1));
+            for (int e = 0; e < 8; ++e) r8[e] = __float_as_uint(__fsub_rn(__uint_as_float(r8[e]), v[e]));
+            tmem_st8(tR + 8 * g, r8);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {  // z_q += mask * z_q_i  (quantize.py:194 / :421), ascending stage order from 0
+            const float a0 = FIRST ? 0.0f : __uint_as_float(a8[e]);
+            a8[e] = __float_as_uint(__fmaf_rn(m[e & 3], v[e], a0));
         }
         if (!LAST) {
-            tmem_st8(tacc + 8 * g, a8);
+            tmem_st8(tA + 8 * g, a8);
         } else if (zq != nullptr) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (VEC_ST == 2) {
-                    if (v0ok) st_cs2(zq, __uint_as_float(a8[2 * u]), __uint_as_float(a8[2 * u + 1]));
-                } else {
-                    if (v0ok) st_cs(zq, __uint_as_float(a8[2 * u]));
-                    if (v1ok) st_cs(zq + 1, __uint_as_float(a8[2 * u + 1]));
-                }
-                zq += zqstep;
-            }
+            store4<VEC_ST>(zq, l4, __uint_as_float(a8[0]), __uint_as_float(a8[1]), __uint_as_float(a8[2]), __uint_as_float(a8[3]), fv);
+            store4<VEC_ST>(zq + zqstep, l4, __uint_as_float(a8[4]), __uint_as_float(a8[5]), __uint_as_float(a8[6]), __uint_as_float(a8[7]), fv);
+            zq += 2 * zqstep;
         }
     }
     if (!LAST) tmem_wait_st();
@@ -185,12 +232,13 @@ template <int D, int K, int VEC_ST, bool ZQIS>
 __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p) {
     using S = EncodeSmem<D, K>;
     constexpr BlobLayout L = BlobLayout(D, K);
-    constexpr int DW = D / NW;  // channels per warp
-    static_assert(D % (NW * 4) == 0, "D must be a multiple of 64");
+    constexpr int DW = D / NW;   // channels per warp
+    constexpr int NCH = DW / 4;  // channels per thread
+    static_assert(D % (NW * 8) == 0, "D must be a multiple of 128");
     static_assert(K % 64 == 0, "codebook size must be a multiple of 64");
 
     extern __shared__ __align__(128) float smem[];
-    float *R = smem + S::OFF_R;
+    float *R = smem + S::OFF_R;  // staging: the tile being prefetched
     float *wb0 = smem + S::OFF_WB0;
     float *wb1 = smem + S::OFF_WB1;
     float *part = smem + S::OFF_PART;  // [NW][CD][TF]; re-used as sbest/sidx after the reduce
@@ -202,7 +250,8 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
     int *nkeep = reinterpret_cast<int *>(smem + S::OFF_NKEEP);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::OFF_BARS);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::OFF_TMEM);
-    constexpr uint32_t TMEM_COLS = (NW / 4) * DW;  // accumulator columns: DW per thread, 4 lane quadrants
+    // per thread: NCH*4 residual columns + NCH*4 accumulator columns; the 4 warps of a lane quadrant sit side by side
+    constexpr uint32_t TMEM_COLS = (NW / 4) * 2 * DW;
     static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two in [32, 512]");
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -254,8 +303,9 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
     __syncthreads();
     tmem_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    // this thread's accumulator strip: its own lane of quadrant w%4, DW columns starting at (w/4)*DW
-    const uint32_t tacc = tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)((w >> 2) * DW);
+    // this thread's strip: its own lane of quadrant w%4; [residual DW cols | accumulators DW cols] at (w/4)*2*DW
+    const uint32_t tR = tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)((w >> 2) * 2 * DW);
+    const uint32_t tA = tR + DW;
     if (tid == 0) issue_piece(0);
 
     auto tile_coords = [&](int it, int &b, int &t0, int &fv) {
@@ -278,13 +328,40 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
     };
     start_tile_load(0);
 
-    // thread coordinates of the phase mappings
-    const int l4 = lane & 7, g4 = lane >> 3;   // in_proj : frames 4*l4..+3, quarter-warp g4 = K sub-slice
-    const int l2 = lane & 15, g2 = lane >> 4;  // search / out_proj : frames 2*l2, 2*l2+1; half-warp g2
-    const int f0 = 2 * l2;
+    // thread coordinates
+    const int l4 = lane & 7, g4 = lane >> 3;   // frames frame_of<VEC_ST>(l4, 0..3); quarter-warp g4 -> channels w*DW + 4i + g4
+    const int l2 = lane & 15, g2 = lane >> 4;  // search: frames 2*l2, 2*l2+1; half-warp g2 -> code pairs
+    const int dbase = w * DW + g4;
 
     double loss_acc = 0.0;               // lane 0 of warp 0
     unsigned long long kept_acc = 0ull;  // lane k of warp 0 counts stage k
+
+    // reduce-scatter of the in_proj partial sums over the four K sub-slices (quarter-warps) of a warp, then to `part`
+    auto scatter_partials = [&](float (&a)[CD][4]) {
+        float h[4][4];
+        const bool up16 = (g4 & 2) != 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const float keep = up16 ? a[c + 4][f] : a[c][f];
+                const float send = up16 ? a[c][f] : a[c + 4][f];
+                h[c][f] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+            }
+        float q2[2][4];
+        const bool up8 = (g4 & 1) != 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const float keep = up8 ? h[c + 2][f] : h[c][f];
+                const float send = up8 ? h[c][f] : h[c + 2][f];
+                q2[c][f] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+            }
+        const int c0 = 4 * (g4 >> 1) + 2 * (g4 & 1);
+        row_store4<VEC_ST>(&part[(w * CD + c0) * TF], l4, q2[0][0], q2[0][1], q2[0][2], q2[0][3]);
+        row_store4<VEC_ST>(&part[(w * CD + c0 + 1) * TF], l4, q2[1][0], q2[1][1], q2[1][2], q2[1][3]);
+    };
 
     for (int it = 0; it < n_my_tiles; ++it) {
         int b, t0, fv;
@@ -312,61 +389,59 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
             }
         }
         cp_async_wait_all();
-        __syncthreads();  // residual tile and nkeep visible
+        __syncthreads();  // staged latent tile and nkeep visible
 
         for (int s = 0; s < n_run; ++s) {
             const bool last = (s == n_run - 1);
             // ================= in_proj: z_e[c][f] = sum_d W_in[c][d] r[d][f] =================
-            // Thread tile 8 channels x 4 frames; the four quarter-warps take four consecutive residual rows per step
-            // (so one LDS.128 delivers 512 useful bytes), i.e. K is split 4 ways inside the warp and NW ways across warps.
+            // Thread tile 8 channels-out x 4 frames over its own NCH residual channels (K split 4 ways inside the warp,
+            // NW ways across warps).  Stage 0 reads the staged latent and moves it into TMEM on the way.
             {
                 const float *W = acquire();
                 float a[CD][4];
 #pragma unroll
                 for (int c = 0; c < CD; ++c) a[c][0] = a[c][1] = a[c][2] = a[c][3] = 0.0f;
-                const float *Wp = W + (w * DW + g4) * CD;
-                const float *Rp = R + (w * DW + g4) * TF + 4 * l4;
-#pragma unroll 4
-                for (int i = 0; i < DW / 4; ++i) {
-                    const float4 rv = *reinterpret_cast<const float4 *>(Rp + i * 4 * TF);
-                    const float4 wa = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD);
-                    const float4 wb = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD + 4);
-                    const float wv[CD] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                const float *Wp = W + dbase * CD;
+                if (s == 0) {
+                    const float *Rp = R + dbase * TF;
 #pragma unroll
-                    for (int c = 0; c < CD; ++c) {
-                        a[c][0] = fmaf(wv[c], rv.x, a[c][0]);
-                        a[c][1] = fmaf(wv[c], rv.y, a[c][1]);
-                        a[c][2] = fmaf(wv[c], rv.z, a[c][2]);
-                        a[c][3] = fmaf(wv[c], rv.w, a[c][3]);
+                    for (int g = 0; g < NCH / 2; ++g) {
+                        uint32_t r8[8];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = 2 * g + u;
+                            float rv[4];
+                            row_load4<VEC_ST>(Rp + i * 4 * TF, l4, rv);
+                            const float4 wa = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD);
+                            const float4 wb = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD + 4);
+                            fma_8x4(a, wa, wb, rv[0], rv[1], rv[2], rv[3]);
+                            r8[4 * u] = __float_as_uint(rv[0]); r8[4 * u + 1] = __float_as_uint(rv[1]);
+                            r8[4 * u + 2] = __float_as_uint(rv[2]); r8[4 * u + 3] = __float_as_uint(rv[3]);
+                        }
+                        if (n_run > 1) tmem_st8(tR + 8 * g, r8);
+                    }
+                    if (n_run > 1) tmem_wait_st();
+                } else {
+                    uint32_t r8[2][8];
+                    tmem_ld8(tR, r8[0]);
+#pragma unroll
+                    for (int g = 0; g < NCH / 2; ++g) {
+                        tmem_wait_ld(r8[g & 1]);
+                        if (g + 1 < NCH / 2) tmem_ld8(tR + 8 * (g + 1), r8[(g + 1) & 1]);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = 2 * g + u;
+                            const float4 wa = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD);
+                            const float4 wb = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD + 4);
+                            fma_8x4(a, wa, wb, __uint_as_float(r8[g & 1][4 * u]), __uint_as_float(r8[g & 1][4 * u + 1]),
+                                    __uint_as_float(r8[g & 1][4 * u + 2]), __uint_as_float(r8[g & 1][4 * u + 3]));
+                        }
                     }
                 }
-                // reduce-scatter over the four K sub-slices: after lane^16 a thread keeps 4 channels, after lane^8 two.
-                float h[4][4];
-                const bool up16 = (g4 & 2) != 0;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        const float keep = up16 ? a[c + 4][f] : a[c][f];
-                        const float send = up16 ? a[c][f] : a[c + 4][f];
-                        h[c][f] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-                    }
-                float q2[2][4];
-                const bool up8 = (g4 & 1) != 0;
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        const float keep = up8 ? h[c + 2][f] : h[c][f];
-                        const float send = up8 ? h[c][f] : h[c + 2][f];
-                        q2[c][f] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-                    }
-                const int c0 = 4 * (g4 >> 1) + 2 * (g4 & 1);
-                *reinterpret_cast<float4 *>(&part[(w * CD + c0) * TF + 4 * l4]) = make_float4(q2[0][0], q2[0][1], q2[0][2], q2[0][3]);
-                *reinterpret_cast<float4 *>(&part[(w * CD + c0 + 1) * TF + 4 * l4]) = make_float4(q2[1][0], q2[1][1], q2[1][2], q2[1][3]);
+                scatter_partials(a);
                 __syncthreads();
-                // the residual is dead after the last stage's in_proj: start fetching the next tile
-                if (last && it + 1 < n_my_tiles) start_tile_load(it + 1);
+                // the staging buffer is free once stage 0 has consumed it: prefetch the next tile for the rest of this one
+                if (s == 0 && it + 1 < n_my_tiles) start_tile_load(it + 1);
                 if (tid < CD * TF) {
                     const int c = w;  // tid >> 5
                     float sacc = part[c * TF + lane];
@@ -405,41 +480,58 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                 __syncthreads();
             }
             // ================= search over the normalised codebook =================
-            // Lane = frame; warp w scans code pairs [w*K/32, (w+1)*K/32) in ascending order with warp-uniform
-            // (broadcast) codebook reads.  The codebook piece is pair-interleaved ([pair][k][2]) so that one
-            // fma.rn.f32x2 advances the dot products of two adjacent codes.
+            // Thread: 2 frames x K/32 code pairs (ascending); the two half-warps take adjacent pairs, so every codebook
+            // LDS.128 is a 2-address broadcast.  The piece is pair-interleaved ([pair][k][2]): one fma.rn.f32x2 advances
+            // the dot products of two adjacent codes.
             {
                 const float *CB = acquire();
                 const float *c2 = CB + K * CD;
-                float2 ea[CD];  // (2e_k, 2e_k) of frame `lane`
+                const int f0 = 2 * l2;
+                float2 ea[CD], eb[CD];  // (2e_k, 2e_k) of frame f0 / f0+1
 #pragma unroll
-                for (int k = 0; k < CD; ++k) ea[k] = dup2(es[k * TF + lane]);
-                const float2 e2a = dup2(e2s[lane]);
-                float best = __int_as_float(0x7f800000);
-                int bi = 0;
-                constexpr int PPW = K / 2 / NW;  // code pairs per warp
-                const float4 *cp = reinterpret_cast<const float4 *>(CB + (w * PPW) * 2 * CD);
-                const float2 *ccp = reinterpret_cast<const float2 *>(c2 + 2 * w * PPW);
-#pragma unroll 4
-                for (int i = 0; i < PPW; ++i) {
-                    const float4 c01 = cp[4 * i], c23 = cp[4 * i + 1], c45 = cp[4 * i + 2], c67 = cp[4 * i + 3];
-                    const float2 cc = ccp[i];
+                for (int k = 0; k < CD; ++k) {
+                    const float2 t = *reinterpret_cast<const float2 *>(&es[k * TF + f0]);
+                    ea[k] = dup2(t.x);
+                    eb[k] = dup2(t.y);
+                }
+                const float2 e2v = *reinterpret_cast<const float2 *>(&e2s[f0]);
+                const float2 e2a = dup2(e2v.x), e2b = dup2(e2v.y);
+                float best0 = __int_as_float(0x7f800000), best1 = best0;
+                int bi0 = 0, bi1 = 0;
+#pragma unroll 2
+                for (int i = 0; i < K / 64; ++i) {
+                    const int pr = 32 * i + 2 * w + g2;  // code pair; codes 2pr, 2pr+1 ascend with i
+                    const float4 *cp = reinterpret_cast<const float4 *>(CB + pr * 2 * CD);
+                    const float4 c01 = cp[0], c23 = cp[1], c45 = cp[2], c67 = cp[3];  // (c_j,k c_j+1,k) for k = 0..7
+                    const float2 cc = *reinterpret_cast<const float2 *>(c2 + 2 * pr);
                     float2 da = __fmul2_rn(ea[0], make_float2(c01.x, c01.y));
-                    da = __ffma2_rn(ea[1], make_float2(c01.z, c01.w), da);
-                    da = __ffma2_rn(ea[2], make_float2(c23.x, c23.y), da);
-                    da = __ffma2_rn(ea[3], make_float2(c23.z, c23.w), da);
-                    da = __ffma2_rn(ea[4], make_float2(c45.x, c45.y), da);
-                    da = __ffma2_rn(ea[5], make_float2(c45.z, c45.w), da);
-                    da = __ffma2_rn(ea[6], make_float2(c67.x, c67.y), da);
-                    da = __ffma2_rn(ea[7], make_float2(c67.z, c67.w), da);
+                    float2 db = __fmul2_rn(eb[0], make_float2(c01.x, c01.y));
+                    da = __ffma2_rn(ea[1], make_float2(c01.z, c01.w), da); db = __ffma2_rn(eb[1], make_float2(c01.z, c01.w), db);
+                    da = __ffma2_rn(ea[2], make_float2(c23.x, c23.y), da); db = __ffma2_rn(eb[2], make_float2(c23.x, c23.y), db);
+                    da = __ffma2_rn(ea[3], make_float2(c23.z, c23.w), da); db = __ffma2_rn(eb[3], make_float2(c23.z, c23.w), db);
+                    da = __ffma2_rn(ea[4], make_float2(c45.x, c45.y), da); db = __ffma2_rn(eb[4], make_float2(c45.x, c45.y), db);
+                    da = __ffma2_rn(ea[5], make_float2(c45.z, c45.w), da); db = __ffma2_rn(eb[5], make_float2(c45.z, c45.w), db);
+                    da = __ffma2_rn(ea[6], make_float2(c67.x, c67.y), da); db = __ffma2_rn(eb[6], make_float2(c67.x, c67.y), db);
+                    da = __ffma2_rn(ea[7], make_float2(c67.z, c67.w), da); db = __ffma2_rn(eb[7], make_float2(c67.z, c67.w), db);
                     // dist = fl(fl(e2 - dot) + c2)
                     const float2 ta = __fadd2_rn(__fadd2_rn(e2a, make_float2(-da.x, -da.y)), cc);
-                    const int j = 2 * (w * PPW + i);
-                    if (ta.x < best) { best = ta.x; bi = j; }
-                    if (ta.y < best) { best = ta.y; bi = j + 1; }
+                    const float2 tb = __fadd2_rn(__fadd2_rn(e2b, make_float2(-db.x, -db.y)), cc);
+                    const int j = 2 * pr;
+                    if (ta.x < best0) { best0 = ta.x; bi0 = j; }
+                    if (ta.y < best0) { best0 = ta.y; bi0 = j + 1; }
+                    if (tb.x < best1) { best1 = tb.x; bi1 = j; }
+                    if (tb.y < best1) { best1 = tb.y; bi1 = j + 1; }
                 }
-                sbest[w * TF + lane] = best;
-                sidx[w * TF + lane] = bi;
+                {   // merge the two code groups of the warp (lane ^ 16)
+                    const float ob0 = __shfl_xor_sync(0xffffffffu, best0, 16), ob1 = __shfl_xor_sync(0xffffffffu, best1, 16);
+                    const int oi0 = __shfl_xor_sync(0xffffffffu, bi0, 16), oi1 = __shfl_xor_sync(0xffffffffu, bi1, 16);
+                    if (ob0 < best0 || (ob0 == best0 && oi0 < bi0)) { best0 = ob0; bi0 = oi0; }
+                    if (ob1 < best1 || (ob1 == best1 && oi1 < bi1)) { best1 = ob1; bi1 = oi1; }
+                }
+                if (g2 == 0) {
+                    *reinterpret_cast<float2 *>(&sbest[w * TF + f0]) = make_float2(best0, best1);
+                    *reinterpret_cast<int2 *>(&sidx[w * TF + f0]) = make_int2(bi0, bi1);
+                }
                 __syncthreads();
             }
             // ===== argmin merge, gather, loss, straight-through: every warp redundantly, lane = frame (no extra barrier) =====
@@ -485,38 +577,33 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
             // ================= out_proj + residual update + masked accumulate =================
             {
                 const float *bo = WO + D * CD;
-                float q0[CD], q1[CD];
+                float q[CD][4], m[4];
 #pragma unroll
-                for (int k = 0; k < CD; ++k) {
-                    q0[k] = __shfl_sync(0xffffffffu, qv[k], f0);
-                    q1[k] = __shfl_sync(0xffffffffu, qv[k], f0 + 1);
-                }
-                const int2 nk = *reinterpret_cast<const int2 *>(&nkeep[f0]);
-                const float m0 = nk.x > s ? 1.0f : 0.0f, m1 = nk.y > s ? 1.0f : 0.0f;
-                const bool v0ok = f0 < fv, v1ok = f0 + 1 < fv;
-                const int dbase = w * DW + g2;
+                for (int k = 0; k < CD; ++k)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) q[k][j] = __shfl_sync(0xffffffffu, qv[k], frame_of<VEC_ST>(l4, j));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[j] = nkeep[frame_of<VEC_ST>(l4, j)] > s ? 1.0f : 0.0f;
                 float *zo = nullptr;
-                if (ZQIS) zo = p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + (long long)dbase * p.zqis_sd + t0 + f0;
-                const long long zstep = 2 * p.zqis_sd;
+                if (ZQIS) zo = p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + (long long)dbase * p.zqis_sd + t0;
+                const long long zstep = 4 * p.zqis_sd;
+                float *zq = nullptr;
+                if (p.z_q != nullptr) zq = p.z_q + (long long)b * p.zq_sb + (long long)dbase * p.zq_sd + t0;
+                const long long zqstep = 4 * p.zq_sd;
                 const float *wp = WO + dbase * CD;
                 const float *bp = bo + dbase;
-                float *rp = R + dbase * TF + f0;
-                float *zq = nullptr;
-                if (p.z_q != nullptr) zq = p.z_q + (long long)b * p.zq_sb + (long long)dbase * p.zq_sd + t0 + f0;
-                const long long zqstep = 2 * p.zq_sd;
                 const bool first = (s == 0);
                 if (first && last)
-                    out_proj_thread<DW / 2, true, true, ZQIS, VEC_ST>(wp, bp, rp, q0, q1, m0, m1, tacc, zo, zstep, zq, zqstep, v0ok, v1ok);
+                    out_proj_thread<NCH, true, true, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
                 else if (first)
-                    out_proj_thread<DW / 2, true, false, ZQIS, VEC_ST>(wp, bp, rp, q0, q1, m0, m1, tacc, zo, zstep, zq, zqstep, v0ok, v1ok);
+                    out_proj_thread<NCH, true, false, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
                 else if (last)
-                    out_proj_thread<DW / 2, false, true, ZQIS, VEC_ST>(wp, bp, rp, q0, q1, m0, m1, tacc, zo, zstep, zq, zqstep, v0ok, v1ok);
+                    out_proj_thread<NCH, false, true, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
                 else
-                    out_proj_thread<DW / 2, false, false, ZQIS, VEC_ST>(wp, bp, rp, q0, q1, m0, m1, tacc, zo, zstep, zq, zqstep, v0ok, v1ok);
-                __syncthreads();  // residual updated; sbest/ze and the weight slot are free again
+                    out_proj_thread<NCH, false, false, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
+                __syncthreads();  // sbest/ze and the weight slot are free again
             }
         }  // stages
-
     }  // tiles
 
     tmem_fence_before_sync();
@@ -547,6 +634,7 @@ static int launch_one(const EncodeParams &p, int grid, cudaStream_t stream) {
 template <int D, int K>
 static int launch_encode(const EncodeParams &p, int grid, cudaStream_t stream) {
     const bool zqis = p.z_q_is != nullptr;
+    if (p.vec_st == 4) return zqis ? launch_one<D, K, 4, true>(p, grid, stream) : launch_one<D, K, 4, false>(p, grid, stream);
     if (p.vec_st == 2) return zqis ? launch_one<D, K, 2, true>(p, grid, stream) : launch_one<D, K, 2, false>(p, grid, stream);
     return zqis ? launch_one<D, K, 1, true>(p, grid, stream) : launch_one<D, K, 1, false>(p, grid, stream);
 }
@@ -606,10 +694,22 @@ static int fill_params(const vrvq_encode_args *a, EncodeParams &p) {
     p.vec_ld = 1;
     if (aligned(a->z, 16) && a->z_stride_b % 4 == 0 && a->z_stride_d % 4 == 0 && a->T % 4 == 0) p.vec_ld = 4;
     else if (aligned(a->z, 8) && a->z_stride_b % 2 == 0 && a->z_stride_d % 2 == 0 && a->T % 2 == 0) p.vec_ld = 2;
-    bool st2 = a->T % 2 == 0;
-    if (a->z_q) st2 = st2 && aligned(a->z_q, 8) && a->z_q_stride_b % 2 == 0 && a->z_q_stride_d % 2 == 0;
-    if (a->z_q_is) st2 = st2 && aligned(a->z_q_is, 8) && a->z_q_is_stride_b % 2 == 0 && a->z_q_is_stride_q % 2 == 0 && a->z_q_is_stride_d % 2 == 0;
-    p.vec_st = st2 ? 2 : 1;
+    auto st_ok = [&](int v) {  // every row start of every output is v*4-byte aligned
+        bool ok = a->T % v == 0;
+        if (a->z_q) ok = ok && aligned(a->z_q, 4 * v) && a->z_q_stride_b % v == 0 && a->z_q_stride_d % v == 0;
+        if (a->z_q_is)
+            ok = ok && aligned(a->z_q_is, 4 * v) && a->z_q_is_stride_b % v == 0 && a->z_q_is_stride_q % v == 0 && a->z_q_is_stride_d % v == 0;
+        return ok;
+    };
+    p.vec_st = st_ok(4) ? 4 : st_ok(2) ? 2 : 1;
+    if (const char *dbg = getenv("VRVQ_DEBUG_MAX_VEC_LD")) {  // profiling knob: cap the load width (never widens it)
+        const int cap = atoi(dbg);
+        if (cap == 1 || cap == 2) p.vec_ld = p.vec_ld < cap ? p.vec_ld : cap;
+    }
+    if (const char *dbg = getenv("VRVQ_DEBUG_MAX_VEC_ST")) {  // profiling knob: cap the store width (never widens it)
+        const int cap = atoi(dbg);
+        if (cap == 1 || cap == 2) p.vec_st = p.vec_st < cap ? p.vec_st : cap;
+    }
     return VRVQ_OK;
 }
 
