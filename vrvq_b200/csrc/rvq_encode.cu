@@ -178,7 +178,7 @@ __device__ __forceinline__ void out_proj_thread(const float *__restrict__ wp, co
                                                 const float (&m)[4], uint32_t tR, uint32_t tA, float *zo, long long zstep, float *zq,
                                                 long long zqstep, int l4, int fv) {
     static_assert(NCH % 2 == 0, "channels per thread must be even");
-#pragma unroll
+#pragma unroll 2
     for (int g = 0; g < NCH / 2; ++g) {
         uint32_t r8[8], a8[8];
         if (!LAST) tmem_ld8(tR + 8 * g, r8);
