@@ -253,24 +253,38 @@ def run_ours(args):
     h2d = zs_p[0].numel() * 4 + imps_p[0].numel() * 4
     d2h = h_codes.numel() * 8 + h_mask.numel() * 4 + h_small.numel() * 8
 
-    def e2e_step(i):
-        z = zs_p[i % N_INPUT_BUFFERS].to(dev, non_blocking=True)
-        imp = imps_p[i % N_INPUT_BUFFERS].to(dev, non_blocking=True)
-        r = model(z, n_quantizers=None, feat_enc=None, level=levels[i % 3], imp_map=imp)
-        h_codes.copy_(r["codes"], non_blocking=True)
-        h_mask.copy_(r["mask_imp"], non_blocking=True)
-        h_small[:Nq].copy_(r["kept_frames"].to(torch.float64), non_blocking=True)
-        h_small[Nq:].copy_(r["commitment_loss"].to(torch.float64).reshape(1), non_blocking=True)
+    # Two streams alternate so that step i+1's host->device copy overlaps step i's kernel and read-back, as a
+    # streaming caller would run it; every step still copies its own inputs in and its own results out.
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    h_codes = [h_codes, torch.empty_like(h_codes).pin_memory()]
+    h_mask = [h_mask, torch.empty_like(h_mask).pin_memory()]
+    h_small = [h_small, torch.empty_like(h_small).pin_memory()]
 
-    e2e_steps = max(3, min(args.steps, 50))
+    def e2e_step(i):
+        k = i % 2
+        with torch.cuda.stream(streams[k]):
+            z = zs_p[i % N_INPUT_BUFFERS].to(dev, non_blocking=True)
+            imp = imps_p[i % N_INPUT_BUFFERS].to(dev, non_blocking=True)
+            r = model(z, n_quantizers=None, feat_enc=None, level=levels[i % 3], imp_map=imp)
+            h_codes[k].copy_(r["codes"], non_blocking=True)
+            h_mask[k].copy_(r["mask_imp"], non_blocking=True)
+            h_small[k][:Nq].copy_(r["kept_frames"].to(torch.float64), non_blocking=True)
+            h_small[k][Nq:].copy_(r["commitment_loss"].to(torch.float64).reshape(1), non_blocking=True)
+
+    e2e_steps = max(4, min(args.steps, 50))
     for i in range(2):
         e2e_step(i)
     barrier()
+    cur = torch.cuda.current_stream(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(cur)
+    for st in streams:
+        st.wait_stream(cur)
     for i in range(e2e_steps):
         e2e_step(i)
-    e1.record()
+    for st in streams:
+        cur.wait_stream(st)
+    e1.record(cur)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     sampler.stop()
@@ -298,7 +312,7 @@ def run_ours(args):
                          "smem_bytes": info["smem_bytes"]},
             "e2e": {"value": world * frames * e2e_steps / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps,
-                    "api": "VBRResidualVectorQuantize.forward(z, level, imp_map) on pinned host buffers; z_q/z_q_is stay on the device"},
+                    "api": "VBRResidualVectorQuantize.forward(z, level, imp_map) on pinned host buffers, two alternating CUDA streams; z_q/z_q_is stay on the device"},
             "gpu_launches": launches * world, "clocks": clocks, "torch": torch.__version__,
         }
         if world == 1 and not args.no_cpu_baseline:
