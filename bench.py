@@ -201,7 +201,12 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout at communicator creation; keep stdout clean for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -318,8 +323,13 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline_run(sd, steps=args.cpu_steps, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
+        if saved_stdout is not None and rank == 0:
+            os.dup2(2, 1)
         dist.barrier()
         dist.destroy_process_group()
     return 0
