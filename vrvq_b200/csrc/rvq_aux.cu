@@ -135,29 +135,51 @@ __global__ void __launch_bounds__(FC_NT) from_codes_kernel(const FromCodesParams
         ms[s][lane] = (p.mask != nullptr && valid) ? p.mask[(long long)b * p.m_sb + (long long)s * p.m_sq + t] : 1.0f;
     }
     __syncthreads();
+    // thread = 4 consecutive frames x one channel at a time; the 4 quarter-warps of a warp take 4 adjacent channels, so the
+    // W_out row reads are quarter-uniform broadcasts and each row store is 8 lanes x 16 B contiguous.
+    const int l4 = lane & 7, g4 = lane >> 3;
+    const int tq = t0 + 4 * l4;
+    const int nvalid = max(0, min(4, p.T - tq));
+    const bool vec4 = (nvalid == 4) && ((p.zq_sd & 3) == 0) && ((p.zq_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.z_q) & 15) == 0) &&
+                      (p.z_q_is == nullptr || (((p.zqis_sd | p.zqis_sq | p.zqis_sb) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.z_q_is) & 15) == 0));
     const int d_begin = blockIdx.y * FC_DCH;
-    for (int dd = w; dd < FC_DCH; dd += FC_NT / 32) {
+    for (int dd = 4 * w + g4; dd < FC_DCH; dd += 4 * (FC_NT / 32)) {
         const int d = d_begin + dd;
         if (d >= p.D) break;
-        float acc = 0.0f;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (int s = 0; s < p.n_run; ++s) {
             const float *wo = stages + (size_t)s * p.stage_floats + p.off_p2 + (size_t)d * CD;
             const float4 wa = __ldg(reinterpret_cast<const float4 *>(wo));
             const float4 wb = __ldg(reinterpret_cast<const float4 *>(wo + 4));
-            float v = __ldg(stages + (size_t)s * p.stage_floats + p.off_p2 + (size_t)p.D * CD + d);
-            v = __fmaf_rn(wa.x, qs[s][0][lane], v);
-            v = __fmaf_rn(wa.y, qs[s][1][lane], v);
-            v = __fmaf_rn(wa.z, qs[s][2][lane], v);
-            v = __fmaf_rn(wa.w, qs[s][3][lane], v);
-            v = __fmaf_rn(wb.x, qs[s][4][lane], v);
-            v = __fmaf_rn(wb.y, qs[s][5][lane], v);
-            v = __fmaf_rn(wb.z, qs[s][6][lane], v);
-            v = __fmaf_rn(wb.w, qs[s][7][lane], v);
-            if (p.z_q_is != nullptr && valid)
-                __stcs(p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + (long long)d * p.zqis_sd + t, v);
-            acc = __fmaf_rn(ms[s][lane], v, acc);
+            const float wv[CD] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const float bias = __ldg(stages + (size_t)s * p.stage_floats + p.off_p2 + (size_t)p.D * CD + d);
+            float v[4] = {bias, bias, bias, bias};
+#pragma unroll
+            for (int k = 0; k < CD; ++k) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = __fmaf_rn(wv[k], qs[s][k][4 * l4 + j], v[j]);
+            }
+            if (p.z_q_is != nullptr) {
+                float *o = p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + (long long)d * p.zqis_sd + tq;
+                if (vec4) {
+                    __stcs(reinterpret_cast<float4 *>(o), make_float4(v[0], v[1], v[2], v[3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nvalid) __stcs(o + j, v[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = __fmaf_rn(ms[s][4 * l4 + j], v[j], acc[j]);
         }
-        if (valid) __stcs(p.z_q + (long long)b * p.zq_sb + (long long)d * p.zq_sd + t, acc);
+        float *o = p.z_q + (long long)b * p.zq_sb + (long long)d * p.zq_sd + tq;
+        if (vec4) {
+            __stcs(reinterpret_cast<float4 *>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < nvalid) __stcs(o + j, acc[j]);
+        }
     }
 }
 

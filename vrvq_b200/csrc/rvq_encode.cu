@@ -24,6 +24,7 @@
 // Arithmetic that must be reproduced bit-for-bit uses explicit __f*_rn intrinsics (packed
 // fma.rn.f32x2 where two independent IEEE FMAs share an instruction); the file is compiled with
 // --fmad=false so nothing else is contracted behind our back.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -60,6 +61,7 @@ struct EncodeParams {
     int B, T, Nq, n_run, tiles_per_b, n_tiles;
     int vec_ld;  // 4 / 2 / 1 floats per global load of z
     int vec_st;  // 4 / 2 / 1 floats per global store of z_q, z_q_is
+    long long *phase_cycles;  // profiling only (VRVQ_DEBUG_PHASES=1): [gridDim.x][8] clock64 totals per phase, else NULL
 };
 
 template <int D, int K>
@@ -158,22 +160,21 @@ __device__ __forceinline__ void store4(float *o, int l4, float a, float b, float
     }
 }
 
-// One 1x8 by 8x4 FMA block: a[c][f] += w[c] * r[f]
-__device__ __forceinline__ void fma_8x4(float (&a)[CD][4], const float4 &wa, const float4 &wb, float r0, float r1, float r2, float r3) {
-    const float wv[CD] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+// One 1x8 by 8x4 FMA block: a[c][f] += w[c] * r[f], as 16 packed fma.rn.f32x2 over adjacent out-channel pairs
+// (the weight pairs come straight from the LDS.128; the residual value is duplicated).  a2[cp][f] = (a[2cp][f], a[2cp+1][f]).
+__device__ __forceinline__ void fma_8x4(float2 (&a2)[CD / 2][4], const float4 &wa, const float4 &wb, float r0, float r1, float r2, float r3) {
+    const float2 w2[CD / 2] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
+    const float2 rr[4] = {dup2(r0), dup2(r1), dup2(r2), dup2(r3)};
 #pragma unroll
-    for (int c = 0; c < CD; ++c) {
-        a[c][0] = fmaf(wv[c], r0, a[c][0]);
-        a[c][1] = fmaf(wv[c], r1, a[c][1]);
-        a[c][2] = fmaf(wv[c], r2, a[c][2]);
-        a[c][3] = fmaf(wv[c], r3, a[c][3]);
-    }
+    for (int cp = 0; cp < CD / 2; ++cp)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) a2[cp][f] = __ffma2_rn(w2[cp], rr[f], a2[cp][f]);
 }
 
 // out_proj + residual update + masked accumulate for one thread: NCH channels (stride 4 in d) x 4 frames.
-// FIRST / LAST and the store shapes are compile-time, so the unrolled body is branch-free.  Residual and z_q
-// accumulators stream through TMEM in groups of 8 columns (2 channels x 4 frames).
-template <int NCH, bool FIRST, bool LAST, bool ZQIS, int VEC_ST>
+// LAST and the store shapes are compile-time, so the body is branch-free.  Residual and z_q accumulators stream through
+// TMEM in groups of 8 columns (2 channels x 4 frames); the accumulators were zeroed when the tile was parked in TMEM.
+template <int NCH, bool LAST, bool ZQIS, int VEC_ST>
 __device__ __forceinline__ void out_proj_thread(const float *__restrict__ wp, const float *__restrict__ bp, const float (&q)[CD][4],
                                                 const float (&m)[4], uint32_t tR, uint32_t tA, float *zo, long long zstep, float *zq,
                                                 long long zqstep, int l4, int fv) {
@@ -182,7 +183,7 @@ __device__ __forceinline__ void out_proj_thread(const float *__restrict__ wp, co
     for (int g = 0; g < NCH / 2; ++g) {
         uint32_t r8[8], a8[8];
         if (!LAST) tmem_ld8(tR + 8 * g, r8);
-        if (!FIRST) tmem_ld8(tA + 8 * g, a8);
+        tmem_ld8(tA + 8 * g, a8);
         float v[8];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -206,7 +207,7 @@ __device__ __forceinline__ void out_proj_thread(const float *__restrict__ wp, co
             v[4 * u] = x[0]; v[4 * u + 1] = x[1]; v[4 * u + 2] = x[2]; v[4 * u + 3] = x[3];
         }
         if (!LAST) tmem_wait_ld(r8);
-        if (!FIRST) tmem_wait_ld(a8);
+        tmem_wait_ld(a8);
         if (!LAST) {  // r <- r - z_q_i  (quantize.py:195 / :360)
 #pragma unroll
             for (int e = 0; e < 8; ++e) r8[e] = __float_as_uint(__fsub_rn(__uint_as_float(r8[e]), v[e]));
@@ -214,8 +215,7 @@ __device__ __forceinline__ void out_proj_thread(const float *__restrict__ wp, co
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {  // z_q += mask * z_q_i  (quantize.py:194 / :421), ascending stage order from 0
-            const float a0 = FIRST ? 0.0f : __uint_as_float(a8[e]);
-            a8[e] = __float_as_uint(__fmaf_rn(m[e & 3], v[e], a0));
+            a8[e] = __float_as_uint(__fmaf_rn(m[e & 3], v[e], __uint_as_float(a8[e])));
         }
         if (!LAST) {
             tmem_st8(tA + 8 * g, a8);
@@ -333,6 +333,16 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
     const int l2 = lane & 15, g2 = lane >> 4;  // search: frames 2*l2, 2*l2+1; half-warp g2 -> code pairs
     const int dbase = w * DW + g4;
 
+    long long ph_last = 0, ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // thread 0 only, when p.phase_cycles != NULL
+    const bool ph_on = (p.phase_cycles != nullptr) && tid == 0;
+    if (ph_on) ph_last = clock64();
+    auto ph_mark = [&](int k) {
+        if (ph_on) {
+            const long long t = clock64();
+            ph_acc[k] += t - ph_last;
+            ph_last = t;
+        }
+    };
     double loss_acc = 0.0;               // lane 0 of warp 0
     unsigned long long kept_acc = 0ull;  // lane k of warp 0 counts stage k
 
@@ -390,6 +400,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
         }
         cp_async_wait_all();
         __syncthreads();  // staged latent tile and nkeep visible
+        ph_mark(0);  // tile setup + wait for the prefetched latent
 
         for (int s = 0; s < n_run; ++s) {
             const bool last = (s == n_run - 1);
@@ -398,15 +409,17 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
             // NW ways across warps).  Stage 0 reads the staged latent and moves it into TMEM on the way.
             {
                 const float *W = acquire();
-                float a[CD][4];
+                float2 a2[CD / 2][4];
 #pragma unroll
-                for (int c = 0; c < CD; ++c) a[c][0] = a[c][1] = a[c][2] = a[c][3] = 0.0f;
+                for (int cp = 0; cp < CD / 2; ++cp) a2[cp][0] = a2[cp][1] = a2[cp][2] = a2[cp][3] = make_float2(0.0f, 0.0f);
                 const float *Wp = W + dbase * CD;
                 if (s == 0) {
                     const float *Rp = R + dbase * TF;
-#pragma unroll
+                    const uint32_t zero8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll 2
                     for (int g = 0; g < NCH / 2; ++g) {
                         uint32_t r8[8];
+                        tmem_st8(tA + 8 * g, zero8);  // z_q accumulators start at +0 (quantize.py:165,335)
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             const int i = 2 * g + u;
@@ -414,17 +427,17 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                             row_load4<VEC_ST>(Rp + i * 4 * TF, l4, rv);
                             const float4 wa = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD);
                             const float4 wb = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD + 4);
-                            fma_8x4(a, wa, wb, rv[0], rv[1], rv[2], rv[3]);
+                            fma_8x4(a2, wa, wb, rv[0], rv[1], rv[2], rv[3]);
                             r8[4 * u] = __float_as_uint(rv[0]); r8[4 * u + 1] = __float_as_uint(rv[1]);
                             r8[4 * u + 2] = __float_as_uint(rv[2]); r8[4 * u + 3] = __float_as_uint(rv[3]);
                         }
                         if (n_run > 1) tmem_st8(tR + 8 * g, r8);
                     }
-                    if (n_run > 1) tmem_wait_st();
+                    tmem_wait_st();
                 } else {
                     uint32_t r8[2][8];
                     tmem_ld8(tR, r8[0]);
-#pragma unroll
+#pragma unroll 2
                     for (int g = 0; g < NCH / 2; ++g) {
                         tmem_wait_ld(r8[g & 1]);
                         if (g + 1 < NCH / 2) tmem_ld8(tR + 8 * (g + 1), r8[(g + 1) & 1]);
@@ -433,13 +446,22 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                             const int i = 2 * g + u;
                             const float4 wa = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD);
                             const float4 wb = *reinterpret_cast<const float4 *>(Wp + i * 4 * CD + 4);
-                            fma_8x4(a, wa, wb, __uint_as_float(r8[g & 1][4 * u]), __uint_as_float(r8[g & 1][4 * u + 1]),
+                            fma_8x4(a2, wa, wb, __uint_as_float(r8[g & 1][4 * u]), __uint_as_float(r8[g & 1][4 * u + 1]),
                                     __uint_as_float(r8[g & 1][4 * u + 2]), __uint_as_float(r8[g & 1][4 * u + 3]));
                         }
                     }
                 }
+                float a[CD][4];
+#pragma unroll
+                for (int cp = 0; cp < CD / 2; ++cp)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        a[2 * cp][f] = a2[cp][f].x;
+                        a[2 * cp + 1][f] = a2[cp][f].y;
+                    }
                 scatter_partials(a);
                 __syncthreads();
+                ph_mark(1);  // in_proj (incl. weight wait)
                 // the staging buffer is free once stage 0 has consumed it: prefetch the next tile for the rest of this one
                 if (s == 0 && it + 1 < n_my_tiles) start_tile_load(it + 1);
                 if (tid < CD * TF) {
@@ -478,6 +500,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                         p.latents[(long long)b * p.lat_sb + (long long)(s * CD + c) * p.lat_sc + t0 + lane] = xc;
                 }
                 __syncthreads();
+                ph_mark(2);  // cross-warp reduce + normalise
             }
             // ================= search over the normalised codebook =================
             // Thread: 2 frames x K/32 code pairs (ascending); the two half-warps take adjacent pairs, so every codebook
@@ -533,6 +556,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                     *reinterpret_cast<int2 *>(&sidx[w * TF + f0]) = make_int2(bi0, bi1);
                 }
                 __syncthreads();
+                ph_mark(3);  // search
             }
             // ===== argmin merge, gather, loss, straight-through: every warp redundantly, lane = frame (no extra barrier) =====
             float qv[CD];
@@ -574,6 +598,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                     loss_acc += ml;
                 }
             }
+            ph_mark(4);  // argmin merge + gather + straight-through (warp 0's view)
             // ================= out_proj + residual update + masked accumulate =================
             {
                 const float *bo = WO + D * CD;
@@ -592,20 +617,18 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                 const long long zqstep = 4 * p.zq_sd;
                 const float *wp = WO + dbase * CD;
                 const float *bp = bo + dbase;
-                const bool first = (s == 0);
-                if (first && last)
-                    out_proj_thread<NCH, true, true, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
-                else if (first)
-                    out_proj_thread<NCH, true, false, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
-                else if (last)
-                    out_proj_thread<NCH, false, true, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
+                if (last)
+                    out_proj_thread<NCH, true, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
                 else
-                    out_proj_thread<NCH, false, false, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
+                    out_proj_thread<NCH, false, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
                 __syncthreads();  // sbest/ze and the weight slot are free again
+                ph_mark(5);  // out_proj
             }
         }  // stages
     }  // tiles
 
+    if (ph_on)
+        for (int k = 0; k < 8; ++k) p.phase_cycles[(size_t)blockIdx.x * 8 + k] = ph_acc[k];
     tmem_fence_before_sync();
     __syncthreads();
     if (w == 0) {
@@ -747,12 +770,31 @@ int encode(const vrvq_encode_args *a, void *stream) {
     rc = pick_grid(p, &grid);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (a->input_dim) {
-        case 1024: return launch_encode<1024, 1024>(p, grid, st);
-        case 512: return launch_encode<512, 1024>(p, grid, st);
-        case 256: return launch_encode<256, 1024>(p, grid, st);
+    const bool dbg = getenv("VRVQ_DEBUG_PHASES") != nullptr;  // profiling only: synchronises and prints per-phase cycles
+    if (dbg) {
+        if (cudaMalloc(&p.phase_cycles, sizeof(long long) * 8 * (size_t)grid) != cudaSuccess) p.phase_cycles = nullptr;
     }
-    return VRVQ_EUNSUPPORTED;
+    switch (a->input_dim) {
+        case 1024: rc = launch_encode<1024, 1024>(p, grid, st); break;
+        case 512: rc = launch_encode<512, 1024>(p, grid, st); break;
+        case 256: rc = launch_encode<256, 1024>(p, grid, st); break;
+        default: rc = VRVQ_EUNSUPPORTED;
+    }
+    if (dbg && p.phase_cycles != nullptr) {
+        static const char *names[8] = {"tile_setup", "in_proj", "reduce_norm", "search", "merge_gather", "out_proj", "-", "-"};
+        long long *h = static_cast<long long *>(malloc(sizeof(long long) * 8 * (size_t)grid));
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, p.phase_cycles, sizeof(long long) * 8 * (size_t)grid, cudaMemcpyDeviceToHost);
+        double tot = 0, acc[8] = {0};
+        for (int g = 0; g < grid; ++g)
+            for (int k = 0; k < 8; ++k) { acc[k] += (double)h[g * 8 + k] / grid; tot += (double)h[g * 8 + k] / grid; }
+        fprintf(stderr, "[vrvq phases] mean cycles per CTA: total %.0f |", tot);
+        for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.0f (%.1f%%)", names[k], acc[k], 100.0 * acc[k] / tot);
+        fprintf(stderr, "\n");
+        free(h);
+        cudaFree(p.phase_cycles);
+    }
+    return rc;
 }
 
 }  // namespace vrvq
