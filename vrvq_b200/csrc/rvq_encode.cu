@@ -78,7 +78,8 @@ struct EncodeSmem {
     static constexpr int OFF_ZE = OFF_PART + PART_FLOATS;
     static constexpr int OFF_ES = OFF_ZE + CD * TF;
     static constexpr int OFF_E2 = OFF_ES + CD * TF;
-    static constexpr int OFF_NKEEP = OFF_E2 + TF;
+    static constexpr int OFF_QS = OFF_E2 + TF;  // [CD][TF] straight-through vectors
+    static constexpr int OFF_NKEEP = OFF_QS + CD * TF;
     static constexpr int OFF_BARS = OFF_NKEEP + TF;  // 2 x uint64
     static constexpr int OFF_TMEM = OFF_BARS + 4;    // TMEM base address written by tcgen05.alloc
     static constexpr int TOTAL_FLOATS = OFF_TMEM + 4;
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
     float *ze = smem + S::OFF_ZE;  // [CD][TF] pre-normalisation latents
     float *es = smem + S::OFF_ES;  // [CD][TF] 2*e
     float *e2s = smem + S::OFF_E2;
+    float *qs = smem + S::OFF_QS;
     int *nkeep = reinterpret_cast<int *>(smem + S::OFF_NKEEP);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::OFF_BARS);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::OFF_TMEM);
@@ -278,7 +280,9 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
             bytes = L.p2_floats() * 4;
         }
         uint64_t *bar = &bars[n & 1u];
-        fence_proxy_async();  // generic-proxy reads of the slot are ordered before the async-proxy overwrite
+        // No proxy fence here: the slot was only READ through the generic proxy, and every reader has passed a __syncthreads
+        // before this point (the usual consumer-release -> TMA-refill hand-over).  A fence.proxy.async would also wait for
+        // thread 0's outstanding global loads (measured: ~600 cycles per stage behind the raw-row gather).
         mbar_arrive_expect_tx(bar, bytes);
         bulk_g2s((n & 1u) ? wb1 : wb0, src, bytes, bar);
     };
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
             ph_last = t;
         }
     };
-    double loss_acc = 0.0;               // lane 0 of warp 0
+    double loss_acc = 0.0;               // lanes 0 and 16 of every warp (the frames they finalise)
     unsigned long long kept_acc = 0ull;  // lane k of warp 0 counts stage k
 
     // reduce-scatter of the in_proj partial sums over the four K sub-slices (quarter-warps) of a warp, then to `part`
@@ -558,55 +562,49 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                 __syncthreads();
                 ph_mark(3);  // search
             }
-            // ===== argmin merge, gather, loss, straight-through: every warp redundantly, lane = frame (no extra barrier) =====
-            float qv[CD];
-            const float *WO;
+            // ===== argmin merge, gather, loss, straight-through: warp w finalises frames 2w and 2w+1 =====
+            // Half-warp h handles frame f = 2w+h: lane i of the half holds warp i's minimum, a 4-step xor butterfly with the
+            // first-index tie rule leaves the winner in every lane, lanes 0..7 fetch the 8 floats of the raw codebook row
+            // (one 32-byte sector per frame; quantize.py:81-85,102) and form the straight-through value (quantize.py:73-75).
+            const float *WO = acquire();  // out_proj weights (and kicks off the next stage's in_proj piece)
             {
-                float best = sbest[lane];
-                int bi = sidx[lane];
+                const int h = lane >> 4, f = 2 * w + h;
+                float best = sbest[(lane & 15) * TF + f];
+                int bi = sidx[(lane & 15) * TF + f];
 #pragma unroll
-                for (int ww = 1; ww < NW; ++ww) {
-                    const float ob = sbest[ww * TF + lane];
-                    const int oi = sidx[ww * TF + lane];
+                for (int off = 8; off > 0; off >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
                     if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
                 }
-                const float *raw = stages + (size_t)s * L.stage_floats() + L.off_raw() + (size_t)bi * CD;
-                const float4 ra = __ldg(reinterpret_cast<const float4 *>(raw));
-                const float4 rb = __ldg(reinterpret_cast<const float4 *>(raw + 4));
-                WO = acquire();  // out_proj weights: the mbarrier wait overlaps the L2 gather latency
-                const float cr[CD] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-                float ls = 0.0f;
+                const int k = lane & 7;
+                const float cr = __ldg(stages + (size_t)s * L.stage_floats() + L.off_raw() + (size_t)bi * CD + k);
+                const float x = ze[k * TF + f];
+                const float diff = __fsub_rn(x, cr);  // quantize.py:69-71
+                const float sq = __fmul_rn(diff, diff);
+                if ((lane & 8) == 0) qs[k * TF + f] = __fadd_rn(x, __fsub_rn(cr, x));
+                float ls = __shfl_sync(0xffffffffu, sq, lane & 16);
 #pragma unroll
-                for (int k = 0; k < CD; ++k) {
-                    const float x = ze[k * TF + lane];
-                    const float diff = __fsub_rn(x, cr[k]);  // quantize.py:69-71
-                    const float sq = __fmul_rn(diff, diff);
-                    ls = (k == 0) ? sq : __fadd_rn(ls, sq);
-                    qv[k] = __fadd_rn(x, __fsub_rn(cr[k], x));  // quantize.py:73-75
-                }
-                if (w == 0) {
+                for (int kk = 1; kk < CD; ++kk) ls = __fadd_rn(ls, __shfl_sync(0xffffffffu, sq, (lane & 16) + kk));
+                if ((lane & 15) == 0 && f < fv) {
                     const float loss = __fdiv_rn(ls, (float)CD);
-                    const bool valid = lane < fv;
-                    if (valid) {
-                        p.codes[(long long)b * p.codes_sb + (long long)s * p.codes_sq + t0 + lane] = (long long)bi;
-                        if (p.loss_pf != nullptr)
-                            p.loss_pf[(long long)b * p.loss_sb + (long long)s * p.loss_sq + t0 + lane] = loss;
-                    }
-                    double ml = (valid && nkeep[lane] > s) ? (double)loss : 0.0;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) ml += __shfl_xor_sync(0xffffffffu, ml, off);
-                    loss_acc += ml;
+                    p.codes[(long long)b * p.codes_sb + (long long)s * p.codes_sq + t0 + f] = (long long)bi;
+                    if (p.loss_pf != nullptr) p.loss_pf[(long long)b * p.loss_sb + (long long)s * p.loss_sq + t0 + f] = loss;
+                    if (nkeep[f] > s) loss_acc += (double)loss;
                 }
             }
-            ph_mark(4);  // argmin merge + gather + straight-through (warp 0's view)
+            __syncthreads();
+            ph_mark(4);  // argmin merge + gather + straight-through
             // ================= out_proj + residual update + masked accumulate =================
             {
                 const float *bo = WO + D * CD;
                 float q[CD][4], m[4];
 #pragma unroll
-                for (int k = 0; k < CD; ++k)
+                for (int k = 0; k < CD; ++k) {  // lane = frame read (conflict-free), then distribute with shuffles
+                    const float qk = qs[k * TF + lane];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) q[k][j] = __shfl_sync(0xffffffffu, qv[k], frame_of<VEC_ST>(l4, j));
+                    for (int j = 0; j < 4; ++j) q[k][j] = __shfl_sync(0xffffffffu, qk, frame_of<VEC_ST>(l4, j));
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) m[j] = nkeep[frame_of<VEC_ST>(l4, j)] > s ? 1.0f : 0.0f;
                 float *zo = nullptr;
@@ -621,20 +619,22 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                     out_proj_thread<NCH, true, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
                 else
                     out_proj_thread<NCH, false, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
+                ph_mark(6);  // out_proj, thread 0's own work
                 __syncthreads();  // sbest/ze and the weight slot are free again
-                ph_mark(5);  // out_proj
+                ph_mark(5);  // out_proj: barrier wait for the slowest warp
             }
         }  // stages
     }  // tiles
 
     if (ph_on)
         for (int k = 0; k < 8; ++k) p.phase_cycles[(size_t)blockIdx.x * 8 + k] = ph_acc[k];
+    if ((lane & 15) == 0 && p.loss_sum != nullptr && loss_acc != 0.0) atomicAdd(p.loss_sum, loss_acc);
     tmem_fence_before_sync();
     __syncthreads();
     if (w == 0) {
         tmem_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
-        if (lane == 0 && p.loss_sum != nullptr) atomicAdd(p.loss_sum, loss_acc);
+
         if (lane < n_run && p.kept != nullptr && kept_acc != 0ull) atomicAdd(&p.kept[lane], kept_acc);
     }
 }
@@ -781,7 +781,7 @@ int encode(const vrvq_encode_args *a, void *stream) {
         default: rc = VRVQ_EUNSUPPORTED;
     }
     if (dbg && p.phase_cycles != nullptr) {
-        static const char *names[8] = {"tile_setup", "in_proj", "reduce_norm", "search", "merge_gather", "out_proj", "-", "-"};
+        static const char *names[8] = {"tile_setup", "in_proj", "reduce_norm", "search", "merge_gather", "out_proj_barrier", "out_proj_work", "-"};
         long long *h = static_cast<long long *>(malloc(sizeof(long long) * 8 * (size_t)grid));
         cudaStreamSynchronize(st);
         cudaMemcpy(h, p.phase_cycles, sizeof(long long) * 8 * (size_t)grid, cudaMemcpyDeviceToHost);
@@ -789,7 +789,7 @@ int encode(const vrvq_encode_args *a, void *stream) {
         for (int g = 0; g < grid; ++g)
             for (int k = 0; k < 8; ++k) { acc[k] += (double)h[g * 8 + k] / grid; tot += (double)h[g * 8 + k] / grid; }
         fprintf(stderr, "[vrvq phases] mean cycles per CTA: total %.0f |", tot);
-        for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.0f (%.1f%%)", names[k], acc[k], 100.0 * acc[k] / tot);
+        for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %.0f (%.1f%%)", names[k], acc[k], 100.0 * acc[k] / tot);
         fprintf(stderr, "\n");
         free(h);
         cudaFree(p.phase_cycles);
