@@ -70,7 +70,8 @@ struct EncodeSmem {
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
     static constexpr int R_FLOATS = D * TF;  // staging buffer for the next tile's latent
     static constexpr int WB_FLOATS = (cmax(cmax(L.p0_floats(), L.p1_floats()), L.p2_floats()) + 3) / 4 * 4;
-    static constexpr int PART_FLOATS = NW * CD * TF;
+    static constexpr int PART_ROW = 10;  // 8 partial sums per (warp, frame), padded to 10 floats: 8-byte aligned pairs, <=2-way banks
+    static constexpr int PART_FLOATS = NW * TF * PART_ROW;
     static constexpr int OFF_R = 0;
     static constexpr int OFF_WB0 = OFF_R + R_FLOATS;
     static constexpr int OFF_WB1 = OFF_WB0 + WB_FLOATS;
@@ -242,7 +243,8 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
     float *R = smem + S::OFF_R;  // staging: the tile being prefetched
     float *wb0 = smem + S::OFF_WB0;
     float *wb1 = smem + S::OFF_WB1;
-    float *part = smem + S::OFF_PART;  // [NW][CD][TF]; re-used as sbest/sidx after the reduce
+    constexpr int PR = S::PART_ROW;
+    float *part = smem + S::OFF_PART;  // in_proj partial sums [NW][TF][PR]; re-used as sbest/sidx after the reduce
     float *sbest = part;               // [NW][TF]
     int *sidx = reinterpret_cast<int *>(part + NW * TF);
     float *ze = smem + S::OFF_ZE;  // [CD][TF] pre-normalisation latents
@@ -373,8 +375,9 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                 q2[c][f] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8));
             }
         const int c0 = 4 * (g4 >> 1) + 2 * (g4 & 1);
-        row_store4<VEC_ST>(&part[(w * CD + c0) * TF], l4, q2[0][0], q2[0][1], q2[0][2], q2[0][3]);
-        row_store4<VEC_ST>(&part[(w * CD + c0 + 1) * TF], l4, q2[1][0], q2[1][1], q2[1][2], q2[1][3]);
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+            *reinterpret_cast<float2 *>(&part[(w * TF + frame_of<VEC_ST>(l4, f)) * PR + c0]) = make_float2(q2[0][f], q2[1][f]);
     };
 
     for (int it = 0; it < n_my_tiles; ++it) {
@@ -468,42 +471,35 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                 ph_mark(1);  // in_proj (incl. weight wait)
                 // the staging buffer is free once stage 0 has consumed it: prefetch the next tile for the rest of this one
                 if (s == 0 && it + 1 < n_my_tiles) start_tile_load(it + 1);
+                // cross-warp reduce + normalise in one phase: thread = (frame tid>>3, channel tid&7); the 8 channels of a frame sit
+                // in 8 adjacent lanes and are exchanged with shuffles (quantize.py:92 in torch's exact op order)
                 if (tid < CD * TF) {
-                    const int c = w;  // tid >> 5
-                    float sacc = part[c * TF + lane];
+                    const int f = tid >> 3, c = tid & 7, lb = lane & ~7;
+                    float sacc = part[f * PR + c];
 #pragma unroll
-                    for (int ww = 1; ww < NW; ++ww) sacc = __fadd_rn(sacc, part[(ww * CD + c) * TF + lane]);
-                    ze[c * TF + lane] = __fadd_rn(sacc, W[D * CD + c]);
-                }
-                __syncthreads();
-                // normalise (quantize.py:92): torch's exact op order, SURVEY.md A.3
-                if (tid < CD * TF) {
-                    const int c = w;
-                    float x[CD];
+                    for (int ww = 1; ww < NW; ++ww) sacc = __fadd_rn(sacc, part[(ww * TF + f) * PR + c]);
+                    const float xc = __fadd_rn(sacc, W[D * CD + c]);
+                    float ss = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < CD; ++k) x[k] = ze[k * TF + lane];
-                    float ss = __fmul_rn(x[0], x[0]);
-#pragma unroll
-                    for (int k = 1; k < CD; ++k) ss = __fadd_rn(ss, __fmul_rn(x[k], x[k]));
-                    const float den = fmaxf(__fsqrt_rn(ss), 1e-12f);
-                    float xc = x[0];
-#pragma unroll
-                    for (int k = 1; k < CD; ++k) xc = (c == k) ? x[k] : xc;
-                    es[c * TF + lane] = __fmul_rn(2.0f, __fdiv_rn(xc, den));
-                    if (c == 0) {
-                        float e = __fdiv_rn(x[0], den);
-                        float e2 = __fmul_rn(e, e);
-#pragma unroll
-                        for (int k = 1; k < CD; ++k) {
-                            e = __fdiv_rn(x[k], den);
-                            e2 = __fadd_rn(e2, __fmul_rn(e, e));
-                        }
-                        e2s[lane] = e2;
+                    for (int k = 0; k < CD; ++k) {
+                        const float xk = __shfl_sync(0xffffffffu, xc, lb + k);
+                        const float sq = __fmul_rn(xk, xk);
+                        ss = (k == 0) ? sq : __fadd_rn(ss, sq);
                     }
-                    if (p.latents != nullptr && lane < fv)
-                        p.latents[(long long)b * p.lat_sb + (long long)(s * CD + c) * p.lat_sc + t0 + lane] = xc;
+                    const float den = fmaxf(__fsqrt_rn(ss), 1e-12f);
+                    const float ec = __fdiv_rn(xc, den);
+                    const float sqe = __fmul_rn(ec, ec);
+                    float e2 = __shfl_sync(0xffffffffu, sqe, lb);
+#pragma unroll
+                    for (int k = 1; k < CD; ++k) e2 = __fadd_rn(e2, __shfl_sync(0xffffffffu, sqe, lb + k));
+                    ze[c * TF + f] = xc;
+                    es[c * TF + f] = __fmul_rn(2.0f, ec);
+                    if (c == 0) e2s[f] = e2;
                 }
                 __syncthreads();
+                // latents of this stage (pre-normalisation z_e), coalesced: warp c writes channel c
+                if (w < CD && p.latents != nullptr && lane < fv)
+                    p.latents[(long long)b * p.lat_sb + (long long)(s * CD + w) * p.lat_sc + t0 + lane] = ze[w * TF + lane];
                 ph_mark(2);  // cross-warp reduce + normalise
             }
             // ================= search over the normalised codebook =================
