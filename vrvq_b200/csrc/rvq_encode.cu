@@ -288,8 +288,10 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
         mbar_arrive_expect_tx(bar, bytes);
         bulk_g2s((n & 1u) ? wb1 : wb0, src, bytes, bar);
     };
-    auto acquire = [&]() -> const float * {  // all threads, at the start of every phase
-        if (tid == 0 && piece + 1 < n_pieces) issue_piece(piece + 1);
+    // all threads, at the start of every phase: wait for this phase's piece; `prefetch` also issues the next piece into the
+    // other slot, which requires that every thread is done with that slot (i.e. has passed a barrier since its last read).
+    auto acquire = [&](bool prefetch) -> const float * {
+        if (prefetch && tid == 0 && piece + 1 < n_pieces) issue_piece(piece + 1);
         mbar_wait(&bars[piece & 1u], (piece >> 1) & 1u);
         const float *buf = (piece & 1u) ? wb1 : wb0;
         ++piece;
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
             // Thread tile 8 channels-out x 4 frames over its own NCH residual channels (K split 4 ways inside the warp,
             // NW ways across warps).  Stage 0 reads the staged latent and moves it into TMEM on the way.
             {
-                const float *W = acquire();
+                const float *W = acquire(false);  // the other slot (previous out_proj weights) may still be in use: no barrier since
                 float2 a2[CD / 2][4];
 #pragma unroll
                 for (int cp = 0; cp < CD / 2; ++cp) a2[cp][0] = a2[cp][1] = a2[cp][2] = a2[cp][3] = make_float2(0.0f, 0.0f);
@@ -468,6 +470,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                     }
                 scatter_partials(a);
                 __syncthreads();
+                if (tid == 0 && piece < n_pieces) issue_piece(piece);  // search piece; every thread has left the previous out_proj
                 ph_mark(1);  // in_proj (incl. weight wait)
                 // the staging buffer is free once stage 0 has consumed it: prefetch the next tile for the rest of this one
                 if (s == 0 && it + 1 < n_my_tiles) start_tile_load(it + 1);
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
             // LDS.128 is a 2-address broadcast.  The piece is pair-interleaved ([pair][k][2]): one fma.rn.f32x2 advances
             // the dot products of two adjacent codes.
             {
-                const float *CB = acquire();
+                const float *CB = acquire(true);
                 const float *c2 = CB + K * CD;
                 const int f0 = 2 * l2;
                 float2 ea[CD], eb[CD];  // (2e_k, 2e_k) of frame f0 / f0+1
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
             // Half-warp h handles frame f = 2w+h: lane i of the half holds warp i's minimum, a 4-step xor butterfly with the
             // first-index tie rule leaves the winner in every lane, lanes 0..7 fetch the 8 floats of the raw codebook row
             // (one 32-byte sector per frame; quantize.py:81-85,102) and form the straight-through value (quantize.py:73-75).
-            const float *WO = acquire();  // out_proj weights (and kicks off the next stage's in_proj piece)
+            const float *WO = acquire(true);  // out_proj weights (and kicks off the next stage's in_proj piece)
             {
                 const int h = lane >> 4, f = 2 * w + h;
                 float best = sbest[(lane & 15) * TF + f];
@@ -616,10 +619,12 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
                 else
                     out_proj_thread<NCH, false, ZQIS, VEC_ST>(wp, bp, q, m, tR, tA, zo, zstep, zq, zqstep, l4, fv);
                 ph_mark(6);  // out_proj, thread 0's own work
-                __syncthreads();  // sbest/ze and the weight slot are free again
-                ph_mark(5);  // out_proj: barrier wait for the slowest warp
+                // No barrier here: the next stage's in_proj only touches thread-private TMEM columns, its own weight slot and (after
+                // its own barrier) `part`; the out_proj weight slot is refilled only after that barrier (see in_proj above).
+                ph_mark(5);  // out_proj
             }
         }  // stages
+        __syncthreads();  // end of tile: nkeep / qs / the exchange buffers are rewritten by the next tile's setup
     }  // tiles
 
     if (ph_on)
