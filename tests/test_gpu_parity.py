@@ -258,3 +258,58 @@ def test_error_behaviour():
         cbr.from_codes(torch.full((1, 8, 4), 1024, dtype=torch.int64).cuda())
     e = cbr(torch.zeros(0, 1024, 7).cuda())
     assert e["codes"].shape == (0, 8, 7) and e["z_q"].shape == (0, 1024, 7)
+
+
+@pytest.mark.parametrize("D,Nq", [(256, 4), (512, 5), (1024, 32)])
+def test_other_input_dims_and_stage_counts_against_oracle(D, Nq):
+    """Every kernel instantiation (D in {256, 512, 1024}) and the largest supported stage count, VBR with z_q_is."""
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(100 + D + Nq, Nq, D))
+    w = c_oracle.OracleWeights.from_state_dict(sd)
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    B, T = 2, 70
+    z_np = gi.make_latents(7 + D, B, D, T, 0.8)
+    imp_np = gi.make_imp_map(8 + D, B, T)
+    lv = torch.tensor([0.4, 1.3], device="cuda")
+    o = c_oracle.encode(w, z_np, None, imp_np, np.array([0.4, 1.3], np.float32))
+    out = ops.rvq_encode(pw, torch.from_numpy(z_np).cuda(), None, torch.from_numpy(imp_np).cuda(), lv, want_z_q_is=True)
+    excused, skip = H.assert_codes_match(w, o, npy(out.codes), max_excused_frac=0.02)
+    assert np.array_equal(npy(out.mask), o["mask"]) and np.array_equal(npy(out.kept), o["kept"])
+    H.assert_close_frames(npy(out.z_q), o["z_q"], skip=skip, what="z_q")
+    H.assert_close_frames(npy(out.z_q_is).reshape(B, -1, T), o["z_q_is"].reshape(B, -1, T), skip=skip, what="z_q_is")
+    H.assert_close_frames(npy(out.latents), o["latents"], skip=skip, what="latents")
+
+
+def test_unsupported_shapes_fail_loudly():
+    import vrvq_b200
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(3, 33, 256))
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    with pytest.raises(vrvq_b200.VrvqError, match="n_run"):  # more than 32 stages
+        ops.rvq_encode(pw, torch.zeros(1, 256, 8, device="cuda"))
+    sd = gi.torch_state_dict(gi.make_state_dict(3, 2, 384))
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    assert not pw.supported()
+    with pytest.raises(vrvq_b200.VrvqError, match="no kernel"):
+        ops.rvq_encode(pw, torch.zeros(1, 384, 8, device="cuda"))
+    sd = gi.torch_state_dict(gi.make_state_dict(3, 2, 256))
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    with pytest.raises(vrvq_b200.VrvqError):  # non-unit stride along T
+        ops.rvq_encode(pw, torch.zeros(1, 256, 16, device="cuda")[:, :, ::2])
+    with pytest.raises(vrvq_b200.VrvqError):  # wrong dtype
+        ops.rvq_encode(pw, torch.zeros(1, 256, 8, device="cuda", dtype=torch.float16))
+
+
+def test_padded_z_q_is_rows_extension_gives_identical_values():
+    case = gi.CASES["vbr_d1024_nq8"]
+    m = build_module(case)
+    z = torch.from_numpy(H.latents_for(case)).cuda()
+    imp = torch.from_numpy(gi.make_imp_map(case["imp_seed"], case["B"], case["T"])).cuda()
+    a = m(z, level=0.5, imp_map=imp)
+    m.pad_z_q_is_rows = True
+    b = m(z, level=0.5, imp_map=imp)
+    assert b["z_q_is"].shape == a["z_q_is"].shape and b["z_q_is"].stride(2) % 32 == 0 and not b["z_q_is"].is_contiguous()
+    for k in ("z_q", "z_q_is", "codes", "latents", "mask_imp"):
+        assert torch.equal(a[k], b[k]), k

@@ -1,0 +1,68 @@
+"""CPU property tests (hypothesis) of the oracle and the host logic: per-frame independence, mask monotonicity,
+CBR prefix property, shard plans."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import c_oracle
+from tests.golden import gen_inputs as gi
+from vrvq_b200 import sharding
+
+_W = {}
+
+
+def weights(Nq=3, D=64):
+    key = (Nq, D)
+    if key not in _W:
+        _W[key] = c_oracle.OracleWeights.from_state_dict(gi.torch_state_dict(gi.make_state_dict(5, Nq, D, 1024)))
+    return _W[key]
+
+
+@settings(max_examples=15, deadline=None)
+@given(seed=st.integers(0, 10_000), B=st.integers(1, 3), T=st.integers(1, 40), level=st.floats(0.05, 3.0))
+def test_oracle_is_per_frame_independent_and_masks_are_prefixes(seed, B, T, level):
+    w = weights()
+    z = gi.make_latents(seed, B, 64, T, 1.0)
+    imp = gi.make_imp_map(seed + 1, B, T)
+    full = c_oracle.encode(w, z, None, imp, level)
+    # mask is a prefix of ones per frame and matches the standalone utility on imp*level*Nq (two fp32 multiplies)
+    assert (full["mask"][:, 1:, :] <= full["mask"][:, :-1, :]).all()
+    x = (imp * np.float32(level)).astype(np.float32) * np.float32(3)
+    assert np.array_equal(full["mask"], c_oracle.generate_mask_hard(x, 3))
+    assert np.array_equal(full["kept"], full["mask"].sum(axis=(0, 2)).astype(np.int64))
+    # any frame window re-encoded alone reproduces the same outputs bit-for-bit (no halo)
+    b, t0 = seed % B, seed % T
+    t1 = min(T, t0 + 1 + seed % 5)
+    part = c_oracle.encode(w, z[b:b + 1, :, t0:t1], None, imp[b:b + 1, :, t0:t1], level)
+    assert np.array_equal(part["codes"], full["codes"][b:b + 1, :, t0:t1])
+    assert np.array_equal(part["z_q"], full["z_q"][b:b + 1, :, t0:t1])
+    # z_q is the masked, ascending-stage sum of z_q_is
+    acc = np.zeros_like(full["z_q"])
+    for k in range(3):
+        acc = acc + full["z_q_is"][:, k] * full["mask"][:, k:k + 1, :]
+    assert np.array_equal(acc, full["z_q"])
+
+
+@settings(max_examples=10, deadline=None)
+@given(seed=st.integers(0, 10_000), n=st.integers(1, 3))
+def test_cbr_early_exit_is_a_prefix_of_the_full_run(seed, n):
+    w = weights()
+    z = gi.make_latents(seed, 2, 64, 9, 1.0)
+    full, part = c_oracle.encode(w, z, None), c_oracle.encode(w, z, n)
+    assert np.array_equal(part["codes"], full["codes"][:, :n]) and np.array_equal(part["latents"], full["latents"][:, :8 * n])
+    zq, zp, zqis = c_oracle.from_codes(w, part["codes"], True)
+    assert np.allclose(zq, part["z_q"], rtol=0, atol=1e-5 * np.abs(part["z_q"]).max())
+    zq2, zp2, codes2 = c_oracle.from_latents(w, part["latents"])
+    assert np.array_equal(codes2, part["codes"]) and np.array_equal(zp2, zp)
+
+
+@settings(max_examples=60, deadline=None)
+@given(B=st.integers(0, 40), T=st.integers(0, 700), world=st.integers(1, 9))
+def test_shard_plans_cover_exactly_once(B, T, world):
+    plan = sharding.plan_shards(B, T, world)
+    seen = np.zeros((B, T), np.int32)
+    for segs in plan:
+        for s in segs:
+            seen[s.b, s.t0:s.t1] += 1
+    assert (seen == 1).all()
+    units = [sharding.merge_whole_items(segs, T) for segs in plan]
+    assert sum((u[2] - u[1]) * T if u[0] == "items" else u[3] - u[2] for us in units for u in us) == B * T

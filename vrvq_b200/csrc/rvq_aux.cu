@@ -48,37 +48,65 @@ __global__ void mask_sum_kernel(const float *__restrict__ mask, long long m_sb, 
 // with mask from imp_map * level_scaled.  One thread per (b,d,t); the Nq reads per output are each
 // coalesced along t.  grid.x covers t in chunks, grid.y = d-blocks, grid.z = b.
 // ---------------------------------------------------------------------------------------------
-constexpr int RM_DPB = 8;  // channels per CTA row-group
+constexpr int RM_DPB = 8;  // channels per CTA row-group (one warp each)
+// VEC consecutive frames per lane (widest access every row start allows), one warp per channel row, Nq independent
+// streaming loads in flight per lane; the mask / kept outputs are produced by the warps of the blockIdx.y == 0 row-group.
+template <int VEC>
 __global__ void __launch_bounds__(256) remask_kernel(const float *__restrict__ zis, long long s_b, long long s_q, long long s_d,
                                                      const float *__restrict__ imp, long long imp_sb, float level_scaled, int D, int T,
                                                      int nq, float *__restrict__ zq, long long zq_sb, long long zq_sd,
                                                      float *__restrict__ mask, long long m_sb, long long m_sq,
                                                      unsigned long long *__restrict__ kept) {
     const int b = blockIdx.z;
-    const int t = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int dr = threadIdx.x >> 5;  // 0..7
-    int nk = 0;
-    if (t < T) {
-        const float x = __fmul_rn(imp[(long long)b * imp_sb + t], level_scaled);
-        for (int k = 0; k < nq; ++k) nk += (__fsub_rn(x, (float)k) >= 0.0f) ? 1 : 0;
+    const int lane = threadIdx.x & 31, dr = threadIdx.x >> 5;
+    const int t = (blockIdx.x * 32 + lane) * VEC;
+    int nk[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        nk[e] = 0;
+        if (t + e < T) {
+            const float x = __fmul_rn(imp[(long long)b * imp_sb + t + e], level_scaled);
+            for (int k = 0; k < nq; ++k) nk[e] += (__fsub_rn(x, (float)k) >= 0.0f) ? 1 : 0;
+        }
     }
     if (blockIdx.y == 0 && dr == 0) {  // one warp per (b, t-chunk) owns the mask / kept outputs
         for (int k = 0; k < nq; ++k) {
-            const bool on = nk > k;
-            const unsigned bal = __ballot_sync(0xffffffffu, on);
-            if ((threadIdx.x & 31) == 0 && kept != nullptr && bal) atomicAdd(&kept[k], (unsigned long long)__popc(bal));
-            if (mask != nullptr && t < T) mask[(long long)b * m_sb + (long long)k * m_sq + t] = on ? 1.0f : 0.0f;
+            int cnt = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const bool on = nk[e] > k;
+                cnt += on ? 1 : 0;
+                if (mask != nullptr && t + e < T) mask[(long long)b * m_sb + (long long)k * m_sq + t + e] = on ? 1.0f : 0.0f;
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0 && kept != nullptr && cnt) atomicAdd(&kept[k], (unsigned long long)cnt);
         }
     }
-    if (t >= T) return;
+    if (t >= T) return;  // T % VEC == 0 whenever VEC > 1, so a lane is entirely valid or entirely out of range
     for (int d = blockIdx.y * RM_DPB + dr; d < D; d += gridDim.y * RM_DPB) {
         const float *src = zis + (long long)b * s_b + (long long)d * s_d + t;
-        float acc = 0.0f;
+        float acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
+#pragma unroll 4
         for (int k = 0; k < nq; ++k) {
-            const float v = __ldcs(src + (long long)k * s_q);
-            acc = __fmaf_rn(k < nk ? 1.0f : 0.0f, v, acc);  // reference multiplies by the 0/1 mask, then sums over k
+            float v[VEC];
+            if (VEC == 4) {
+                const float4 q = __ldcs(reinterpret_cast<const float4 *>(src + (long long)k * s_q));
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            } else if (VEC == 2) {
+                const float2 q = __ldcs(reinterpret_cast<const float2 *>(src + (long long)k * s_q));
+                v[0] = q.x; v[1] = q.y;
+            } else {
+                v[0] = __ldcs(src + (long long)k * s_q);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = __fmaf_rn(k < nk[e] ? 1.0f : 0.0f, v[e], acc[e]);  // mask multiply, ascending-k sum
         }
-        __stcs(zq + (long long)b * zq_sb + (long long)d * zq_sd + t, acc);
+        float *o = zq + (long long)b * zq_sb + (long long)d * zq_sd + t;
+        if (VEC == 4) __stcs(reinterpret_cast<float4 *>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+        else if (VEC == 2) __stcs(reinterpret_cast<float2 *>(o), make_float2(acc[0], acc[1]));
+        else __stcs(o, acc[0]);
     }
 }
 
@@ -106,9 +134,16 @@ struct FromCodesParams {
 
 constexpr int FC_NT = 256;
 constexpr int FC_DCH = 128;  // channels handled per CTA (grid.y covers D / FC_DCH)
+constexpr int FC_SG = 8;     // stages whose W_out chunk is staged in shared memory at a time
+// Shared memory: gathered rows qs[n_run<=32][8][32] (padded), masks ms[32][32], W_out/b_out chunk for FC_SG stages of
+// this CTA's FC_DCH channels.  Thread = 4 consecutive frames x 4 channels (dd = 16i + 4w' + g4); per stage it loads its
+// 32 q values once (8 LDS.128) and then runs 4 x 32 FMAs on quarter-uniform broadcast reads of W_out.
 __global__ void __launch_bounds__(FC_NT) from_codes_kernel(const FromCodesParams p) {
-    __shared__ float qs[32][CD][33];  // [stage (<=32)][k][frame], padded
-    __shared__ float ms[32][33];
+    extern __shared__ __align__(16) float fc_smem[];  // sized by the launcher: n_run*(256+32) + FC_SG*FC_DCH*(CD+1) floats
+    float(*qs)[CD][32] = reinterpret_cast<float(*)[CD][32]>(fc_smem);
+    float(*ms)[32] = reinterpret_cast<float(*)[32]>(fc_smem + p.n_run * CD * 32);
+    float(*wsm)[FC_DCH][CD] = reinterpret_cast<float(*)[FC_DCH][CD]>(fc_smem + p.n_run * (CD * 32 + 32));
+    float(*bsm)[FC_DCH] = reinterpret_cast<float(*)[FC_DCH]>(fc_smem + p.n_run * (CD * 32 + 32) + FC_SG * FC_DCH * CD);
     const int tile = blockIdx.x;
     const int b = tile / p.tiles_per_b, t0 = (tile % p.tiles_per_b) * 32;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -134,51 +169,80 @@ __global__ void __launch_bounds__(FC_NT) from_codes_kernel(const FromCodesParams
         }
         ms[s][lane] = (p.mask != nullptr && valid) ? p.mask[(long long)b * p.m_sb + (long long)s * p.m_sq + t] : 1.0f;
     }
-    __syncthreads();
-    // thread = 4 consecutive frames x one channel at a time; the 4 quarter-warps of a warp take 4 adjacent channels, so the
-    // W_out row reads are quarter-uniform broadcasts and each row store is 8 lanes x 16 B contiguous.
     const int l4 = lane & 7, g4 = lane >> 3;
     const int tq = t0 + 4 * l4;
     const int nvalid = max(0, min(4, p.T - tq));
     const bool vec4 = (nvalid == 4) && ((p.zq_sd & 3) == 0) && ((p.zq_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.z_q) & 15) == 0) &&
                       (p.z_q_is == nullptr || (((p.zqis_sd | p.zqis_sq | p.zqis_sb) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.z_q_is) & 15) == 0));
     const int d_begin = blockIdx.y * FC_DCH;
-    for (int dd = 4 * w + g4; dd < FC_DCH; dd += 4 * (FC_NT / 32)) {
-        const int d = d_begin + dd;
-        if (d >= p.D) break;
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (int s = 0; s < p.n_run; ++s) {
-            const float *wo = stages + (size_t)s * p.stage_floats + p.off_p2 + (size_t)d * CD;
-            const float4 wa = __ldg(reinterpret_cast<const float4 *>(wo));
-            const float4 wb = __ldg(reinterpret_cast<const float4 *>(wo + 4));
-            const float wv[CD] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-            const float bias = __ldg(stages + (size_t)s * p.stage_floats + p.off_p2 + (size_t)p.D * CD + d);
-            float v[4] = {bias, bias, bias, bias};
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+    for (int s0 = 0; s0 < p.n_run; s0 += FC_SG) {
+        const int ns = min(FC_SG, p.n_run - s0);
+        __syncthreads();  // gather done (first pass) / previous chunk consumed
+        for (int i = threadIdx.x; i < ns * FC_DCH * CD / 4; i += FC_NT) {  // W_out rows of this chunk, 16 bytes per thread
+            const int sl = i / (FC_DCH * CD / 4), r = i % (FC_DCH * CD / 4);
+            const int d = d_begin + (r * 4) / CD;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d < p.D) v = __ldg(reinterpret_cast<const float4 *>(stages + (size_t)(s0 + sl) * p.stage_floats + p.off_p2 + (size_t)d_begin * CD) + r);
+            reinterpret_cast<float4 *>(&wsm[sl][0][0])[r] = v;
+        }
+        for (int i = threadIdx.x; i < ns * FC_DCH; i += FC_NT) {
+            const int sl = i / FC_DCH, dd = i % FC_DCH;
+            bsm[sl][dd] = (d_begin + dd < p.D) ? __ldg(stages + (size_t)(s0 + sl) * p.stage_floats + p.off_p2 + (size_t)p.D * CD + d_begin + dd) : 0.0f;
+        }
+        __syncthreads();
+        for (int sl = 0; sl < ns; ++sl) {
+            const int s = s0 + sl;
+            float q[CD][4];
 #pragma unroll
             for (int k = 0; k < CD; ++k) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = __fmaf_rn(wv[k], qs[s][k][4 * l4 + j], v[j]);
+                const float4 qv = *reinterpret_cast<const float4 *>(&qs[s][k][4 * l4]);
+                q[k][0] = qv.x; q[k][1] = qv.y; q[k][2] = qv.z; q[k][3] = qv.w;
             }
-            if (p.z_q_is != nullptr) {
-                float *o = p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + (long long)d * p.zqis_sd + tq;
-                if (vec4) {
-                    __stcs(reinterpret_cast<float4 *>(o), make_float4(v[0], v[1], v[2], v[3]));
-                } else {
+            const float4 mv = *reinterpret_cast<const float4 *>(&ms[s][4 * l4]);
+            const float m[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < nvalid) __stcs(o + j, v[j]);
+            for (int i = 0; i < 4; ++i) {
+                const int dd = 32 * i + 4 * w + g4;
+                const float4 wa = *reinterpret_cast<const float4 *>(&wsm[sl][dd][0]);
+                const float4 wb = *reinterpret_cast<const float4 *>(&wsm[sl][dd][4]);
+                const float wv[CD] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                const float bias = bsm[sl][dd];
+                float v[4] = {bias, bias, bias, bias};
+#pragma unroll
+                for (int k = 0; k < CD; ++k) {  // bias-initialised ascending-k chain, as in the encode kernel and the oracle
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = __fmaf_rn(wv[k], q[k][j], v[j]);
                 }
-            }
+                const int d = d_begin + dd;
+                if (p.z_q_is != nullptr && d < p.D) {
+                    float *o = p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + (long long)d * p.zqis_sd + tq;
+                    if (vec4) {
+                        __stcs(reinterpret_cast<float4 *>(o), make_float4(v[0], v[1], v[2], v[3]));
+                    } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = __fmaf_rn(ms[s][4 * l4 + j], v[j], acc[j]);
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nvalid) __stcs(o + j, v[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(m[j], v[j], acc[i][j]);  // ascending stage order from 0
+            }
         }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int d = d_begin + 32 * i + 4 * w + g4;
+        if (d >= p.D) continue;
         float *o = p.z_q + (long long)b * p.zq_sb + (long long)d * p.zq_sd + tq;
         if (vec4) {
-            __stcs(reinterpret_cast<float4 *>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+            __stcs(reinterpret_cast<float4 *>(o), make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (j < nvalid) __stcs(o + j, acc[j]);
+                if (j < nvalid) __stcs(o + j, acc[i][j]);
         }
     }
 }
@@ -296,11 +360,21 @@ int launch_remask(const float *zis, long long s_b, long long s_q, long long s_d,
         set_error("vrvq_remask_f32: B must be <= 65535");
         return VRVQ_EUNSUPPORTED;
     }
-    const int tx = (T + 31) / 32;
+    auto ok = [&](int v) {
+        return T % v == 0 && reinterpret_cast<uintptr_t>(zis) % (4 * v) == 0 && reinterpret_cast<uintptr_t>(zq) % (4 * v) == 0 && s_b % v == 0 &&
+               s_q % v == 0 && s_d % v == 0 && zq_sb % v == 0 && zq_sd % v == 0;
+    };
+    const int vec = ok(4) ? 4 : ok(2) ? 2 : 1;
+    const int tx = (T + 32 * vec - 1) / (32 * vec);
     int dy = (D + RM_DPB - 1) / RM_DPB;
-    if (dy > 65535) dy = 65535;
-    remask_kernel<<<dim3(tx, dy, B), 256, 0, st>>>(zis, s_b, s_q, s_d, imp, imp_sb, level_scaled, D, T, nq, zq, zq_sb, zq_sd, mask, m_sb,
-                                                   m_sq, kept);
+    if (dy > 64) dy = 64;  // each warp then walks D / (8 * 64) channel rows; plenty of CTAs (tx * 64 * B) for 148 SMs
+    const dim3 grid(tx, dy, B);
+    if (vec == 4)
+        remask_kernel<4><<<grid, 256, 0, st>>>(zis, s_b, s_q, s_d, imp, imp_sb, level_scaled, D, T, nq, zq, zq_sb, zq_sd, mask, m_sb, m_sq, kept);
+    else if (vec == 2)
+        remask_kernel<2><<<grid, 256, 0, st>>>(zis, s_b, s_q, s_d, imp, imp_sb, level_scaled, D, T, nq, zq, zq_sb, zq_sd, mask, m_sb, m_sq, kept);
+    else
+        remask_kernel<1><<<grid, 256, 0, st>>>(zis, s_b, s_q, s_d, imp, imp_sb, level_scaled, D, T, nq, zq, zq_sb, zq_sd, mask, m_sb, m_sq, kept);
     return check_cuda(cudaGetLastError(), "remask_kernel launch");
 }
 
@@ -359,7 +433,15 @@ int launch_from_codes(const vrvq_from_codes_args *a, cudaStream_t st) {
         return VRVQ_EUNSUPPORTED;
     }
     const int gy = (a->input_dim + FC_DCH - 1) / FC_DCH;
-    from_codes_kernel<<<dim3((unsigned)tiles, gy), FC_NT, 0, st>>>(p);
+    const int smem = (int)sizeof(float) * (a->n_run * (CD * 32 + 32) + FC_SG * FC_DCH * (CD + 1));
+    static int smem_allowed = 48 * 1024;
+    if (smem > smem_allowed) {
+        int rc = check_cuda(cudaFuncSetAttribute(from_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024),
+                            "cudaFuncSetAttribute(from_codes_kernel)");
+        if (rc) return rc;
+        smem_allowed = 96 * 1024;
+    }
+    from_codes_kernel<<<dim3((unsigned)tiles, gy), FC_NT, smem, st>>>(p);
     return check_cuda(cudaGetLastError(), "from_codes_kernel launch");
 }
 

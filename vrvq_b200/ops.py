@@ -84,11 +84,17 @@ def _check_view(t: torch.Tensor, name: str):
 class EncodeOutputs:
     """Pre-allocated outputs + accumulators of one encode call (re-usable across calls of equal shape)."""
 
-    def __init__(self, B, D, T, n_run, device, z_q=True, z_q_is=False, latents=True, mask=True, loss_pf=False):
+    def __init__(self, B, D, T, n_run, device, z_q=True, z_q_is=False, latents=True, mask=True, loss_pf=False, pad_z_q_is_rows=False):
         f32 = dict(dtype=torch.float32, device=device)
         self.codes = torch.empty((B, n_run, T), dtype=torch.int64, device=device)
         self.z_q = torch.empty((B, D, T), **f32) if z_q else None
-        self.z_q_is = torch.empty((B, n_run, D, T), **f32) if z_q_is else None
+        if z_q_is and pad_z_q_is_rows and T % TILE_FRAMES:
+            # opt-in: row pitch rounded up to a tile (128 bytes), returned as a [..., :T] view.  Every row then starts on a
+            # cache line, which removes the partial-sector stores of a T like 862 (DESIGN.md section 4, "Stores").
+            tp = (T + TILE_FRAMES - 1) // TILE_FRAMES * TILE_FRAMES
+            self.z_q_is = torch.empty((B, n_run, D, tp), **f32)[..., :T]
+        else:
+            self.z_q_is = torch.empty((B, n_run, D, T), **f32) if z_q_is else None
         self.latents = torch.empty((B, CD * n_run, T), **f32) if latents else None
         self.mask = torch.empty((B, n_run, T), **f32) if mask else None
         self.loss_pf = torch.empty((B, n_run, T), **f32) if loss_pf else None

