@@ -90,8 +90,14 @@ class ResidualVectorQuantize(nn.Module):
 
     # ---- weights ----
     def packed_weights(self, device) -> ops.PackedWeights:
-        """Fold weight-norm on the CPU (bit-identical to the reference's hook) and pack once per parameter version."""
-        key = (tuple(_param_key(q) for q in self.quantizers), str(device))
+        """Fold weight-norm on the CPU (bit-identical to the reference's hook) and pack once per parameter version.
+        The per-call check is cheap: the in-place version counters of all stage parameters plus one storage address
+        (module.to() / load_state_dict move or rewrite all of them together)."""
+        plist = self.__dict__.get("_plist")
+        if plist is None or len(plist) != 7 * len(self.quantizers):
+            plist = [p for q in self.quantizers for p in q.parameters()]
+            self.__dict__["_plist"] = plist
+        key = (tuple(p._version for p in plist), plist[0].data_ptr(), plist[-1].data_ptr(), device)
         if self._packed is None or self._packed_key != key:
             cols = list(zip(*[q.folded() for q in self.quantizers]))
             self._packed = ops.PackedWeights(*[torch.stack(c) for c in cols], device=device)
