@@ -37,7 +37,7 @@ def test_config3_nq28_against_oracle_subset():
 
 def test_config4_long_form_shard_properties():
     """60 s items (T=5168): one 8-GPU shard's worth of batch (B=32 would be 677 MB; B=8 here) -- frame-split and batch-split
-    launches reproduce the single launch bit-for-bit, z_q = sum of masked z_q_is, kept counts match the mask."""
+    launches reproduce the single launch bit-for-bit, z_q = sum of masked z_q_is (fp32 tolerance), kept counts match the mask."""
     from vrvq_b200 import ops, sharding
 
     sd = gi.torch_state_dict(gi.make_state_dict(81, 8, 1024))
@@ -47,11 +47,12 @@ def test_config4_long_form_shard_properties():
     z = torch.randn(B, 1024, T, generator=g).cuda()
     imp = torch.rand(B, 1, T, generator=g).cuda()
     full = ops.rvq_encode(pw, z, None, imp, 0.7, want_z_q_is=True)
-    # (1) masked sum of the per-stage outputs, ascending stage order, equals the fused z_q exactly
+    # (1) masked sum of the per-stage outputs, ascending stage order (quantize.py:421), equals the fused z_q within the fp32
+    # tolerance (the fused z_q is one tensor-core GEMM over the kept stages, not a sum of the rounded stage outputs)
     acc = torch.zeros_like(full.z_q)
     for k in range(8):
-        acc = torch.addcmul(acc, full.z_q_is[:, k], full.mask[:, k:k + 1, :].expand(-1, 1024, -1)) if False else acc + full.z_q_is[:, k] * full.mask[:, k:k + 1, :]
-    assert torch.equal(acc, full.z_q)
+        acc = acc + full.z_q_is[:, k] * full.mask[:, k:k + 1, :]
+    H.assert_close_frames(npy(full.z_q), npy(acc), what="fused z_q vs masked sum of z_q_is")
     # (2) kept counts == column sums of the mask; mask is a prefix of ones per frame
     assert torch.equal(full.kept, full.mask.sum(dim=(0, 2)).to(torch.int64))
     assert bool((full.mask[:, 1:, :] <= full.mask[:, :-1, :]).all())
@@ -87,4 +88,5 @@ def test_remask_level_sweep_matches_fused_encode():
     for level in (0.25, 0.5, 1.0, 2.0):  # powers of two: imp*level*8 == imp*(level*8) bit-for-bit
         fused = ops.rvq_encode(pw, z, None, imp, level, want_z_q_is=False)
         zq, mask, kept = ops.remask(base.z_q_is, imp, level * 8)
-        assert torch.equal(mask, fused.mask) and torch.equal(zq, fused.z_q) and torch.equal(kept, fused.kept)
+        assert torch.equal(mask, fused.mask) and torch.equal(kept, fused.kept)
+        H.assert_close_frames(npy(zq), npy(fused.z_q), what=f"re-masked z_q at level {level}")

@@ -196,7 +196,8 @@ def test_config2_shape_against_oracle():
         assert np.array_equal(npy(mk2), ref_mask)
         same = np.array_equal(ref_mask, o["mask"])
         if same:
-            assert torch.equal(zq2, out.z_q), "re-masked z_q must equal the fused z_q bit-for-bit"
+            # the fused z_q is one tensor-core GEMM over all kept stages, the re-mask sums the stored fp32 stage outputs
+            H.assert_close_frames(npy(zq2), npy(out.z_q), what="re-masked z_q vs fused z_q")
             assert np.array_equal(npy(kept2), o["kept"])
     print(f"config-2 shape: {total_excused} audited near-tie frame(s) of {3 * B * T}")
 

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvrvq.so")
-SOURCES = ["abi.cu", "rvq_encode.cu", "rvq_aux.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "vrvq.h")]
+SOURCES = ["abi.cu", "rvq_encode.cu", "rvq_encode_tc.cu", "rvq_aux.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "encode_params.cuh"), os.path.join(os.path.dirname(HERE), "include", "vrvq.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

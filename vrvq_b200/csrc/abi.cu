@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 
 #include "common.cuh"
 
@@ -74,6 +75,77 @@ static void normalize_row(const float *x, float *e, float *c2) {
     *c2 = s2;
 }
 
+
+// round-to-nearest (ties away from zero, like cvt.rna.tf32.f32) TF32 head of x; x - head is exact in fp32
+static float tf32_head(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;  // inf / nan
+    u = (u + 0x1000u) & 0xffffe000u;
+    float h;
+    memcpy(&h, &u, 4);
+    return h;
+}
+
+// element (row r, k) of a canonical K-major UMMA tile with R rows (common.cuh)
+static inline size_t umma_idx(int R, int r, int k) { return ((size_t)(k / 4) * R + r) * 4 + (k % 4); }
+
+// Tensor-core section of the blob (layout: common.cuh TcLayout).  w_in [Nq][8][D], w_out [Nq][D][8], b_out [Nq][D].
+static void pack_tc_section(int Nq, int D, const float *w_in, const float *b_in, const float *w_out, const float *b_out, float *tc) {
+    const TcLayout T(D, Nq);
+    memset(tc, 0, sizeof(float) * (size_t)T.total());
+    // WIN: chunk c = channels 32c..32c+31 (k = channel - 32c); rows 0..63 heads (row = 8*stage + out-channel), rows 64..127 remainders
+    for (int c = 0; c < T.nch(); ++c) {
+        float *tile = tc + T.off_win() + (size_t)c * 4096;
+        for (int s = 0; s < Nq; ++s)
+            for (int oc = 0; oc < CD; ++oc)
+                for (int k = 0; k < 32; ++k) {
+                    const float x = w_in[((size_t)s * CD + oc) * D + 32 * c + k];
+                    const float h = tf32_head(x);
+                    tile[umma_idx(128, 8 * s + oc, k)] = h;
+                    tile[umma_idx(128, 64 + 8 * s + oc, k)] = x - h;
+                }
+    }
+    // WOUT / BOUT: row i of chunk j <-> channel 128j + 4(i%32) + i/32
+    for (int j = 0; j < T.nj(); ++j)
+        for (int i = 0; i < 128; ++i) {
+            const int ch = 128 * j + 4 * (i % 32) + i / 32;
+            for (int s = 0; s < Nq; ++s) {
+                float *hi = tc + T.off_wout() + ((size_t)s * T.nj() + j) * 3072, *lo = hi + 1024, *bt = hi + 2048;
+                for (int k = 0; k < CD; ++k) {
+                    const float x = w_out[((size_t)s * D + ch) * CD + k];
+                    const float h = tf32_head(x);
+                    hi[umma_idx(128, i, k)] = h;
+                    lo[umma_idx(128, i, k)] = x - h;
+                }
+                const float bv = b_out[(size_t)s * D + ch];
+                const float bh = tf32_head(bv);
+                bt[umma_idx(128, i, 0)] = bh;
+                bt[umma_idx(128, i, 1)] = bv - bh;
+                float *bhi = tc + T.off_bout() + (size_t)j * 2048, *blo = bhi + 1024;
+                bhi[umma_idx(128, i, s)] = bh;
+                blo[umma_idx(128, i, s)] = bv - bh;
+            }
+        }
+    // GG: for j < s: G = W_in[s] W_out[j] (8x8) and g = W_in[s] b_out[j], accumulated in binary64, rounded once
+    for (int j = 0; j < Nq; ++j)
+        for (int s = j + 1; s < Nq; ++s) {
+            float *G = tc + T.off_gg() + (size_t)TcLayout::pair_index(Nq, j, s) * 72;
+            for (int c = 0; c < CD; ++c) {
+                const float *wi = w_in + ((size_t)s * CD + c) * D;
+                for (int k = 0; k < CD; ++k) {
+                    double acc = 0.0;
+                    for (int d = 0; d < D; ++d) acc += (double)wi[d] * (double)w_out[((size_t)j * D + d) * CD + k];
+                    G[c * 8 + k] = (float)acc;
+                }
+                double acc = 0.0;
+                for (int d = 0; d < D; ++d) acc += (double)wi[d] * (double)b_out[(size_t)j * D + d];
+                G[64 + c] = (float)acc;
+            }
+        }
+    memcpy(tc + T.off_bin(), b_in, sizeof(float) * (size_t)Nq * CD);
+}
+
 }  // namespace vrvq
 
 using namespace vrvq;
@@ -89,7 +161,9 @@ int vrvq_supported(int input_dim, int codebook_size, int codebook_dim) { return 
 size_t vrvq_blob_bytes(int n_codebooks, int input_dim, int codebook_size, int codebook_dim) {
     if (n_codebooks <= 0 || input_dim <= 0 || codebook_size <= 0 || codebook_dim != CD) return 0;
     const BlobLayout L(input_dim, codebook_size);
-    return sizeof(float) * ((size_t)BLOB_HDR_FLOATS + (size_t)n_codebooks * (size_t)L.stage_floats());
+    size_t floats = (size_t)BLOB_HDR_FLOATS + (size_t)n_codebooks * (size_t)L.stage_floats();
+    if (tc_shape_ok(input_dim, codebook_size, n_codebooks)) floats += (size_t)TcLayout(input_dim, n_codebooks).total();
+    return sizeof(float) * floats;
 }
 
 int vrvq_pack_weights(int n_codebooks, int input_dim, int codebook_size, int codebook_dim, const float *w_in, const float *b_in,
@@ -123,6 +197,10 @@ int vrvq_pack_weights(int n_codebooks, int input_dim, int codebook_size, int cod
     h.input_dim = D;
     h.codebook_size = K;
     h.stage_floats = L.stage_floats();
+    const bool tc = tc_shape_ok(D, K, n_codebooks);
+    const size_t tc_off = (size_t)BLOB_HDR_FLOATS + (size_t)n_codebooks * (size_t)L.stage_floats();
+    h.pad[0] = tc ? (int32_t)tc_off : 0;  // tensor-core section (rvq_encode_tc.cu), 0 = absent
+    h.pad[1] = tc ? TcLayout(D, n_codebooks).total() : 0;
     memcpy(blob, &h, sizeof(h));
     for (int s = 0; s < n_codebooks; ++s) {
         float *st = blob + BLOB_HDR_FLOATS + (size_t)s * L.stage_floats();
@@ -141,6 +219,7 @@ int vrvq_pack_weights(int n_codebooks, int input_dim, int codebook_size, int cod
         memcpy(p2 + (size_t)D * CD, b_out + (size_t)s * D, sizeof(float) * D);
         memcpy(raw, cb, sizeof(float) * (size_t)K * CD);
     }
+    if (tc) pack_tc_section(n_codebooks, D, w_in, b_in, w_out, b_out, blob + tc_off);
     return VRVQ_OK;
 }
 

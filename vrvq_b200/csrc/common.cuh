@@ -122,6 +122,82 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
 
+// ---- tensor-core path (rvq_encode_tc.cu): extra blob section + tcgen05.mma helpers -------------------------------
+// The TC section is appended to the blob after the per-stage sections (header.pad[0] = offset in floats, 0 = absent).
+// All operand tiles are stored in the canonical K-major no-swizzle UMMA layout: element (row r, k) of a tile with R rows
+// lives at float index ((k / 4) * R + r) * 4 + (k % 4), i.e. 8 rows x 16 bytes core matrices, SBO = 128 B, LBO = R * 16 B.
+//   WIN  [D/32 chunks][8 kg][128 rows][4]   in_proj B operand of one 32-channel chunk: rows 0..63 = TF32 heads of W_in
+//        (row n = 8*stage + out-channel, zero rows above 8*Nq), rows 64..127 = the remainders (W - head)
+//   WOUT [Nq][D/128 chunks][3072]: [hi | lo | bias] tiles of [2 kg][128 rows][4]; row i of chunk j = channel 128j + 4(i%32) + i/32;
+//        bias tile: k = 0 -> head of b_out, k = 1 -> remainder, other k zero (multiplied by a constant tile of ones)
+//   BOUT [D/128 chunks][hi,lo][2 kg][128 rows][4]  bias as a B operand for the final GEMM: element (row, k = stage) = b_out[stage][channel(row)]
+//   GG   [Nq(Nq-1)/2][72]  for j < s: G = W_in[s] W_out[j] (8x8, row-major [c][k]) followed by g = W_in[s] b_out[j] (8)
+//   BIN  [Nq][8] b_in
+struct TcLayout {
+    int D, Nq;
+    __host__ __device__ constexpr TcLayout(int d, int nq) : D(d), Nq(nq) {}
+    __host__ __device__ constexpr int nch() const { return D / 32; }
+    __host__ __device__ constexpr int nj() const { return D / 128; }
+    __host__ __device__ constexpr int off_win() const { return 0; }
+    __host__ __device__ constexpr int off_wout() const { return nch() * 4096; }
+    __host__ __device__ constexpr int off_bout() const { return off_wout() + Nq * nj() * 3072; }
+    __host__ __device__ constexpr int off_gg() const { return off_bout() + nj() * 2048; }
+    __host__ __device__ constexpr int gg_floats() const { return (Nq * (Nq - 1) / 2 * 72 + 3) / 4 * 4; }
+    __host__ __device__ constexpr int off_bin() const { return off_gg() + gg_floats(); }
+    __host__ __device__ constexpr int total() const { return off_bin() + Nq * 8; }
+    __host__ __device__ static constexpr int pair_index(int nq, int j, int s) { return j * nq - j * (j + 1) / 2 + (s - j - 1); }
+};
+constexpr int TC_MAX_NQ = 8;
+__host__ __device__ constexpr bool tc_shape_ok(int D, int K, int Nq) { return K == 1024 && (D == 1024 || D == 512 || D == 256) && Nq >= 1 && Nq <= TC_MAX_NQ; }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+           ((uint64_t)1 << 46);
+}
+// instruction descriptor for kind::tf32 with fp32 accumulation, A and B K-major (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// arrives on the mbarrier once every tcgen05 operation this thread issued so far has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
+}
+// round-to-nearest TF32 head of an fp32 value (low 13 mantissa bits zero); x - head is exact in fp32
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    return __uint_as_float(h);
+}
+
 // streaming (evict-first) global stores for write-once outputs
 __device__ __forceinline__ void st_cs(float *p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs2(float *p, float a, float b) { __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b)); }

@@ -28,6 +28,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "encode_params.cuh"
 
 namespace vrvq {
 
@@ -35,34 +36,6 @@ constexpr int TF = 32;   // frames per tile
 constexpr int NT = 512;  // threads per CTA
 constexpr int NW = NT / 32;
 
-struct EncodeParams {
-    const float *blob;
-    const float *z;
-    long long z_sb, z_sd;
-    const float *imp;
-    long long imp_sb;
-    const float *level_dev;
-    long long level_stride;
-    float level_host;
-    long long *codes;
-    long long codes_sb, codes_sq;
-    float *z_q;
-    long long zq_sb, zq_sd;
-    float *z_q_is;
-    long long zqis_sb, zqis_sq, zqis_sd;
-    float *latents;
-    long long lat_sb, lat_sc;
-    float *mask;
-    long long mask_sb, mask_sq;
-    float *loss_pf;
-    long long loss_sb, loss_sq;
-    double *loss_sum;
-    unsigned long long *kept;
-    int B, T, Nq, n_run, tiles_per_b, n_tiles;
-    int vec_ld;  // 4 / 2 / 1 floats per global load of z
-    int vec_st;  // 4 / 2 / 1 floats per global store of z_q, z_q_is
-    long long *phase_cycles;  // profiling only (VRVQ_DEBUG_PHASES=1): [gridDim.x][8] clock64 totals per phase, else NULL
-};
 
 template <int D, int K>
 struct EncodeSmem {
@@ -672,7 +645,7 @@ static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_
 
 int encode_supported(int D, int K, int cd) { return cd == CD && K == 1024 && (D == 1024 || D == 512 || D == 256); }
 
-static int fill_params(const vrvq_encode_args *a, EncodeParams &p) {
+int fill_encode_params(const vrvq_encode_args *a, EncodeParams &p) {
     if (a == nullptr || a->struct_size != sizeof(vrvq_encode_args)) {
         set_error("vrvq_rvq_encode_f32: args is NULL or struct_size mismatch (ABI %d expects %zu bytes)", VRVQ_ABI_VERSION,
                   sizeof(vrvq_encode_args));
@@ -747,10 +720,18 @@ static int pick_grid(const EncodeParams &p, int *grid) {
     return VRVQ_OK;
 }
 
+// VRVQ_ENCODE_IMPL=cuda forces the CUDA-core kernel (A/B comparisons); default: tensor-core kernel where it applies
+static bool use_tc(const vrvq_encode_args *a) {
+    const char *impl = getenv("VRVQ_ENCODE_IMPL");
+    if (impl != nullptr && impl[0] == 'c') return false;
+    return encode_tc_usable(a) != 0;
+}
+
 int encode_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem) {
     EncodeParams p{};
-    int rc = fill_params(a, p);
+    int rc = fill_encode_params(a, p);
     if (rc) return rc;
+    if (use_tc(a)) return encode_tc_launch_info(a, grid, block, smem);
     int g = 0;
     rc = pick_grid(p, &g);
     if (rc) return rc;
@@ -762,11 +743,12 @@ int encode_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *sm
 
 int encode(const vrvq_encode_args *a, void *stream) {
     EncodeParams p{};
-    int rc = fill_params(a, p);
+    int rc = fill_encode_params(a, p);
     if (rc) return rc;
     if (p.n_tiles == 0) return VRVQ_OK;
     rc = check_device();
     if (rc) return rc;
+    if (use_tc(a)) return encode_tc(a, p, stream);
     int grid = 0;
     rc = pick_grid(p, &grid);
     if (rc) return rc;

@@ -1,0 +1,856 @@
+// Fused residual-vector-quantisation encode for B200 (sm_100a) -- tensor-core formulation.
+//
+// The reference loop (models/quantize.py:182-202 / :353-365) keeps a [D x T] residual and runs, per stage,
+// in_proj (D -> 8), a nearest-neighbour search and out_proj (8 -> D).  Because both projections are linear, the
+// pre-normalisation latents of ALL stages are one skinny GEMM of the input plus 8x8 corrections:
+//     z_e[s] = W_in[s] (z - sum_{j<s} (W_out[j] q_j + b_out[j])) + b_in[s]
+//            = (W_in[s] z + b_in[s]) - sum_{j<s} (G[s][j] q_j + g[s][j]),   G[s][j] = W_in[s] W_out[j],  g = W_in[s] b_out[j]
+// so the residual never exists.  One CTA owns a tile of up to 128 consecutive frames of one batch item (frame = TMEM
+// lane = MMA row) and runs:
+//   phase L  z tile -> registers -> (hi, lo) TF32 split -> shared memory (canonical UMMA layout), tcgen05.mma kind::tf32
+//            with the 3xTF32 split (hi*hi + hi*lo + lo*hi), M = 128 frames, N = 64 = 8 x Nq, K = D.  The tensor core
+//            rounds its fp32 accumulator toward zero on every k-step, so the accumulator is drained into a running
+//            fp32 sum (also in TMEM) every 128 channels; measured error 3.5e-7 rms / 1.3e-6 max relative, better than
+//            an fp32 FMA chain (profiles/r1_micro_tc3x.txt).
+//   phase S  per stage: bias + L2-normalise + exact fp32 search on the CUDA cores (same op order as the CUDA-core
+//            kernel / the oracle), argmin merge, raw-row gather, straight-through q, per-frame loss, codes; 8x8 corrections
+//            of the later stages' latents through TMEM; q (hi, lo) written as the next MMA's A operand.
+//            out_proj of the stage = tcgen05.mma M = 128 frames, N = 128 channels, K = 8 (x3 split) per 128-channel chunk
+//            into a two-deep TMEM ring that dedicated epilogue warps drain to global memory (lane = frame, so every
+//            warp-level store writes 128 contiguous bytes of one channel row), overlapping the next stage's search.
+//   final    z_q = sum_s mask_s (W_out[s] q_s + b_out[s]) as one GEMM over K = 8 Nq (+ the mask-weighted bias rows) from
+//            the masked A tiles kept in shared memory.
+// Warp roles: warps 0-7 load/split (phase L) and search (phase S), warps 0-3 additionally own one frame per thread
+// (drains, normalise, merge, gather); warps 8-11 are the epilogue; lane 0 of warp 12 issues every tcgen05.mma and every
+// cp.async.bulk weight copy.  Everything is synchronised with mbarriers; two CTA-wide barriers per tile.
+//
+// Exactness: codes are decided by the same fp32 search as before; only z_e differs from the reference's conv1d by
+// rounding (as any two conv implementations do), so codes can differ only at fp32 near-ties (audited in tests).
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "encode_params.cuh"
+
+namespace vrvq {
+
+constexpr int TCK = 1024;      // codebook size
+constexpr int TC_NTH = 448;    // 14 warps: 8 search/load, 4 epilogue, MMA issuer, copy producer
+constexpr int TC_NSEARCH = 256;
+
+// shared memory map (bytes).  Phase L uses [0, 147456); phase S re-uses that region.
+constexpr int SM_LR = 0;           // phase L ring, 3 slots x 48 KB: A hi [8 kg][128 frames][4] | A lo | W_in [8 kg][128 rows][4]
+constexpr int L_SLOT = 49152, L_SLOTS = 3;  // (W_in rows 0-63 heads, 64-127 remainders)
+constexpr int SM_AT = 0;           // phase S: per-stage A tiles, 8 x (hi 4 KB | lo 4 KB): [2 kg][128 frames][4]
+constexpr int SM_AM = 65536;       // phase S: mask tile (A operand of the bias rows of the final GEMM) [2 kg][128][4]
+constexpr int SM_WO = 69632;       // phase S: W_out ring, 4 slots x 12 KB (hi | lo | bias tile)
+constexpr int SM_CB1 = 118784;     // search codebook buffer 1 (36864 B)
+constexpr int SM_CB0 = 155648;     // search codebook buffer 0 (outside the phase-L region: prefetched during phase L)
+constexpr int SM_ES = 192512;      // [8][128] 2*e
+constexpr int SM_E2 = SM_ES + 4096;   // [128]
+constexpr int SM_SB = SM_E2 + 512;    // [8 slices][128] best distance
+constexpr int SM_SI = SM_SB + 4096;   // [8 slices][128] best index
+constexpr int SM_GG = SM_SI + 4096;   // correction matrices, <= 28 x 72 floats
+constexpr int SM_BIN = SM_GG + 8192;  // b_in [8][8]
+constexpr int SM_NK = SM_BIN + 256;   // keep counts [128]
+constexpr int SM_ONES = SM_NK + 512;  // constant A tile [2 kg][128][4]: k = 0, 1 -> 1.0 (multiplies the bias tile)
+constexpr int SM_BAR = SM_ONES + 4096;  // mbarriers
+constexpr int SM_TMEM = SM_BAR + 1024;
+constexpr int SM_TOTAL = SM_TMEM + 16;
+constexpr int W_SLOT = 12288, W_SLOTS = 4;
+constexpr int F_SLOT = 40960, F_SLOTS = 3, F_ITEMS = 5;  // final-GEMM ring (<= 5 chunks of 8 KB per step) over the W_out ring and both codebook buffers
+static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+static_assert(SM_WO + W_SLOTS * W_SLOT == SM_CB1 && SM_CB1 + 36864 == SM_CB0 && SM_CB0 + 36864 == SM_ES, "shared memory map");
+static_assert(SM_WO + F_SLOTS * F_SLOT == SM_ES, "final ring covers [SM_WO, SM_ES)");
+static_assert(L_SLOTS * L_SLOT <= SM_CB0, "phase-L ring must not reach codebook buffer 0");
+
+enum {
+    B_L_FULL = 0, B_L_EMPTY = 4, B_SET_FULL = 24, B_SET_EMPTY = 26, B_W_FULL = 28, B_W_EMPTY = 32,
+    B_D_FULL = 36, B_D_EMPTY = 38, B_CB_FULL = 40, B_A_READY = 42, B_ZQ_READY = 50, B_MMA_DONE = 51, B_F_FULL = 52, B_F_EMPTY = 56,
+    B_COUNT = 60
+};
+
+// TMEM columns: [0,64) running z_e sums of all stages; phase L accumulator sets at 64 + 128*set (hi*hi | lo terms);
+// phase S out_proj ring at 64 + 128*buf.
+constexpr uint32_t TM_COLS = 512;
+constexpr uint32_t TM_RUN = 0, TM_SET = 64;
+
+// Every wait in this kernel is bounded: a protocol bug traps (and reports which barrier) instead of hanging the GPU.
+__device__ __noinline__ void tc_wait_timeout(const uint64_t *bar, const uint64_t *bars, uint32_t parity) {
+    printf("[vrvq tc] mbarrier %d wait timed out (parity %u, block %d, thread %d)\n", (int)(bar - bars), parity, (int)blockIdx.x, (int)threadIdx.x);
+    __trap();
+}
+#define TC_WAIT(bar_, parity_)                                                   \
+    do {                                                                         \
+        uint64_t *b__ = (bar_);                                                  \
+        const uint32_t p__ = (parity_);                                          \
+        uint32_t spins__ = 0;                                                    \
+        while (!mbar_try_wait(b__, p__)) {                                       \
+            if (++spins__ > (1u << 26)) tc_wait_timeout(b__, bars, p__);         \
+        }                                                                        \
+    } while (0)
+
+struct TcParams {
+    EncodeParams e;
+    const float *tc;  // TC section of the blob
+    int adv;          // frames per tile (multiple of 8, <= 128)
+    int tiles_per_b, n_tiles;
+};
+
+// all K-major no-swizzle tiles of this kernel have 128 rows: LBO = 2048 B (next 4-wide k group), SBO = 128 B (next 8 rows)
+constexpr uint64_t DESC_128 = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)(2048 >> 4) << 16);
+__device__ __forceinline__ uint64_t desc128(uint32_t saddr) { return DESC_128 | (uint64_t)(saddr >> 4); }
+
+template <int D, bool ZQIS>
+__global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P) {
+    constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;  // 32-channel chunks, accumulator drained every 4 chunks
+    static_assert(NCH % 4 == 0, "D must be a multiple of 128");
+    const EncodeParams &p = P.e;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_TMEM);
+    float *es = reinterpret_cast<float *>(smem + SM_ES);
+    float *e2s = reinterpret_cast<float *>(smem + SM_E2);
+    float *sbest = reinterpret_cast<float *>(smem + SM_SB);
+    int *sidx = reinterpret_cast<int *>(smem + SM_SI);
+    float *ggs = reinterpret_cast<float *>(smem + SM_GG);
+    float *bins = reinterpret_cast<float *>(smem + SM_BIN);
+    int *nkeep = reinterpret_cast<int *>(smem + SM_NK);
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int n_run = p.n_run, Nq = p.Nq;
+    const TcLayout TL(D, Nq);
+    constexpr BlobLayout L = BlobLayout(D, TCK);
+    const float *stages = p.blob + BLOB_HDR_FLOATS;
+    const int n_my_tiles = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (n_my_tiles <= 0) return;
+
+    // ---- one-time setup -------------------------------------------------------------------------------------
+    if (tid == 0) {
+        // phase-L slot: 8 loader warps + the producer's expect_tx arrive; released by one tcgen05.commit
+        for (int i = 0; i < L_SLOTS; ++i) { mbar_init(&bars[B_L_FULL + i], 9); mbar_init(&bars[B_L_EMPTY + i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[B_SET_FULL + i], 1); mbar_init(&bars[B_SET_EMPTY + i], 4);
+            mbar_init(&bars[B_D_FULL + i], 1); mbar_init(&bars[B_D_EMPTY + i], 4);
+            mbar_init(&bars[B_CB_FULL + i], 1);
+        }
+        for (int i = 0; i < W_SLOTS; ++i) { mbar_init(&bars[B_W_FULL + i], 1); mbar_init(&bars[B_W_EMPTY + i], 1); }
+        for (int i = 0; i < 8; ++i) mbar_init(&bars[B_A_READY + i], 4);
+        mbar_init(&bars[B_ZQ_READY], 4);
+        mbar_init(&bars[B_MMA_DONE], 1);
+        for (int i = 0; i < F_SLOTS; ++i) { mbar_init(&bars[B_F_FULL + i], 1); mbar_init(&bars[B_F_EMPTY + i], 1); }
+        fence_mbar_init();
+    }
+    if (w == 12) {
+        tmem_alloc(tmem_slot, TM_COLS);
+        tmem_relinquish();
+    }
+    for (int i = tid; i < TL.gg_floats(); i += TC_NTH) ggs[i] = P.tc[TL.off_gg() + i];
+    for (int i = tid; i < Nq * 8; i += TC_NTH) bins[i] = P.tc[TL.off_bin() + i];
+    for (int i = tid; i < 256; i += TC_NTH)  // ones tile: k group 0 = (1, 1, 0, 0) for every row, k group 1 = 0
+        reinterpret_cast<float4 *>(smem + SM_ONES)[i] = i < 128 ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+
+    // profiling only (VRVQ_DEBUG_PHASES=1): clock64 totals per phase for one thread of each role
+    const int ph_role = tid == 0 ? 0 : tid == 256 ? 1 : tid == 384 ? 2 : tid == 416 ? 3 : -1;
+    const bool ph_on = p.phase_cycles != nullptr && ph_role >= 0;
+    long long ph_last = 0, ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ph_on) ph_last = clock64();
+    auto ph_mark = [&](int k) {
+        if (ph_on) {
+            const long long t = clock64();
+            ph_acc[k] += t - ph_last;
+            ph_last = t;
+        }
+    };
+
+    double loss_acc = 0.0;               // frame threads
+    unsigned long long kept_acc = 0ull;  // lane k of warps 0-3 counts stage k
+    uint32_t wn = 0, fn = 0, dn = 0;     // W_out ring / final ring step counters, out_proj unit counter
+    uint32_t cbu0 = 0, cbu1 = 0;         // uses of the two codebook buffers
+
+    for (int it = 0; it < n_my_tiles; ++it) {
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int b = tile / P.tiles_per_b;
+        const int t0 = (tile % P.tiles_per_b) * P.adv;
+        const int fv = min(P.adv, p.T - t0);  // valid frames (lanes) of this tile
+        const uint32_t lbase = (uint32_t)it * NCH, gbase = (uint32_t)it * NG;
+        const uint32_t tpar = (uint32_t)it & 1u;
+        const int n_stage_steps = ZQIS ? n_run * NJ : 0;
+        const int n_final_steps = (p.z_q != nullptr) ? NJ * ((n_run + F_ITEMS) / F_ITEMS) : 0;  // ceil((n_run + 1) / F_ITEMS) per 128-channel chunk
+
+        if (w < 8) {
+            // =====================================================================================================
+            // Search group.  Frame threads (warps 0-3): f = tid = TMEM lane.
+            // =====================================================================================================
+            const int f = tid & 127;
+            const uint32_t tq = tmem + ((uint32_t)(32 * (w & 3)) << 16);  // this warp's lane quarter
+            if (w < 4) {
+                // ---- keep counts, mask, kept-frame counts (quantize.py:389, utils.py:59-60) ----
+                int nk = 0;
+                if (f < fv) {
+                    if (p.imp != nullptr) {
+                        const float lv = p.level_dev ? p.level_dev[(long long)b * p.level_stride] : p.level_host;
+                        const float x = __fmul_rn(__fmul_rn(p.imp[(long long)b * p.imp_sb + t0 + f], lv), (float)Nq);
+                        for (int k = 0; k < n_run; ++k) nk += (__fsub_rn(x, (float)k) >= 0.0f) ? 1 : 0;
+                    } else {
+                        nk = n_run;
+                    }
+                }
+                nkeep[f] = nk;
+                for (int k = 0; k < n_run; ++k) {
+                    const bool on = nk > k;
+                    const unsigned bal = __ballot_sync(0xffffffffu, on);
+                    if (lane == k) kept_acc += (unsigned long long)__popc(bal);
+                    if (p.mask != nullptr && f < fv) p.mask[(long long)b * p.mask_sb + (long long)k * p.mask_sq + t0 + f] = on ? 1.0f : 0.0f;
+                }
+            }
+            ph_mark(0);
+            // ---- phase L: load, split, stage (256 threads: frame f, half q of each 32-channel chunk) ----
+            {
+                const int q = tid >> 7;
+                const bool valid = f < fv;
+                const float *zp = p.z + (long long)b * p.z_sb + t0 + f + (long long)(16 * q) * p.z_sd;
+                const long long zstep = 32 * p.z_sd;
+                float x[2][16];
+                auto ldchunk = [&](const float *src, float (&v)[16]) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = valid ? __ldcs(src + (long long)i * p.z_sd) : 0.0f;
+                };
+                auto drain = [&](int g) {  // frame threads: fold accumulator set of group g into the running sums
+                    const uint32_t gg = gbase + (uint32_t)g, set = gg & 1u;
+                    TC_WAIT(&bars[B_SET_FULL + set], (gg >> 1) & 1u);
+                    tmem_fence_after_sync();
+                    const uint32_t ts = tq + TM_SET + 128u * set;
+#pragma unroll 2
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        uint32_t hh[8], lo[8], run[8];
+                        tmem_ld8(ts + 8 * c8, hh);
+                        tmem_ld8(ts + 64 + 8 * c8, lo);
+                        if (g > 0) tmem_ld8(tq + TM_RUN + 8 * c8, run);
+                        tmem_wait_ld(hh);
+                        tmem_wait_ld(lo);
+                        if (g > 0) tmem_wait_ld(run);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float v = __fadd_rn(__uint_as_float(hh[i]), __uint_as_float(lo[i]));
+                            if (g > 0) v = __fadd_rn(__uint_as_float(run[i]), v);
+                            run[i] = __float_as_uint(v);
+                        }
+                        tmem_st8(tq + TM_RUN + 8 * c8, run);
+                    }
+                    tmem_wait_st();
+                    tmem_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[B_SET_EMPTY + set]);
+                };
+                const float *zc = zp;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) { ldchunk(zc, x[u]); zc += zstep; }
+                for (int c0 = 0; c0 < NCH; c0 += 2) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int c = c0 + u;
+                        float h[16], l[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            h[i] = tf32_hi(x[u][i]);
+                            l[i] = __fsub_rn(x[u][i], h[i]);
+                        }
+                        if (c + 2 < NCH) { ldchunk(zc, x[u]); zc += zstep; }
+                        const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS, use = n / L_SLOTS;
+                        if (use >= 1) TC_WAIT(&bars[B_L_EMPTY + sl], (use - 1) & 1u);
+                        unsigned char *slot = smem + SM_LR + sl * L_SLOT + (4 * q) * 2048 + f * 16;
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            *reinterpret_cast<float4 *>(slot + g4 * 2048) = make_float4(h[4 * g4], h[4 * g4 + 1], h[4 * g4 + 2], h[4 * g4 + 3]);
+                            *reinterpret_cast<float4 *>(slot + 16384 + g4 * 2048) = make_float4(l[4 * g4], l[4 * g4 + 1], l[4 * g4 + 2], l[4 * g4 + 3]);
+                        }
+                        // No fence.proxy.async here: it would also wait for this thread's prefetched global loads (a full
+                        // memory latency per chunk).  The release-arrive orders the stores; the MMA thread fences after its wait.
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars[B_L_FULL + sl]);
+                        if (w < 4 && (c & 3) == 1 && c >= 5) drain((c - 5) >> 2);
+                    }
+                }
+                if (w < 4) drain(NG - 1);
+            }
+            ph_mark(1);
+            tmem_fence_before_sync();
+            __syncthreads();  // L -> S: every phase-L MMA has completed (the last drain waited for them); region re-usable
+            tmem_fence_after_sync();
+            ph_mark(2);
+
+            // ---- phase S ----
+            float zev[8];  // frame threads: z_e of the current stage
+            for (int s = 0; s < n_run; ++s) {
+                if (w < 4) {
+                    // bias, latents, normalise (quantize.py:66,92 in torch's op order)
+                    uint32_t r8[8];
+                    tmem_ld8(tq + TM_RUN + 8 * s, r8);
+                    tmem_wait_ld(r8);
+                    float ss = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        zev[k] = __fadd_rn(__uint_as_float(r8[k]), bins[s * 8 + k]);
+                        const float sq = __fmul_rn(zev[k], zev[k]);
+                        ss = (k == 0) ? sq : __fadd_rn(ss, sq);
+                    }
+                    const float den = fmaxf(__fsqrt_rn(ss), 1e-12f);
+                    float e2 = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float ec = __fdiv_rn(zev[k], den);
+                        const float sqe = __fmul_rn(ec, ec);
+                        e2 = (k == 0) ? sqe : __fadd_rn(e2, sqe);
+                        es[k * 128 + f] = __fmul_rn(2.0f, ec);
+                    }
+                    e2s[f] = e2;
+                    if (p.latents != nullptr && f < fv) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)(s * 8 + k) * p.lat_sc + t0 + f] = zev[k];
+                    }
+                }
+                named_bar_sync(1, TC_NSEARCH);
+                ph_mark(3);
+                if (4 * lane < fv) {  // lanes whose 4 frames lie beyond the tile skip the search (their slots are never read back)
+                    // ---- search: warp w = code slice (pairs 8i + w, ascending), lane = frames 4*lane .. 4*lane+3 ----
+                    const uint32_t use = (s & 1) ? (cbu1 + (uint32_t)(s >> 1)) : (cbu0 + (uint32_t)(s >> 1));
+                    TC_WAIT(&bars[B_CB_FULL + (s & 1)], use & 1u);
+                    const float *CB = reinterpret_cast<const float *>(smem + ((s & 1) ? SM_CB1 : SM_CB0));
+                    const float *c2 = CB + TCK * 8;
+                    float2 e[8][4];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 t = *reinterpret_cast<const float4 *>(&es[k * 128 + 4 * lane]);
+                        e[k][0] = make_float2(t.x, t.x); e[k][1] = make_float2(t.y, t.y);
+                        e[k][2] = make_float2(t.z, t.z); e[k][3] = make_float2(t.w, t.w);
+                    }
+                    const float4 e2v = *reinterpret_cast<const float4 *>(&e2s[4 * lane]);
+                    const float e2f[4] = {e2v.x, e2v.y, e2v.z, e2v.w};
+                    float best[4];
+                    int bp[4];  // pair index of the current minimum; which code of the pair is resolved in the merge step
+#pragma unroll
+                    for (int fr = 0; fr < 4; ++fr) { best[fr] = __int_as_float(0x7f800000); bp[fr] = w; }
+#pragma unroll 2
+                    for (int i = 0; i < TCK / 16; ++i) {
+                        const int pr = 8 * i + w;
+                        const float4 *cp = reinterpret_cast<const float4 *>(CB + pr * 16);
+                        const float4 c01 = cp[0], c23 = cp[1], c45 = cp[2], c67 = cp[3];
+                        const float2 cc = *reinterpret_cast<const float2 *>(c2 + 2 * pr);
+#pragma unroll
+                        for (int fr = 0; fr < 4; ++fr) {
+                            float2 d = __fmul2_rn(e[0][fr], make_float2(c01.x, c01.y));
+                            d = __ffma2_rn(e[1][fr], make_float2(c01.z, c01.w), d);
+                            d = __ffma2_rn(e[2][fr], make_float2(c23.x, c23.y), d);
+                            d = __ffma2_rn(e[3][fr], make_float2(c23.z, c23.w), d);
+                            d = __ffma2_rn(e[4][fr], make_float2(c45.x, c45.y), d);
+                            d = __ffma2_rn(e[5][fr], make_float2(c45.z, c45.w), d);
+                            d = __ffma2_rn(e[6][fr], make_float2(c67.x, c67.y), d);
+                            d = __ffma2_rn(e[7][fr], make_float2(c67.z, c67.w), d);
+                            // dist = fl(fl(e2 - dot) + c2)   (quantize.py:96-100)
+                            const float2 t = __fadd2_rn(__fadd2_rn(make_float2(e2f[fr], e2f[fr]), make_float2(-d.x, -d.y)), cc);
+                            float nb;
+                            asm("min.f32 %0, %1, %2, %3;" : "=f"(nb) : "f"(best[fr]), "f"(t.x), "f"(t.y));  // FMNMX3
+                            if (nb < best[fr]) bp[fr] = pr;  // strict: the first pair reaching the minimum wins
+                            best[fr] = nb;
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(&sbest[w * 128 + 4 * lane]) = make_float4(best[0], best[1], best[2], best[3]);
+                    *reinterpret_cast<int4 *>(&sidx[w * 128 + 4 * lane]) = make_int4(bp[0], bp[1], bp[2], bp[3]);
+                }
+                named_bar_sync(1, TC_NSEARCH);
+                ph_mark(4);
+                if (w < 4) {
+                    // ---- argmin merge (first index on ties), gather, loss, straight-through (quantize.py:69-75,81-85,102) ----
+                    float best = sbest[f];
+                    int bpair = sidx[f];
+#pragma unroll
+                    for (int sl = 1; sl < 8; ++sl) {
+                        const float ob = sbest[sl * 128 + f];
+                        const int oi = sidx[sl * 128 + f];
+                        if (ob < best || (ob == best && oi < bpair)) { best = ob; bpair = oi; }
+                    }
+                    if (f >= fv) bpair = 0;  // lanes beyond the tile were not searched: any valid pair
+                    int bi;
+                    {   // which code of the winning pair: recompute its two distances with the search loop's exact arithmetic
+                        const float *CB = reinterpret_cast<const float *>(smem + ((s & 1) ? SM_CB1 : SM_CB0));
+                        const float4 *cp = reinterpret_cast<const float4 *>(CB + bpair * 16);
+                        const float4 c01 = cp[0], c23 = cp[1], c45 = cp[2], c67 = cp[3];
+                        const float2 cc = *reinterpret_cast<const float2 *>(CB + TCK * 8 + 2 * bpair);
+                        const float ca[8] = {c01.x, c01.z, c23.x, c23.z, c45.x, c45.z, c67.x, c67.z};
+                        const float cb[8] = {c01.y, c01.w, c23.y, c23.w, c45.y, c45.w, c67.y, c67.w};
+                        float da = 0.f, db = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float ek = es[k * 128 + f];
+                            da = (k == 0) ? __fmul_rn(ek, ca[0]) : __fmaf_rn(ek, ca[k], da);
+                            db = (k == 0) ? __fmul_rn(ek, cb[0]) : __fmaf_rn(ek, cb[k], db);
+                        }
+                        const float e2 = e2s[f];
+                        const float ta = __fadd_rn(__fadd_rn(e2, -da), cc.x), tb = __fadd_rn(__fadd_rn(e2, -db), cc.y);
+                        bi = 2 * bpair + ((tb < ta) ? 1 : 0);
+                    }
+                    const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)s * L.stage_floats() + L.off_raw() + (size_t)bi * 8);
+                    const float4 ra = __ldg(rawp), rb = __ldg(rawp + 1);
+                    const float cr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                    float qv[8], ls = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float diff = __fsub_rn(zev[k], cr[k]);
+                        const float sq = __fmul_rn(diff, diff);
+                        ls = (k == 0) ? sq : __fadd_rn(ls, sq);
+                        qv[k] = __fadd_rn(zev[k], __fsub_rn(cr[k], zev[k]));
+                    }
+                    if (f < fv) {
+                        const float loss = __fdiv_rn(ls, 8.0f);
+                        p.codes[(long long)b * p.codes_sb + (long long)s * p.codes_sq + t0 + f] = (long long)bi;
+                        if (p.loss_pf != nullptr) p.loss_pf[(long long)b * p.loss_sb + (long long)s * p.loss_sq + t0 + f] = loss;
+                        if (nkeep[f] > s) loss_acc += (double)loss;
+                    }
+                    // A operand of this stage's out_proj: q split into TF32 head and remainder
+                    {
+                        float h[8], l[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { h[k] = tf32_hi(qv[k]); l[k] = __fsub_rn(qv[k], h[k]); }
+                        unsigned char *at = smem + SM_AT + s * 8192 + f * 16;
+                        *reinterpret_cast<float4 *>(at) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4 *>(at + 2048) = make_float4(h[4], h[5], h[6], h[7]);
+                        *reinterpret_cast<float4 *>(at + 4096) = make_float4(l[0], l[1], l[2], l[3]);
+                        *reinterpret_cast<float4 *>(at + 4096 + 2048) = make_float4(l[4], l[5], l[6], l[7]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[B_A_READY + s]);
+                    // corrections of the later stages: z_e[s2] -= G[s2][s] q + g[s2][s]
+                    for (int s2 = s + 1; s2 < n_run; ++s2) {
+                        const float *G = ggs + TcLayout::pair_index(Nq, s, s2) * 72;
+                        uint32_t r8[8];
+                        tmem_ld8(tq + TM_RUN + 8 * s2, r8);
+                        float a[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 g0 = *reinterpret_cast<const float4 *>(G + c * 8), g1 = *reinterpret_cast<const float4 *>(G + c * 8 + 4);
+                            float acc = G[64 + c];
+                            acc = __fmaf_rn(g0.x, qv[0], acc); acc = __fmaf_rn(g0.y, qv[1], acc);
+                            acc = __fmaf_rn(g0.z, qv[2], acc); acc = __fmaf_rn(g0.w, qv[3], acc);
+                            acc = __fmaf_rn(g1.x, qv[4], acc); acc = __fmaf_rn(g1.y, qv[5], acc);
+                            acc = __fmaf_rn(g1.z, qv[6], acc); acc = __fmaf_rn(g1.w, qv[7], acc);
+                            a[c] = acc;
+                        }
+                        tmem_wait_ld(r8);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) r8[c] = __float_as_uint(__fsub_rn(__uint_as_float(r8[c]), a[c]));
+                        tmem_st8(tq + TM_RUN + 8 * s2, r8);
+                    }
+                    tmem_wait_st();
+                }
+                ph_mark(5);
+            }
+            if (w < 4) {
+                // ---- mask the A tiles for the final z_q GEMM (quantize.py:194 / :421) once every per-stage MMA has read them ----
+                TC_WAIT(&bars[B_MMA_DONE], tpar);
+                const int nk = nkeep[f];
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s = nk; s < n_run; ++s) {
+                    unsigned char *at = smem + SM_AT + s * 8192 + f * 16;
+                    *reinterpret_cast<float4 *>(at) = zero;
+                    *reinterpret_cast<float4 *>(at + 2048) = zero;
+                    *reinterpret_cast<float4 *>(at + 4096) = zero;
+                    *reinterpret_cast<float4 *>(at + 4096 + 2048) = zero;
+                }
+                unsigned char *am = smem + SM_AM + f * 16;
+                *reinterpret_cast<float4 *>(am) = make_float4(nk > 0 ? 1.f : 0.f, nk > 1 ? 1.f : 0.f, nk > 2 ? 1.f : 0.f, nk > 3 ? 1.f : 0.f);
+                *reinterpret_cast<float4 *>(am + 2048) = make_float4(nk > 4 ? 1.f : 0.f, nk > 5 ? 1.f : 0.f, nk > 6 ? 1.f : 0.f, nk > 7 ? 1.f : 0.f);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[B_ZQ_READY]);
+            }
+            ph_mark(6);
+        } else if (w < 12) {
+            // =====================================================================================================
+            // Epilogue warps: TMEM -> global.  Lane quarter q4 = w - 8, frame f = 32*q4 + lane.
+            // =====================================================================================================
+            tmem_fence_before_sync();
+            __syncthreads();  // L -> S
+            tmem_fence_after_sync();
+            ph_mark(0);
+            const int q4 = w - 8, f = 32 * q4 + lane;
+            const bool valid = f < fv;
+            const uint32_t tq = tmem + ((uint32_t)(32 * q4) << 16);
+            // one unit = 128 channels x 128 frames: column 32*piece + i of the TMEM buffer <-> channel 128j + 4i + piece
+            auto unit = [&](float *outj, long long rstride) {  // outj = row 128j of the output at this thread's frame
+                const uint32_t buf = dn & 1u;
+                TC_WAIT(&bars[B_D_FULL + buf], (dn >> 1) & 1u);
+                tmem_fence_after_sync();
+                ph_mark(1);
+                const uint32_t tcol = tq + TM_SET + 128u * buf;
+                const long long step = 4 * rstride;
+                uint32_t va[32], vb[32];
+                auto put = [&](const uint32_t (&v)[32], int piece) {
+                    if (valid) {
+                        float *o = outj + (long long)piece * rstride;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            st_cs(o, __uint_as_float(v[i]));
+                            o += step;
+                        }
+                    }
+                };
+                tmem_ld32(tcol, va);
+                tmem_wait_ld32(va);
+                tmem_ld32(tcol + 32, vb);
+                put(va, 0);
+                tmem_wait_ld32(vb);
+                tmem_ld32(tcol + 64, va);
+                put(vb, 1);
+                tmem_wait_ld32(va);
+                tmem_ld32(tcol + 96, vb);
+                put(va, 2);
+                tmem_wait_ld32(vb);
+                tmem_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[B_D_EMPTY + buf]);  // the MMA thread may refill this buffer
+                put(vb, 3);
+                ++dn;
+                ph_mark(2);
+            };
+            if (ZQIS) {
+                for (int s = 0; s < n_run; ++s) {
+                    float *outp = p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + t0 + f;
+                    for (int j = 0; j < NJ; ++j) unit(outp + (long long)(128 * j) * p.zqis_sd, p.zqis_sd);
+                }
+            }
+            if (p.z_q != nullptr) {
+                float *outp = p.z_q + (long long)b * p.zq_sb + t0 + f;
+                for (int j = 0; j < NJ; ++j) unit(outp + (long long)(128 * j) * p.zq_sd, p.zq_sd);
+            }
+        } else if (w == 12) {
+            // =====================================================================================================
+            // MMA issuer: lane 0 of warp 12.
+            // =====================================================================================================
+            constexpr uint32_t ID_128 = umma_idesc_tf32(128, 128), ID_64 = umma_idesc_tf32(128, 64);
+            if (lane == 0) {
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS;
+                    TC_WAIT(&bars[B_L_FULL + sl], (n / L_SLOTS) & 1u);
+                    const uint32_t gg = gbase + (uint32_t)(c >> 2), set = gg & 1u;
+                    if ((c & 3) == 0 && gg >= 2) TC_WAIT(&bars[B_SET_EMPTY + set], ((gg >> 1) - 1) & 1u);
+                    fence_proxy_async();  // generic-proxy stores of the loader warps (acquired above) -> async proxy
+                    tmem_fence_after_sync();
+                    const uint64_t a_hi = desc128(smem_base + SM_LR + sl * L_SLOT);  // lo tile at +16 KB, W_in tile at +32 KB
+                    const uint64_t a_lo = a_hi + (16384 >> 4), bw = a_hi + (32768 >> 4);
+                    const uint32_t d = tmem + TM_SET + 128u * set;
+                    // [hi*hi | hi*lo] in one N = 128 MMA (B rows 0-63 heads, 64-127 remainders), lo*hi added to the second half
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        umma_tf32(d, a_hi + ks * (4096 >> 4), bw + ks * (4096 >> 4), ID_128, (c & 3) != 0 || ks != 0);
+                        umma_tf32(d + 64, a_lo + ks * (4096 >> 4), bw + ks * (4096 >> 4), ID_64, true);
+                    }
+                    umma_commit(&bars[B_L_EMPTY + sl]);
+                    if ((c & 3) == 3) umma_commit(&bars[B_SET_FULL + set]);
+                }
+            }
+            ph_mark(0);
+            __syncwarp();
+            tmem_fence_before_sync();
+            __syncthreads();  // L -> S
+            tmem_fence_after_sync();
+            ph_mark(1);
+            if (lane == 0) {
+                const uint64_t ones = desc128(smem_base + SM_ONES);
+                uint32_t step = wn;
+                auto take_w = [&]() -> uint64_t {
+                    const uint32_t slot = step % W_SLOTS;
+                    TC_WAIT(&bars[B_W_FULL + slot], (step / W_SLOTS) & 1u);
+                    return desc128(smem_base + SM_WO + slot * W_SLOT);
+                };
+                auto release_w = [&]() {
+                    umma_commit(&bars[B_W_EMPTY + step % W_SLOTS]);
+                    ++step;
+                };
+                auto wait_dbuf = [&]() -> uint32_t {
+                    const uint32_t buf = dn & 1u, use = dn >> 1;
+                    if (use >= 1) TC_WAIT(&bars[B_D_EMPTY + buf], (use - 1) & 1u);
+                    return buf;
+                };
+                for (int s = 0; s < n_run; ++s) {
+                    TC_WAIT(&bars[B_A_READY + s], tpar);
+                    fence_proxy_async();
+                    tmem_fence_after_sync();
+                    ph_mark(2);
+                    if (ZQIS) {
+                        const uint64_t ah = desc128(smem_base + SM_AT + s * 8192), al = ah + (4096 >> 4);
+                        for (int j = 0; j < NJ; ++j) {
+                            const uint64_t wb = take_w();  // hi tile; lo at +4096 B, bias tile at +8192 B
+                            const uint32_t buf = wait_dbuf();
+                            tmem_fence_after_sync();
+                            const uint32_t d = tmem + TM_SET + 128u * buf;
+                            umma_tf32(d, al, wb, ID_128, false);
+                            umma_tf32(d, ah, wb + (4096 >> 4), ID_128, true);
+                            umma_tf32(d, ones, wb + (8192 >> 4), ID_128, true);
+                            umma_tf32(d, ah, wb, ID_128, true);
+                            release_w();
+                            umma_commit(&bars[B_D_FULL + buf]);
+                            ++dn;
+                        }
+                        ph_mark(3);
+                    }
+                }
+                umma_commit(&bars[B_MMA_DONE]);
+                if (p.z_q != nullptr) {
+                    TC_WAIT(&bars[B_ZQ_READY], tpar);
+                    fence_proxy_async();
+                    tmem_fence_after_sync();
+                    ph_mark(4);
+                    const uint64_t am = desc128(smem_base + SM_AM);
+                    uint32_t fstep = fn;
+                    for (int j = 0; j < NJ; ++j) {
+                        const uint32_t buf = wait_dbuf();
+                        const uint32_t d = tmem + TM_SET + 128u * buf;
+                        for (int s0 = 0; s0 <= n_run; s0 += F_ITEMS) {  // one ring step = up to F_ITEMS chunks (stages s0.., then the bias)
+                            const uint32_t slot = fstep % F_SLOTS;
+                            TC_WAIT(&bars[B_F_FULL + slot], (fstep / F_SLOTS) & 1u);
+                            tmem_fence_after_sync();
+                            const int s1 = min(s0 + F_ITEMS, n_run + 1);
+                            for (int s = s0; s < s1; ++s) {
+                                const uint64_t wb = desc128(smem_base + SM_WO + slot * F_SLOT + (s - s0) * 8192);
+                                if (s < n_run) {
+                                    const uint64_t ah = desc128(smem_base + SM_AT + s * 8192), al = ah + (4096 >> 4);
+                                    umma_tf32(d, al, wb, ID_128, s > 0);
+                                    umma_tf32(d, ah, wb + (4096 >> 4), ID_128, true);
+                                    umma_tf32(d, ah, wb, ID_128, true);
+                                } else {  // + sum_s mask_s b_out[s]
+                                    umma_tf32(d, am, wb + (4096 >> 4), ID_128, true);
+                                    umma_tf32(d, am, wb, ID_128, true);
+                                }
+                            }
+                            umma_commit(&bars[B_F_EMPTY + slot]);
+                            ++fstep;
+                        }
+                        umma_commit(&bars[B_D_FULL + buf]);
+                        ++dn;
+                    }
+                    ph_mark(5);
+                }
+            }
+            __syncwarp();
+        } else {
+            // =====================================================================================================
+            // Copy producer: lane 0 of warp 13 issues every cp.async.bulk (W_in ring, W_out ring, search codebooks).
+            // =====================================================================================================
+            if (lane == 0) {
+                const float *win = P.tc + TL.off_win();
+                // codebook of stage 0 (its buffer is outside the phase-L region)
+                mbar_arrive_expect_tx(&bars[B_CB_FULL + 0], 36864);
+                bulk_g2s(smem + SM_CB0, stages + L.off_p1(), 36864, &bars[B_CB_FULL + 0]);
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t m = lbase + (uint32_t)c, slot = m % L_SLOTS, use = m / L_SLOTS;
+                    if (use >= 1) TC_WAIT(&bars[B_L_EMPTY + slot], (use - 1) & 1u);
+                    mbar_arrive_expect_tx(&bars[B_L_FULL + slot], 16384);
+                    bulk_g2s(smem + SM_LR + slot * L_SLOT + 32768, win + (size_t)c * 4096, 16384, &bars[B_L_FULL + slot]);
+                }
+            }
+            ph_mark(0);
+            __syncwarp();
+            tmem_fence_before_sync();
+            __syncthreads();  // L -> S
+            tmem_fence_after_sync();
+            if (lane == 0) {
+                if (n_run > 1) {  // codebook of stage 1 (its buffer is inside the phase-L region)
+                    mbar_arrive_expect_tx(&bars[B_CB_FULL + 1], 36864);
+                    bulk_g2s(smem + SM_CB1, stages + (size_t)1 * L.stage_floats() + L.off_p1(), 36864, &bars[B_CB_FULL + 1]);
+                }
+                // W_out ring of the per-stage out_proj: chunk (s, j), row-major; refills of the search codebooks interleaved
+                const float *wout = P.tc + TL.off_wout();
+                const float *bout = P.tc + TL.off_bout();
+                int wi = 0, cs = 0;
+                uint32_t spins = 0;
+                while (wi < n_stage_steps || cs < n_run) {
+                    bool progressed = false;
+                    if (wi < n_stage_steps) {
+                        const uint32_t m = wn + (uint32_t)wi, slot = m % W_SLOTS, use = m / W_SLOTS;
+                        if (use == 0 || mbar_try_wait(&bars[B_W_EMPTY + slot], (use - 1) & 1u)) {
+                            mbar_arrive_expect_tx(&bars[B_W_FULL + slot], 12288);
+                            bulk_g2s(smem + SM_WO + slot * W_SLOT, wout + (size_t)wi * 3072, 12288, &bars[B_W_FULL + slot]);
+                            ++wi;
+                            progressed = true;
+                        }
+                    }
+                    if (cs < n_run && mbar_try_wait(&bars[B_A_READY + cs], tpar)) {
+                        // the search group is done with the codebook of stage cs: refill its buffer
+                        if (cs + 2 < n_run) {
+                            mbar_arrive_expect_tx(&bars[B_CB_FULL + (cs & 1)], 36864);
+                            bulk_g2s(smem + ((cs & 1) ? SM_CB1 : SM_CB0), stages + (size_t)(cs + 2) * L.stage_floats() + L.off_p1(), 36864,
+                                     &bars[B_CB_FULL + (cs & 1)]);
+                        }
+                        ++cs;
+                        progressed = true;
+                    }
+                    if (progressed) spins = 0;
+                    else if (++spins > (1u << 26)) tc_wait_timeout(&bars[B_W_EMPTY], bars, 99);
+                }
+                // final GEMM ring: for j: W_out (0..n_run-1, j) then the bias chunk j.  Its slots overlay the W_out ring and the
+                // codebook buffers, so it starts once every per-stage MMA has completed (and the last search is over).
+                if (n_final_steps > 0) {
+                    TC_WAIT(&bars[B_MMA_DONE], tpar);
+                    uint32_t m = fn;
+                    for (int j = 0; j < NJ; ++j)
+                        for (int s0 = 0; s0 <= n_run; s0 += F_ITEMS, ++m) {
+                            const uint32_t slot = m % F_SLOTS, use = m / F_SLOTS;
+                            if (use >= 1) TC_WAIT(&bars[B_F_EMPTY + slot], (use - 1) & 1u);
+                            const int s1 = min(s0 + F_ITEMS, n_run + 1);
+                            mbar_arrive_expect_tx(&bars[B_F_FULL + slot], (uint32_t)(s1 - s0) * 8192u);
+                            for (int sx = s0; sx < s1; ++sx) {
+                                const float *src = sx < n_run ? wout + ((size_t)sx * NJ + j) * 3072 : bout + (size_t)j * 2048;
+                                bulk_g2s(smem + SM_WO + slot * F_SLOT + (sx - s0) * 8192, src, 8192, &bars[B_F_FULL + slot]);
+                            }
+                        }
+                }
+            }
+            ph_mark(1);
+            __syncwarp();
+        }
+        wn += (uint32_t)n_stage_steps;
+        fn += (uint32_t)n_final_steps;
+        cbu0 += (uint32_t)((n_run + 1) >> 1);  // buffer 0 serves the even stages, buffer 1 the odd ones
+        cbu1 += (uint32_t)(n_run >> 1);
+        tmem_fence_before_sync();
+        __syncthreads();  // end of tile: every MMA of the tile has completed (the epilogue waited for the last one)
+        tmem_fence_after_sync();
+        ph_mark(7);
+    }
+    if (ph_on)
+        for (int k = 0; k < 8; ++k) p.phase_cycles[((size_t)blockIdx.x * 4 + ph_role) * 8 + k] = ph_acc[k];
+
+    // ---- teardown ----
+    if (w < 4) {
+        // loss: one binary64 atomic per warp; kept counts: one atomic per stage per warp
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+        if (lane == 0 && p.loss_sum != nullptr && loss_acc != 0.0) atomicAdd(p.loss_sum, loss_acc);
+        if (lane < n_run && p.kept != nullptr && kept_acc != 0ull) atomicAdd(&p.kept[lane], kept_acc);
+    }
+    if (w == 12) tmem_dealloc(tmem, TM_COLS);
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static int pick_tiling(int B, int T, int sms, int *adv, int *tiles_per_b) {
+    // tiles of `adv` frames (multiple of 8, <= 128) per batch item; minimise waves x adv (the time of the slowest CTA)
+    const int nt_min = (T + 127) / 128;
+    long best_cost = -1;
+    int best_nt = nt_min, best_adv = 128;
+    for (int nt = nt_min; nt <= nt_min * 4 + 4; ++nt) {
+        int a = ((T + nt - 1) / nt + 7) / 8 * 8;
+        if (a > 128) continue;
+        if (a < 8) a = 8;
+        const int nt_eff = (T + a - 1) / a;
+        const long tiles = (long)B * nt_eff;
+        const long waves = (tiles + sms - 1) / sms;
+        const long cost = waves * (a + 24);  // + a fixed per-tile cost (pipeline fill, first search)
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nt = nt_eff; best_adv = a; }
+    }
+    *adv = best_adv;
+    *tiles_per_b = best_nt;
+    return 0;
+}
+
+int encode_tc_usable(const vrvq_encode_args *a) {
+    return tc_shape_ok(a->input_dim, a->codebook_size, a->n_codebooks) ? 1 : 0;
+}
+
+static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParams &P, int *grid) {
+    P.e = e;
+    const BlobLayout L(a->input_dim, a->codebook_size);
+    const size_t tc_off = (size_t)BLOB_HDR_FLOATS + (size_t)a->n_codebooks * (size_t)L.stage_floats();
+    P.tc = static_cast<const float *>(a->blob) + tc_off;
+    int dev = 0, sms = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    rc = check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+    if (rc) return rc;
+    pick_tiling(a->B, a->T, sms, &P.adv, &P.tiles_per_b);
+    if (const char *dbg = getenv("VRVQ_DEBUG_TILE_FRAMES")) {  // profiling knob
+        const int v = atoi(dbg);
+        if (v >= 8 && v <= 128 && v % 8 == 0) { P.adv = v; P.tiles_per_b = (a->T + v - 1) / v; }
+    }
+    P.n_tiles = P.tiles_per_b * a->B;
+    *grid = P.n_tiles < sms ? P.n_tiles : sms;
+    return VRVQ_OK;
+}
+
+template <int D, bool ZQIS>
+static int launch_tc(const TcParams &P, int grid, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        int rc = check_cuda(cudaFuncSetAttribute(rvq_encode_tc_kernel<D, ZQIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL),
+                            "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
+        if (rc) return rc;
+        attr_done = true;
+    }
+    rvq_encode_tc_kernel<D, ZQIS><<<grid, TC_NTH, SM_TOTAL, st>>>(P);
+    return check_cuda(cudaGetLastError(), "rvq_encode_tc_kernel launch");
+}
+
+int encode_tc_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem) {
+    EncodeParams e{};
+    int rc = fill_encode_params(a, e);
+    if (rc) return rc;
+    TcParams P{};
+    int g = 0;
+    rc = make_params(a, e, P, &g);
+    if (rc) return rc;
+    if (grid) *grid = g;
+    if (block) *block = TC_NTH;
+    if (smem) *smem = SM_TOTAL;
+    return VRVQ_OK;
+}
+
+int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
+    TcParams P{};
+    int grid = 0;
+    int rc = make_params(a, e, P, &grid);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool zqis = a->z_q_is != nullptr;
+    const bool dbg = getenv("VRVQ_DEBUG_PHASES") != nullptr;  // profiling only: synchronises and prints per-phase cycles
+    P.e.phase_cycles = nullptr;
+    if (dbg && cudaMalloc(&P.e.phase_cycles, sizeof(long long) * 32 * (size_t)grid) != cudaSuccess) P.e.phase_cycles = nullptr;
+    switch (a->input_dim) {
+        case 1024: rc = zqis ? launch_tc<1024, true>(P, grid, st) : launch_tc<1024, false>(P, grid, st); break;
+        case 512: rc = zqis ? launch_tc<512, true>(P, grid, st) : launch_tc<512, false>(P, grid, st); break;
+        case 256: rc = zqis ? launch_tc<256, true>(P, grid, st) : launch_tc<256, false>(P, grid, st); break;
+        default: rc = VRVQ_EUNSUPPORTED;
+    }
+    if (dbg && P.e.phase_cycles != nullptr) {
+        static const char *names[4][8] = {
+            {"setup", "phaseL", "L2S_wait", "prep", "search", "merge_corr", "mask_pass", "end_wait"},
+            {"L_idle", "wait_full", "store", "-", "-", "-", "-", "end_wait"},
+            {"phaseL", "L2S_wait", "wait_ready", "stage_units", "wait_zq", "final", "-", "end_wait"},
+            {"phaseL", "phaseS", "-", "-", "-", "-", "-", "end_wait"}};
+        static const char *roles[4] = {"search", "epilogue", "issuer", "producer"};
+        long long *h = static_cast<long long *>(malloc(sizeof(long long) * 32 * (size_t)grid));
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, P.e.phase_cycles, sizeof(long long) * 32 * (size_t)grid, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[vrvq tc phases] grid %d, tile %d frames, %d tiles; mean cycles per CTA\n", grid, P.adv, P.n_tiles);
+        for (int r = 0; r < 4; ++r) {
+            double acc[8] = {0}, tot = 0;
+            for (int g = 0; g < grid; ++g)
+                for (int k = 0; k < 8; ++k) { acc[k] += (double)h[(g * 4 + r) * 8 + k] / grid; tot += (double)h[(g * 4 + r) * 8 + k] / grid; }
+            fprintf(stderr, "  %-8s total %.0f |", roles[r], tot);
+            for (int k = 0; k < 8; ++k)
+                if (names[r][k][0] != '-') fprintf(stderr, " %s %.0f", names[r][k], acc[k]);
+            fprintf(stderr, "\n");
+        }
+        free(h);
+        cudaFree(P.e.phase_cycles);
+    }
+    return rc;
+}
+
+}  // namespace vrvq
