@@ -91,7 +91,8 @@ static float tf32_head(float x) {
 static inline size_t umma_idx(int R, int r, int k) { return ((size_t)(k / 4) * R + r) * 4 + (k % 4); }
 
 // Tensor-core section of the blob (layout: common.cuh TcLayout).  w_in [Nq][8][D], w_out [Nq][D][8], b_out [Nq][D].
-static void pack_tc_section(int Nq, int D, const float *w_in, const float *b_in, const float *w_out, const float *b_out, float *tc) {
+static void pack_tc_section(int Nq, int D, int K, const float *w_in, const float *b_in, const float *w_out, const float *b_out,
+                            const float *codebook, float *tc) {
     const TcLayout T(D, Nq);
     memset(tc, 0, sizeof(float) * (size_t)T.total());
     // WIN: chunk c = channels 32c..32c+31 (k = channel - 32c); rows 0..63 heads (row = 8*stage + out-channel), rows 64..127 remainders
@@ -144,6 +145,15 @@ static void pack_tc_section(int Nq, int D, const float *w_in, const float *b_in,
             }
         }
     memcpy(tc + T.off_bin(), b_in, sizeof(float) * (size_t)Nq * CD);
+    // CBK: F.normalize(codebook) (same arithmetic as the P1 section) as a [2 kg][K][4] tile, then c2[K]
+    for (int s = 0; s < Nq; ++s) {
+        float *cbk = tc + T.off_cbk() + (size_t)s * 9216;
+        for (int j = 0; j < K; ++j) {
+            float e[CD];
+            normalize_row(codebook + ((size_t)s * K + j) * CD, e, cbk + 8192 + j);
+            for (int k = 0; k < CD; ++k) cbk[(size_t)(k / 4) * 4096 + (size_t)j * 4 + (k % 4)] = e[k];
+        }
+    }
 }
 
 }  // namespace vrvq
@@ -219,7 +229,7 @@ int vrvq_pack_weights(int n_codebooks, int input_dim, int codebook_size, int cod
         memcpy(p2 + (size_t)D * CD, b_out + (size_t)s * D, sizeof(float) * D);
         memcpy(raw, cb, sizeof(float) * (size_t)K * CD);
     }
-    if (tc) pack_tc_section(n_codebooks, D, w_in, b_in, w_out, b_out, blob + tc_off);
+    if (tc) pack_tc_section(n_codebooks, D, K, w_in, b_in, w_out, b_out, codebook, blob + tc_off);
     return VRVQ_OK;
 }
 

@@ -133,6 +133,8 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 //   BOUT [D/128 chunks][hi,lo][2 kg][128 rows][4]  bias as a B operand for the final GEMM: element (row, k = stage) = b_out[stage][channel(row)]
 //   GG   [Nq(Nq-1)/2][72]  for j < s: G = W_in[s] W_out[j] (8x8, row-major [c][k]) followed by g = W_in[s] b_out[j] (8)
 //   BIN  [Nq][8] b_in
+//   CBK  [Nq][9216]: normalised codebook as a K-major B operand [2 kg][1024 codes][4] (also read row-wise for the exact re-scoring),
+//        then c2[1024]
 struct TcLayout {
     int D, Nq;
     __host__ __device__ constexpr TcLayout(int d, int nq) : D(d), Nq(nq) {}
@@ -144,7 +146,8 @@ struct TcLayout {
     __host__ __device__ constexpr int off_gg() const { return off_bout() + nj() * 2048; }
     __host__ __device__ constexpr int gg_floats() const { return (Nq * (Nq - 1) / 2 * 72 + 3) / 4 * 4; }
     __host__ __device__ constexpr int off_bin() const { return off_gg() + gg_floats(); }
-    __host__ __device__ constexpr int total() const { return off_bin() + Nq * 8; }
+    __host__ __device__ constexpr int off_cbk() const { return off_bin() + Nq * 8; }
+    __host__ __device__ constexpr int total() const { return off_cbk() + Nq * 9216; }
     __host__ __device__ static constexpr int pair_index(int nq, int j, int s) { return j * nq - j * (j + 1) / 2 + (s - j - 1); }
 };
 constexpr int TC_MAX_NQ = 8;

@@ -35,7 +35,7 @@
 namespace vrvq {
 
 constexpr int TCK = 1024;      // codebook size
-constexpr int TC_NTH = 448;    // 14 warps: 8 search/load, 4 epilogue, MMA issuer, copy producer
+constexpr int TC_NTH = 480;    // 15 warps: 8 search/load, 4 epilogue, MMA issuer, copy producer, search-MMA issuer
 constexpr int TC_NSEARCH = 256;
 
 // shared memory map (bytes).  Phase L uses [0, 147456); phase S re-uses that region.
@@ -46,11 +46,10 @@ constexpr int SM_AM = 65536;       // phase S: mask tile (A operand of the bias 
 constexpr int SM_WO = 69632;       // phase S: W_out ring, 4 slots x 12 KB (hi | lo | bias tile)
 constexpr int SM_CB1 = 118784;     // search codebook buffer 1 (36864 B)
 constexpr int SM_CB0 = 155648;     // search codebook buffer 0 (outside the phase-L region: prefetched during phase L)
-constexpr int SM_ES = 192512;      // [8][128] 2*e
+constexpr int SM_ES = 192512;      // A operand of the search MMA: 2*e as a [2 kg][128 frames][4] tile
 constexpr int SM_E2 = SM_ES + 4096;   // [128]
-constexpr int SM_SB = SM_E2 + 512;    // [8 slices][128] best distance
-constexpr int SM_SI = SM_SB + 4096;   // [8 slices][128] best index
-constexpr int SM_GG = SM_SI + 4096;   // correction matrices, <= 28 x 72 floats
+constexpr int SM_SB = SM_E2 + 512;    // candidate lists: 256 threads x 16 x u32 (16 KB); then [2][128] best distance / index
+constexpr int SM_GG = SM_SB + 16384;   // correction matrices, <= 28 x 72 floats
 constexpr int SM_BIN = SM_GG + 8192;  // b_in [8][8]
 constexpr int SM_NK = SM_BIN + 256;   // keep counts [128]
 constexpr int SM_ONES = SM_NK + 512;  // constant A tile [2 kg][128][4]: k = 0, 1 -> 1.0 (multiplies the bias tile)
@@ -67,13 +66,14 @@ static_assert(L_SLOTS * L_SLOT <= SM_CB0, "phase-L ring must not reach codebook 
 enum {
     B_L_FULL = 0, B_L_EMPTY = 4, B_SET_FULL = 24, B_SET_EMPTY = 26, B_W_FULL = 28, B_W_EMPTY = 32,
     B_D_FULL = 36, B_D_EMPTY = 38, B_CB_FULL = 40, B_A_READY = 42, B_ZQ_READY = 50, B_MMA_DONE = 51, B_F_FULL = 52, B_F_EMPTY = 56,
-    B_COUNT = 60
+    B_E_READY = 60, B_SB_FULL = 61, B_SB_EMPTY = 64, B_COUNT = 67
 };
 
 // TMEM columns: [0,64) running z_e sums of all stages; phase L accumulator sets at 64 + 128*set (hi*hi | lo terms);
 // phase S out_proj ring at 64 + 128*buf.
 constexpr uint32_t TM_COLS = 512;
-constexpr uint32_t TM_RUN = 0, TM_SET = 64;
+constexpr uint32_t TM_RUN = 0, TM_SET = 64, TM_SCORE = 320;  // search scores: 3 x 64 columns at TM_SCORE (chunk g -> buffer g % 3)
+constexpr float SEARCH_MARGIN = 0.012f;  // > 2 x the TF32 score error bound 2^-9 * sum|2 e_k c_k| <= 2^-8 (unit vectors)
 
 // Every wait in this kernel is bounded: a protocol bug traps (and reports which barrier) instead of hanging the GPU.
 __device__ __noinline__ void tc_wait_timeout(const uint64_t *bar, const uint64_t *bars, uint32_t parity) {
@@ -95,6 +95,7 @@ struct TcParams {
     const float *tc;  // TC section of the blob
     int adv;          // frames per tile (multiple of 8, <= 128)
     int tiles_per_b, n_tiles;
+    int dbg;  // VRVQ_DEBUG_TC bit mask (profiling experiments only; results become invalid)
 };
 
 // all K-major no-swizzle tiles of this kernel have 128 rows: LBO = 2048 B (next 4-wide k group), SBO = 128 B (next 8 rows)
@@ -111,8 +112,6 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_TMEM);
     float *es = reinterpret_cast<float *>(smem + SM_ES);
     float *e2s = reinterpret_cast<float *>(smem + SM_E2);
-    float *sbest = reinterpret_cast<float *>(smem + SM_SB);
-    int *sidx = reinterpret_cast<int *>(smem + SM_SI);
     float *ggs = reinterpret_cast<float *>(smem + SM_GG);
     float *bins = reinterpret_cast<float *>(smem + SM_BIN);
     int *nkeep = reinterpret_cast<int *>(smem + SM_NK);
@@ -139,6 +138,8 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         mbar_init(&bars[B_ZQ_READY], 4);
         mbar_init(&bars[B_MMA_DONE], 1);
         for (int i = 0; i < F_SLOTS; ++i) { mbar_init(&bars[B_F_FULL + i], 1); mbar_init(&bars[B_F_EMPTY + i], 1); }
+        mbar_init(&bars[B_E_READY], 4);
+        for (int i = 0; i < 3; ++i) { mbar_init(&bars[B_SB_FULL + i], 1); mbar_init(&bars[B_SB_EMPTY + i], 4); }
         fence_mbar_init();
     }
     if (w == 12) {
@@ -158,8 +159,9 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
 
     // profiling only (VRVQ_DEBUG_PHASES=1): clock64 totals per phase for one thread of each role
     const int ph_role = tid == 0 ? 0 : tid == 256 ? 1 : tid == 384 ? 2 : tid == 416 ? 3 : -1;
+    uint32_t gstage = 0;  // stages processed so far by this CTA (search-score ring / E_READY phase bookkeeping)
     const bool ph_on = p.phase_cycles != nullptr && ph_role >= 0;
-    long long ph_last = 0, ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_last = 0, ph_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (ph_on) ph_last = clock64();
     auto ph_mark = [&](int k) {
         if (ph_on) {
@@ -308,94 +310,154 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                         const float ec = __fdiv_rn(zev[k], den);
                         const float sqe = __fmul_rn(ec, ec);
                         e2 = (k == 0) ? sqe : __fadd_rn(e2, sqe);
-                        es[k * 128 + f] = __fmul_rn(2.0f, ec);
+                        es[(k >> 2) * 512 + f * 4 + (k & 3)] = __fmul_rn(2.0f, ec);
                     }
                     e2s[f] = e2;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[B_E_READY]);  // the search-MMA issuer may start on this stage
                     if (p.latents != nullptr && f < fv) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)(s * 8 + k) * p.lat_sc + t0 + f] = zev[k];
                     }
                 }
-                named_bar_sync(1, TC_NSEARCH);
+                named_bar_sync(1, TC_NSEARCH);  // 2e / e2 of the stage visible to warps 4-7
                 ph_mark(3);
-                if (4 * lane < fv) {  // lanes whose 4 frames lie beyond the tile skip the search (their slots are never read back)
-                    // ---- search: warp w = code slice (pairs 8i + w, ascending), lane = frames 4*lane .. 4*lane+3 ----
-                    const uint32_t use = (s & 1) ? (cbu1 + (uint32_t)(s >> 1)) : (cbu0 + (uint32_t)(s >> 1));
-                    TC_WAIT(&bars[B_CB_FULL + (s & 1)], use & 1u);
+                float bd_pub;
+                int bi_pub;
+                {
+                    // ---- search (quantize.py:96-101): the tensor core scores all 1024 codes per frame (TF32, |error| <= 2^-8),
+                    // each thread scans half of the codes of its frame for scores within SEARCH_MARGIN of the running maximum and
+                    // re-scores those candidates with the reference's exact fp32 arithmetic (first index wins ties) ----
+                    const int h = w >> 2;  // warps 0-3 take the even 64-code chunks (score buffer 0), warps 4-7 the odd ones
+                    const uint32_t cbuse = (s & 1) ? (cbu1 + (uint32_t)(s >> 1)) : (cbu0 + (uint32_t)(s >> 1));
                     const float *CB = reinterpret_cast<const float *>(smem + ((s & 1) ? SM_CB1 : SM_CB0));
-                    const float *c2 = CB + TCK * 8;
-                    float2 e[8][4];
+                    uint32_t *list = reinterpret_cast<uint32_t *>(smem + SM_SB) + tid;  // (group maximum, group id) entries, [entry][thread]: no bank conflicts
+                    const float4 ea = *reinterpret_cast<const float4 *>(&es[f * 4]), eb = *reinterpret_cast<const float4 *>(&es[512 + f * 4]);
+                    const float e2 = e2s[f];
+                    float bd = __int_as_float(0x7f800000);
+                    int bidx = 0x7fffffff;
+                    float runmax = __int_as_float(0xff800000);
+                    int cnt = 0;
+                    for (int ci = 0; ci < 8; ++ci) {
+                        const uint32_t gc = (gstage + (uint32_t)s) * 16u + (uint32_t)(2 * ci + h), sbuf = gc % 3u;
+                        const uint32_t tsc = tq + TM_SCORE + 64u * sbuf;
+                        TC_WAIT(&bars[B_SB_FULL + sbuf], (gc / 3u) & 1u);
+                        tmem_fence_after_sync();
+                        ph_mark(8);
+                        uint32_t va[32], vb[32];
+                        tmem_ld32(tsc, va);
+                        tmem_ld32(tsc + 32, vb);
+                        tmem_wait_ld32(va);
+                        tmem_wait_ld32(vb);
+                        tmem_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars[B_SB_EMPTY + sbuf]);
+                        ph_mark(9);
+                        // maxima of the eight 8-code groups of this chunk (FMNMX3)
+                        float g[8];
+#define VRVQ_GROUP_MAX(dst, v, o)                                                                                                       \
+    {                                                                                                                                   \
+        float m_;                                                                                                                       \
+        asm("max.f32 %0, %1, %2, %3;" : "=f"(m_) : "f"(__uint_as_float(v[o])), "f"(__uint_as_float(v[o + 1])), "f"(__uint_as_float(v[o + 2]))); \
+        asm("max.f32 %0, %1, %2, %3;" : "=f"(m_) : "f"(m_), "f"(__uint_as_float(v[o + 3])), "f"(__uint_as_float(v[o + 4])));               \
+        asm("max.f32 %0, %1, %2, %3;" : "=f"(m_) : "f"(m_), "f"(__uint_as_float(v[o + 5])), "f"(__uint_as_float(v[o + 6])));               \
+        dst = fmaxf(m_, __uint_as_float(v[o + 7]));                                                                                     \
+    }
+                        VRVQ_GROUP_MAX(g[0], va, 0) VRVQ_GROUP_MAX(g[1], va, 8) VRVQ_GROUP_MAX(g[2], va, 16) VRVQ_GROUP_MAX(g[3], va, 24)
+                        VRVQ_GROUP_MAX(g[4], vb, 0) VRVQ_GROUP_MAX(g[5], vb, 8) VRVQ_GROUP_MAX(g[6], vb, 16) VRVQ_GROUP_MAX(g[7], vb, 24)
+#undef VRVQ_GROUP_MAX
+                        float cm;
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(g[0]), "f"(g[1]), "f"(g[2]));
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(cm), "f"(g[3]), "f"(g[4]));
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(cm), "f"(g[5]), "f"(g[6]));
+                        runmax = fmaxf(runmax, fmaxf(cm, g[7]));
+                        const float thr = runmax - SEARCH_MARGIN;
+                        const uint32_t gid0 = (uint32_t)(2 * ci + h) * 8u;  // group id = code / 8
+                        // branch-free append of every group whose maximum is within the margin: entry = (max & ~0xff) | group id
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float4 t = *reinterpret_cast<const float4 *>(&es[k * 128 + 4 * lane]);
-                        e[k][0] = make_float2(t.x, t.x); e[k][1] = make_float2(t.y, t.y);
-                        e[k][2] = make_float2(t.z, t.z); e[k][3] = make_float2(t.w, t.w);
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t entry = (__float_as_uint(g[i]) & 0xffffff00u) | (gid0 + (uint32_t)i);
+                            const uint32_t addr = smem_u32(list) + 1024u * (uint32_t)min(cnt, 15);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p st.shared.u32 [%3], %4;\n\t@p add.s32 %0, %0, 1;\n\t}"
+                                : "+r"(cnt)
+                                : "f"(g[i]), "f"(thr), "r"(addr), "r"(entry)
+                                : "memory");
+                        }
+                        ph_mark(10);
                     }
-                    const float4 e2v = *reinterpret_cast<const float4 *>(&e2s[4 * lane]);
-                    const float e2f[4] = {e2v.x, e2v.y, e2v.z, e2v.w};
-                    float best[4];
-                    int bp[4];  // pair index of the current minimum; which code of the pair is resolved in the merge step
+                    if (!(P.dbg & 2)) TC_WAIT(&bars[B_CB_FULL + (s & 1)], cbuse & 1u);  // (long complete: the score MMAs read the same buffer)
+                    {
+                        // Work list of 8-code groups to re-score exactly.  Normal case: the (<= 3) groups still within the margin of
+                        // the final maximum (the stored maximum lost its low 8 bits: 1e-4 of slack), compacted first so that a warp
+                        // runs the expensive body only max-over-lanes times.  Fallbacks: every listed group (more than 3 hits), or
+                        // every group of this thread's half of the codebook (list overflow: degenerate frames, e.g. an all-zero latent).
+                        const float thr = runmax - SEARCH_MARGIN - 1e-4f;
+                        int c0 = -1, c1 = -1, c2 = -1, nc = 0;
+                        const int nlist = cnt <= 16 ? cnt : 0;
+                        for (int i = 0; i < nlist; ++i) {
+                            const uint32_t entry = list[i * 256];
+                            const bool hit = __uint_as_float(entry & 0xffffff00u) >= thr;
+                            const int gidx = (int)(entry & 0xffu);
+                            c2 = (hit && nc == 2) ? gidx : c2;
+                            c1 = (hit && nc == 1) ? gidx : c1;
+                            c0 = (hit && nc == 0) ? gidx : c0;
+                            nc += hit ? 1 : 0;
+                        }
+                        const int mode = cnt > 16 ? 2 : nc > 3 ? 1 : 0;
+                        const int total = (P.dbg & 1) ? 0 : mode == 2 ? 64 : mode == 1 ? cnt : nc;
+                        for (int wi = 0; wi < total; ++wi) {
+                            int gid;
+                            if (mode == 0) {
+                                gid = wi == 0 ? c0 : wi == 1 ? c1 : c2;
+                            } else if (mode == 1) {
+                                const uint32_t entry = list[wi * 256];
+                                gid = (__uint_as_float(entry & 0xffffff00u) >= thr) ? (int)(entry & 0xffu) : -1;
+                            } else {
+                                gid = (2 * (wi >> 3) + h) * 8 + (wi & 7);
+                            }
+                            if (gid >= 0) {
+                                const float4 *r0 = reinterpret_cast<const float4 *>(CB + gid * 32), *r1 = reinterpret_cast<const float4 *>(CB + 4096 + gid * 32);
+                                const float *c2p = CB + 8192 + gid * 8;
 #pragma unroll
-                    for (int fr = 0; fr < 4; ++fr) { best[fr] = __int_as_float(0x7f800000); bp[fr] = w; }
-#pragma unroll 2
-                    for (int i = 0; i < TCK / 16; ++i) {
-                        const int pr = 8 * i + w;
-                        const float4 *cp = reinterpret_cast<const float4 *>(CB + pr * 16);
-                        const float4 c01 = cp[0], c23 = cp[1], c45 = cp[2], c67 = cp[3];
-                        const float2 cc = *reinterpret_cast<const float2 *>(c2 + 2 * pr);
-#pragma unroll
-                        for (int fr = 0; fr < 4; ++fr) {
-                            float2 d = __fmul2_rn(e[0][fr], make_float2(c01.x, c01.y));
-                            d = __ffma2_rn(e[1][fr], make_float2(c01.z, c01.w), d);
-                            d = __ffma2_rn(e[2][fr], make_float2(c23.x, c23.y), d);
-                            d = __ffma2_rn(e[3][fr], make_float2(c23.z, c23.w), d);
-                            d = __ffma2_rn(e[4][fr], make_float2(c45.x, c45.y), d);
-                            d = __ffma2_rn(e[5][fr], make_float2(c45.z, c45.w), d);
-                            d = __ffma2_rn(e[6][fr], make_float2(c67.x, c67.y), d);
-                            d = __ffma2_rn(e[7][fr], make_float2(c67.z, c67.w), d);
-                            // dist = fl(fl(e2 - dot) + c2)   (quantize.py:96-100)
-                            const float2 t = __fadd2_rn(__fadd2_rn(make_float2(e2f[fr], e2f[fr]), make_float2(-d.x, -d.y)), cc);
-                            float nb;
-                            asm("min.f32 %0, %1, %2, %3;" : "=f"(nb) : "f"(best[fr]), "f"(t.x), "f"(t.y));  // FMNMX3
-                            if (nb < best[fr]) bp[fr] = pr;  // strict: the first pair reaching the minimum wins
-                            best[fr] = nb;
+                                for (int j8 = 0; j8 < 8; ++j8) {  // exact distance of code 8*gid + jj; lexicographic (distance, index) minimum
+                                    const int jj = (j8 + lane) & 7;  // lane-staggered: the rows of different groups share their banks
+                                    const float4 ca = r0[jj], cb4 = r1[jj];
+                                    float d = __fmul_rn(ea.x, ca.x);
+                                    d = __fmaf_rn(ea.y, ca.y, d); d = __fmaf_rn(ea.z, ca.z, d); d = __fmaf_rn(ea.w, ca.w, d);
+                                    d = __fmaf_rn(eb.x, cb4.x, d); d = __fmaf_rn(eb.y, cb4.y, d); d = __fmaf_rn(eb.z, cb4.z, d); d = __fmaf_rn(eb.w, cb4.w, d);
+                                    const float t = __fadd_rn(__fadd_rn(e2, -d), c2p[jj]);  // dist = fl(fl(e2 - dot) + c2)
+                                    const int jx = gid * 8 + jj;
+                                    if (t < bd || (t == bd && jx < bidx)) { bd = t; bidx = jx; }
+                                }
+                            }
                         }
                     }
-                    *reinterpret_cast<float4 *>(&sbest[w * 128 + 4 * lane]) = make_float4(best[0], best[1], best[2], best[3]);
-                    *reinterpret_cast<int4 *>(&sidx[w * 128 + 4 * lane]) = make_int4(bp[0], bp[1], bp[2], bp[3]);
+                    ph_mark(11);
+                    bd_pub = bd;
+                    bi_pub = bidx;
+                }
+                named_bar_sync(1, TC_NSEARCH);
+                {
+                    float *sbd = reinterpret_cast<float *>(smem + SM_SB);  // [2][128] best distance, [2][128] best index
+                    int *sbi = reinterpret_cast<int *>(smem + SM_SB + 1024);
+                    sbd[(w >> 2) * 128 + f] = bd_pub;
+                    sbi[(w >> 2) * 128 + f] = bi_pub;
                 }
                 named_bar_sync(1, TC_NSEARCH);
                 ph_mark(4);
                 if (w < 4) {
-                    // ---- argmin merge (first index on ties), gather, loss, straight-through (quantize.py:69-75,81-85,102) ----
-                    float best = sbest[f];
-                    int bpair = sidx[f];
-#pragma unroll
-                    for (int sl = 1; sl < 8; ++sl) {
-                        const float ob = sbest[sl * 128 + f];
-                        const int oi = sidx[sl * 128 + f];
-                        if (ob < best || (ob == best && oi < bpair)) { best = ob; bpair = oi; }
+                    // ---- merge of the two halves (first index on ties), gather, loss, straight-through (quantize.py:69-75,81-85,102) ----
+                    const float *sbd = reinterpret_cast<const float *>(smem + SM_SB);
+                    const int *sbi = reinterpret_cast<const int *>(smem + SM_SB + 1024);
+                    float best = sbd[f];
+                    int bi = sbi[f];
+                    {
+                        const float ob = sbd[128 + f];
+                        const int oi = sbi[128 + f];
+                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
                     }
-                    if (f >= fv) bpair = 0;  // lanes beyond the tile were not searched: any valid pair
-                    int bi;
-                    {   // which code of the winning pair: recompute its two distances with the search loop's exact arithmetic
-                        const float *CB = reinterpret_cast<const float *>(smem + ((s & 1) ? SM_CB1 : SM_CB0));
-                        const float4 *cp = reinterpret_cast<const float4 *>(CB + bpair * 16);
-                        const float4 c01 = cp[0], c23 = cp[1], c45 = cp[2], c67 = cp[3];
-                        const float2 cc = *reinterpret_cast<const float2 *>(CB + TCK * 8 + 2 * bpair);
-                        const float ca[8] = {c01.x, c01.z, c23.x, c23.z, c45.x, c45.z, c67.x, c67.z};
-                        const float cb[8] = {c01.y, c01.w, c23.y, c23.w, c45.y, c45.w, c67.y, c67.w};
-                        float da = 0.f, db = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const float ek = es[k * 128 + f];
-                            da = (k == 0) ? __fmul_rn(ek, ca[0]) : __fmaf_rn(ek, ca[k], da);
-                            db = (k == 0) ? __fmul_rn(ek, cb[0]) : __fmaf_rn(ek, cb[k], db);
-                        }
-                        const float e2 = e2s[f];
-                        const float ta = __fadd_rn(__fadd_rn(e2, -da), cc.x), tb = __fadd_rn(__fadd_rn(e2, -db), cc.y);
-                        bi = 2 * bpair + ((tb < ta) ? 1 : 0);
-                    }
+                    if (bi >= TCK) bi = 0;  // no candidate at all (NaN latent): code 0, like an argmin over NaNs that never updates
                     const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)s * L.stage_floats() + L.off_raw() + (size_t)bi * 8);
                     const float4 ra = __ldg(rawp), rb = __ldg(rawp + 1);
                     const float cr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
@@ -640,6 +702,37 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                 }
             }
             __syncwarp();
+        } else if (w == 14) {
+            // =====================================================================================================
+            // Search-MMA issuer: lane 0 of warp 14.  Per stage, 16 MMAs of M = 128 frames x N = 64 codes x K = 8 (plain TF32)
+            // into three rotating 64-column score buffers; chunk c is scanned by warps 4(c%2) .. 4(c%2)+3.
+            // =====================================================================================================
+            __syncwarp();
+            tmem_fence_before_sync();
+            __syncthreads();  // L -> S
+            tmem_fence_after_sync();
+            if (lane == 0) {
+                constexpr uint32_t ID_S = umma_idesc_tf32(128, 64);
+                // codebook tile: 1024 rows -> LBO = 16384 B, SBO = 128 B
+                constexpr uint64_t DESC_CB = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)(16384 >> 4) << 16);
+                const uint64_t ae = desc128(smem_base + SM_ES);
+                for (int s = 0; s < n_run; ++s) {
+                    const uint32_t gs = gstage + (uint32_t)s;
+                    TC_WAIT(&bars[B_E_READY], gs & 1u);
+                    const uint32_t cbuse = (s & 1) ? (cbu1 + (uint32_t)(s >> 1)) : (cbu0 + (uint32_t)(s >> 1));
+                    TC_WAIT(&bars[B_CB_FULL + (s & 1)], cbuse & 1u);
+                    fence_proxy_async();
+                    const uint64_t cb = DESC_CB | (uint64_t)((smem_base + ((s & 1) ? SM_CB1 : SM_CB0)) >> 4);
+                    for (int c = 0; c < 16; ++c) {
+                        const uint32_t gc = gs * 16u + (uint32_t)c, sbuf = gc % 3u, use = gc / 3u;
+                        if (use >= 1) TC_WAIT(&bars[B_SB_EMPTY + sbuf], (use - 1) & 1u);
+                        tmem_fence_after_sync();
+                        umma_tf32(tmem + TM_SCORE + 64u * sbuf, ae, cb + (uint64_t)(c * (64 * 16 >> 4)), ID_S, false);
+                        umma_commit(&bars[B_SB_FULL + sbuf]);
+                    }
+                }
+            }
+            __syncwarp();
         } else {
             // =====================================================================================================
             // Copy producer: lane 0 of warp 13 issues every cp.async.bulk (W_in ring, W_out ring, search codebooks).
@@ -648,7 +741,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                 const float *win = P.tc + TL.off_win();
                 // codebook of stage 0 (its buffer is outside the phase-L region)
                 mbar_arrive_expect_tx(&bars[B_CB_FULL + 0], 36864);
-                bulk_g2s(smem + SM_CB0, stages + L.off_p1(), 36864, &bars[B_CB_FULL + 0]);
+                bulk_g2s(smem + SM_CB0, P.tc + TL.off_cbk(), 36864, &bars[B_CB_FULL + 0]);
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t m = lbase + (uint32_t)c, slot = m % L_SLOTS, use = m / L_SLOTS;
                     if (use >= 1) TC_WAIT(&bars[B_L_EMPTY + slot], (use - 1) & 1u);
@@ -664,7 +757,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
             if (lane == 0) {
                 if (n_run > 1) {  // codebook of stage 1 (its buffer is inside the phase-L region)
                     mbar_arrive_expect_tx(&bars[B_CB_FULL + 1], 36864);
-                    bulk_g2s(smem + SM_CB1, stages + (size_t)1 * L.stage_floats() + L.off_p1(), 36864, &bars[B_CB_FULL + 1]);
+                    bulk_g2s(smem + SM_CB1, P.tc + TL.off_cbk() + 9216, 36864, &bars[B_CB_FULL + 1]);
                 }
                 // W_out ring of the per-stage out_proj: chunk (s, j), row-major; refills of the search codebooks interleaved
                 const float *wout = P.tc + TL.off_wout();
@@ -686,7 +779,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                         // the search group is done with the codebook of stage cs: refill its buffer
                         if (cs + 2 < n_run) {
                             mbar_arrive_expect_tx(&bars[B_CB_FULL + (cs & 1)], 36864);
-                            bulk_g2s(smem + ((cs & 1) ? SM_CB1 : SM_CB0), stages + (size_t)(cs + 2) * L.stage_floats() + L.off_p1(), 36864,
+                            bulk_g2s(smem + ((cs & 1) ? SM_CB1 : SM_CB0), P.tc + TL.off_cbk() + (size_t)(cs + 2) * 9216, 36864,
                                      &bars[B_CB_FULL + (cs & 1)]);
                         }
                         ++cs;
@@ -718,6 +811,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         }
         wn += (uint32_t)n_stage_steps;
         fn += (uint32_t)n_final_steps;
+        gstage += (uint32_t)n_run;
         cbu0 += (uint32_t)((n_run + 1) >> 1);  // buffer 0 serves the even stages, buffer 1 the odd ones
         cbu1 += (uint32_t)(n_run >> 1);
         tmem_fence_before_sync();
@@ -726,7 +820,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         ph_mark(7);
     }
     if (ph_on)
-        for (int k = 0; k < 8; ++k) p.phase_cycles[((size_t)blockIdx.x * 4 + ph_role) * 8 + k] = ph_acc[k];
+        for (int k = 0; k < 16; ++k) p.phase_cycles[((size_t)blockIdx.x * 4 + ph_role) * 16 + k] = ph_acc[k];
 
     // ---- teardown ----
     if (w < 4) {
@@ -780,6 +874,7 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
         if (v >= 8 && v <= 128 && v % 8 == 0) { P.adv = v; P.tiles_per_b = (a->T + v - 1) / v; }
     }
     P.n_tiles = P.tiles_per_b * a->B;
+    P.dbg = getenv("VRVQ_DEBUG_TC") ? atoi(getenv("VRVQ_DEBUG_TC")) : 0;
     *grid = P.n_tiles < sms ? P.n_tiles : sms;
     return VRVQ_OK;
 }
@@ -820,7 +915,7 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
     const bool zqis = a->z_q_is != nullptr;
     const bool dbg = getenv("VRVQ_DEBUG_PHASES") != nullptr;  // profiling only: synchronises and prints per-phase cycles
     P.e.phase_cycles = nullptr;
-    if (dbg && cudaMalloc(&P.e.phase_cycles, sizeof(long long) * 32 * (size_t)grid) != cudaSuccess) P.e.phase_cycles = nullptr;
+    if (dbg && cudaMalloc(&P.e.phase_cycles, sizeof(long long) * 64 * (size_t)grid) != cudaSuccess) P.e.phase_cycles = nullptr;
     switch (a->input_dim) {
         case 1024: rc = zqis ? launch_tc<1024, true>(P, grid, st) : launch_tc<1024, false>(P, grid, st); break;
         case 512: rc = zqis ? launch_tc<512, true>(P, grid, st) : launch_tc<512, false>(P, grid, st); break;
@@ -828,22 +923,22 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
         default: rc = VRVQ_EUNSUPPORTED;
     }
     if (dbg && P.e.phase_cycles != nullptr) {
-        static const char *names[4][8] = {
-            {"setup", "phaseL", "L2S_wait", "prep", "search", "merge_corr", "mask_pass", "end_wait"},
-            {"L_idle", "wait_full", "store", "-", "-", "-", "-", "end_wait"},
-            {"phaseL", "L2S_wait", "wait_ready", "stage_units", "wait_zq", "final", "-", "end_wait"},
-            {"phaseL", "phaseS", "-", "-", "-", "-", "-", "end_wait"}};
+        static const char *names[4][16] = {
+            {"setup", "phaseL", "L2S_wait", "prep", "search_tail", "merge_corr", "mask_pass", "end_wait", "scan:wait_full", "scan:ld", "scan:filter", "scan:rescore", "#cnt", "#nc", "#warpmaxcnt", "-"},
+            {"L_idle", "wait_full", "store", "-", "-", "-", "-", "end_wait", "-", "-", "-", "-", "-", "-", "-", "-"},
+            {"phaseL", "L2S_wait", "wait_ready", "stage_units", "wait_zq", "final", "-", "end_wait", "-", "-", "-", "-", "-", "-", "-", "-"},
+            {"phaseL", "phaseS", "-", "-", "-", "-", "-", "end_wait", "-", "-", "-", "-", "-", "-", "-", "-"}};
         static const char *roles[4] = {"search", "epilogue", "issuer", "producer"};
-        long long *h = static_cast<long long *>(malloc(sizeof(long long) * 32 * (size_t)grid));
+        long long *h = static_cast<long long *>(malloc(sizeof(long long) * 64 * (size_t)grid));
         cudaStreamSynchronize(st);
-        cudaMemcpy(h, P.e.phase_cycles, sizeof(long long) * 32 * (size_t)grid, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h, P.e.phase_cycles, sizeof(long long) * 64 * (size_t)grid, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[vrvq tc phases] grid %d, tile %d frames, %d tiles; mean cycles per CTA\n", grid, P.adv, P.n_tiles);
         for (int r = 0; r < 4; ++r) {
-            double acc[8] = {0}, tot = 0;
+            double acc[16] = {0}, tot = 0;
             for (int g = 0; g < grid; ++g)
-                for (int k = 0; k < 8; ++k) { acc[k] += (double)h[(g * 4 + r) * 8 + k] / grid; tot += (double)h[(g * 4 + r) * 8 + k] / grid; }
+                for (int k = 0; k < 16; ++k) { acc[k] += (double)h[(g * 4 + r) * 16 + k] / grid; if (k < 12) tot += (double)h[(g * 4 + r) * 16 + k] / grid; }
             fprintf(stderr, "  %-8s total %.0f |", roles[r], tot);
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < 16; ++k)
                 if (names[r][k][0] != '-') fprintf(stderr, " %s %.0f", names[r][k], acc[k]);
             fprintf(stderr, "\n");
         }
