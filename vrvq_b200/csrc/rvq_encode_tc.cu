@@ -93,7 +93,7 @@ __device__ __noinline__ void tc_wait_timeout(const uint64_t *bar, const uint64_t
 struct TcParams {
     EncodeParams e;
     const float *tc;  // TC section of the blob
-    int adv;          // frames per tile (multiple of 8, <= 128)
+    int adv;          // frames per tile (multiple of 8, <= 120)
     int tiles_per_b, n_tiles;
     int dbg;  // VRVQ_DEBUG_TC bit mask (profiling experiments only; results become invalid)
 };
@@ -101,6 +101,26 @@ struct TcParams {
 // all K-major no-swizzle tiles of this kernel have 128 rows: LBO = 2048 B (next 4-wide k group), SBO = 128 B (next 8 rows)
 constexpr uint64_t DESC_128 = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)(2048 >> 4) << 16);
 __device__ __forceinline__ uint64_t desc128(uint32_t saddr) { return DESC_128 | (uint64_t)(saddr >> 4); }
+
+// Sector-aligned stores.  TMEM lane r of an out_proj accumulator holds frame t0 - 8 + delta + r, where delta in [1, 8] is the
+// A-operand row shift of the MMA that produced it (tile row r' <-> frame t0 - 8 + r': rows 0-7 are the previous tile's last
+// frames, re-computed here as a halo).  delta is chosen per channel class p = channel % 4 (column 32p + i of a 128-channel unit
+// holds channel 128j + 4i + p) so that each warp-level store of 32 consecutive frames of one channel row starts on a 32-byte
+// sector: with an even row pitch the start alignment of a row only depends on p.  Odd pitches get delta = 8 (no shift).
+// Returns delta_p for p = 0..3 packed in 4 bytes; base8 = float index of (row 128j, frame t0 - 8) modulo 8, same for every j.
+__device__ __forceinline__ uint32_t class_shifts(uint32_t base8, long long rstride) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+        uint32_t c = (base8 + (uint32_t)pc * (uint32_t)(rstride & 7)) & 7u;
+        uint32_t dl = (rstride & 1) ? 8u : (c == 0u ? 8u : 8u - c);
+        packed |= dl << (8 * pc);
+    }
+    return packed;
+}
+__device__ __forceinline__ uint32_t base_mod8(const float *ptr, long long off) {
+    return (uint32_t)(((reinterpret_cast<uintptr_t>(ptr) >> 2) + (unsigned long long)off) & 7ull);
+}
 
 template <int D, bool ZQIS>
 __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P) {
@@ -180,7 +200,8 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         const int b = tile / P.tiles_per_b;
         const int t0 = (tile % P.tiles_per_b) * P.adv;
-        const int fv = min(P.adv, p.T - t0);  // valid frames (lanes) of this tile
+        const int fv = min(P.adv, p.T - t0);  // frames this tile owns: tile rows 8 .. 8+fv-1 (rows 0-7: halo = the previous 8 frames)
+        const bool last_tile = (tile % P.tiles_per_b) == P.tiles_per_b - 1;
         const uint32_t lbase = (uint32_t)it * NCH, gbase = (uint32_t)it * NG;
         const uint32_t tpar = (uint32_t)it & 1u;
         const int n_stage_steps = ZQIS ? n_run * NJ : 0;
@@ -190,15 +211,18 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
             // =====================================================================================================
             // Search group.  Frame threads (warps 0-3): f = tid = TMEM lane.
             // =====================================================================================================
-            const int f = tid & 127;
+            const int f = tid & 127;            // tile row = TMEM lane
+            const int fr = t0 - 8 + f;          // its frame
+            const bool own = f >= 8 && f - 8 < fv;              // frames whose per-frame outputs this tile writes
+            const bool inb = fr >= 0 && (f < 8 || f - 8 < fv);  // rows that hold a real frame (halo rows of the first tile do not)
             const uint32_t tq = tmem + ((uint32_t)(32 * (w & 3)) << 16);  // this warp's lane quarter
             if (w < 4) {
                 // ---- keep counts, mask, kept-frame counts (quantize.py:389, utils.py:59-60) ----
                 int nk = 0;
-                if (f < fv) {
+                if (own) {
                     if (p.imp != nullptr) {
                         const float lv = p.level_dev ? p.level_dev[(long long)b * p.level_stride] : p.level_host;
-                        const float x = __fmul_rn(__fmul_rn(p.imp[(long long)b * p.imp_sb + t0 + f], lv), (float)Nq);
+                        const float x = __fmul_rn(__fmul_rn(p.imp[(long long)b * p.imp_sb + fr], lv), (float)Nq);
                         for (int k = 0; k < n_run; ++k) nk += (__fsub_rn(x, (float)k) >= 0.0f) ? 1 : 0;
                     } else {
                         nk = n_run;
@@ -209,15 +233,15 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                     const bool on = nk > k;
                     const unsigned bal = __ballot_sync(0xffffffffu, on);
                     if (lane == k) kept_acc += (unsigned long long)__popc(bal);
-                    if (p.mask != nullptr && f < fv) p.mask[(long long)b * p.mask_sb + (long long)k * p.mask_sq + t0 + f] = on ? 1.0f : 0.0f;
+                    if (p.mask != nullptr && own) p.mask[(long long)b * p.mask_sb + (long long)k * p.mask_sq + fr] = on ? 1.0f : 0.0f;
                 }
             }
             ph_mark(0);
             // ---- phase L: load, split, stage (256 threads: frame f, half q of each 32-channel chunk) ----
             {
                 const int q = tid >> 7;
-                const bool valid = f < fv;
-                const float *zp = p.z + (long long)b * p.z_sb + t0 + f + (long long)(16 * q) * p.z_sd;
+                const bool valid = inb;
+                const float *zp = p.z + (long long)b * p.z_sb + fr + (long long)(16 * q) * p.z_sd;
                 const long long zstep = 32 * p.z_sd;
                 float x[2][16];
                 auto ldchunk = [&](const float *src, float (&v)[16]) {
@@ -315,9 +339,9 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                     e2s[f] = e2;
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars[B_E_READY]);  // the search-MMA issuer may start on this stage
-                    if (p.latents != nullptr && f < fv) {
+                    if (p.latents != nullptr && own) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)(s * 8 + k) * p.lat_sc + t0 + f] = zev[k];
+                        for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)(s * 8 + k) * p.lat_sc + fr] = zev[k];
                     }
                 }
                 named_bar_sync(1, TC_NSEARCH);  // 2e / e2 of the stage visible to warps 4-7
@@ -469,10 +493,10 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                         ls = (k == 0) ? sq : __fadd_rn(ls, sq);
                         qv[k] = __fadd_rn(zev[k], __fsub_rn(cr[k], zev[k]));
                     }
-                    if (f < fv) {
+                    if (own) {
                         const float loss = __fdiv_rn(ls, 8.0f);
-                        p.codes[(long long)b * p.codes_sb + (long long)s * p.codes_sq + t0 + f] = (long long)bi;
-                        if (p.loss_pf != nullptr) p.loss_pf[(long long)b * p.loss_sb + (long long)s * p.loss_sq + t0 + f] = loss;
+                        p.codes[(long long)b * p.codes_sb + (long long)s * p.codes_sq + fr] = (long long)bi;
+                        if (p.loss_pf != nullptr) p.loss_pf[(long long)b * p.loss_sb + (long long)s * p.loss_sq + fr] = loss;
                         if (nkeep[f] > s) loss_acc += (double)loss;
                     }
                     // A operand of this stage's out_proj: q split into TF32 head and remainder
@@ -542,25 +566,31 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
             ph_mark(0);
-            const int q4 = w - 8, f = 32 * q4 + lane;
-            const bool valid = f < fv;
+            const int q4 = w - 8, r = 32 * q4 + lane;  // TMEM lane
             const uint32_t tq = tmem + ((uint32_t)(32 * q4) << 16);
-            // one unit = 128 channels x 128 frames: column 32*piece + i of the TMEM buffer <-> channel 128j + 4i + piece
-            auto unit = [&](float *outj, long long rstride) {  // outj = row 128j of the output at this thread's frame
+            // One unit = 128 channels x 128 lanes: column 32p + i of the TMEM buffer <-> channel 128j + 4i + p, lane r <-> frame
+            // t0 - 8 + delta_p + r.  The tile owns, per class, the frames [t0 - 8 + delta_p, t0 + adv - 8 + delta_p) (the last tile of
+            // an item up to T), so consecutive tiles cover every row exactly once and every 32-lane store starts on a sector.
+            auto unit = [&](float *row0, long long rstride, uint32_t shifts) {  // row0 = (row 128j, frame 0) of the output
                 const uint32_t buf = dn & 1u;
                 TC_WAIT(&bars[B_D_FULL + buf], (dn >> 1) & 1u);
                 tmem_fence_after_sync();
                 ph_mark(1);
                 const uint32_t tcol = tq + TM_SET + 128u * buf;
-                const long long step = 4 * rstride;
+                const uint32_t stepb = (uint32_t)(16 * rstride);  // bytes between channels 4 apart (row pitch < 2^28 floats: checked on the host)
                 uint32_t va[32], vb[32];
                 auto put = [&](const uint32_t (&v)[32], int piece) {
-                    if (valid) {
-                        float *o = outj + (long long)piece * rstride;
+                    const int dl = (int)((shifts >> (8 * piece)) & 0xffu);
+                    const int frame = t0 - 8 + dl + r;
+                    const bool ok = frame >= 0 && (last_tile ? frame < p.T : r < P.adv);
+                    if (ok) {
+                        const unsigned long long o = reinterpret_cast<unsigned long long>(row0 + (long long)piece * rstride + frame);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            st_cs(o, __uint_as_float(v[i]));
-                            o += step;
+                            // one independent IMAD.WIDE per address (a running 64-bit pointer costs a 4-instruction dependent chain per store)
+                            unsigned long long a;
+                            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(stepb), "r"((uint32_t)i), "l"(o));
+                            asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(a), "f"(__uint_as_float(v[i])) : "memory");
                         }
                     }
                 };
@@ -584,19 +614,20 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
             };
             if (ZQIS) {
                 for (int s = 0; s < n_run; ++s) {
-                    float *outp = p.z_q_is + (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + t0 + f;
-                    for (int j = 0; j < NJ; ++j) unit(outp + (long long)(128 * j) * p.zqis_sd, p.zqis_sd);
+                    const long long off = (long long)b * p.zqis_sb + (long long)s * p.zqis_sq;
+                    const uint32_t shifts = class_shifts(base_mod8(p.z_q_is, off + t0), p.zqis_sd);
+                    for (int j = 0; j < NJ; ++j) unit(p.z_q_is + off + (long long)(128 * j) * p.zqis_sd, p.zqis_sd, shifts);
                 }
             }
-            if (p.z_q != nullptr) {
-                float *outp = p.z_q + (long long)b * p.zq_sb + t0 + f;
-                for (int j = 0; j < NJ; ++j) unit(outp + (long long)(128 * j) * p.zq_sd, p.zq_sd);
+            if (p.z_q != nullptr) {  // the final GEMM uses delta = 8 for every class: lane r <-> frame t0 + r
+                float *outp = p.z_q + (long long)b * p.zq_sb;
+                for (int j = 0; j < NJ; ++j) unit(outp + (long long)(128 * j) * p.zq_sd, p.zq_sd, 0x08080808u);
             }
         } else if (w == 12) {
             // =====================================================================================================
             // MMA issuer: lane 0 of warp 12.
             // =====================================================================================================
-            constexpr uint32_t ID_128 = umma_idesc_tf32(128, 128), ID_64 = umma_idesc_tf32(128, 64);
+            constexpr uint32_t ID_128 = umma_idesc_tf32(128, 128), ID_64 = umma_idesc_tf32(128, 64), ID_32 = umma_idesc_tf32(128, 32);
             if (lane == 0) {
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS;
@@ -648,15 +679,30 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                     ph_mark(2);
                     if (ZQIS) {
                         const uint64_t ah = desc128(smem_base + SM_AT + s * 8192), al = ah + (4096 >> 4);
+                        // A-operand row shift per channel class (one tile row = 16 bytes = one unit of the descriptor address)
+                        const uint32_t shifts = class_shifts(base_mod8(p.z_q_is, (long long)b * p.zqis_sb + (long long)s * p.zqis_sq + t0), p.zqis_sd);
+                        const bool uniform = shifts == (shifts & 0xffu) * 0x01010101u;
                         for (int j = 0; j < NJ; ++j) {
                             const uint64_t wb = take_w();  // hi tile; lo at +4096 B, bias tile at +8192 B
                             const uint32_t buf = wait_dbuf();
                             tmem_fence_after_sync();
                             const uint32_t d = tmem + TM_SET + 128u * buf;
-                            umma_tf32(d, al, wb, ID_128, false);
-                            umma_tf32(d, ah, wb + (4096 >> 4), ID_128, true);
-                            umma_tf32(d, ones, wb + (8192 >> 4), ID_128, true);
-                            umma_tf32(d, ah, wb, ID_128, true);
+                            if (uniform) {
+                                const uint64_t sh = shifts & 0xffu;
+                                umma_tf32(d, al + sh, wb, ID_128, false);
+                                umma_tf32(d, ah + sh, wb + (4096 >> 4), ID_128, true);
+                                umma_tf32(d, ones, wb + (8192 >> 4), ID_128, true);
+                                umma_tf32(d, ah + sh, wb, ID_128, true);
+                            } else {
+#pragma unroll
+                                for (int pc = 0; pc < 4; ++pc) {  // class pc: B rows / D columns 32pc .. 32pc+31
+                                    const uint64_t sh = (shifts >> (8 * pc)) & 0xffu, wp = wb + 32 * pc;
+                                    umma_tf32(d + 32 * pc, al + sh, wp, ID_32, false);
+                                    umma_tf32(d + 32 * pc, ah + sh, wp + (4096 >> 4), ID_32, true);
+                                    umma_tf32(d + 32 * pc, ones, wp + (8192 >> 4), ID_32, true);
+                                    umma_tf32(d + 32 * pc, ah + sh, wp, ID_32, true);
+                                }
+                            }
                             release_w();
                             umma_commit(&bars[B_D_FULL + buf]);
                             ++dn;
@@ -670,7 +716,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                     fence_proxy_async();
                     tmem_fence_after_sync();
                     ph_mark(4);
-                    const uint64_t am = desc128(smem_base + SM_AM);
+                    const uint64_t am = desc128(smem_base + SM_AM) + 8;
                     uint32_t fstep = fn;
                     for (int j = 0; j < NJ; ++j) {
                         const uint32_t buf = wait_dbuf();
@@ -683,7 +729,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                             for (int s = s0; s < s1; ++s) {
                                 const uint64_t wb = desc128(smem_base + SM_WO + slot * F_SLOT + (s - s0) * 8192);
                                 if (s < n_run) {
-                                    const uint64_t ah = desc128(smem_base + SM_AT + s * 8192), al = ah + (4096 >> 4);
+                                    const uint64_t ah = desc128(smem_base + SM_AT + s * 8192) + 8, al = ah + (4096 >> 4);  // + 8 rows: skip the halo
                                     umma_tf32(d, al, wb, ID_128, s > 0);
                                     umma_tf32(d, ah, wb + (4096 >> 4), ID_128, true);
                                     umma_tf32(d, ah, wb, ID_128, true);
@@ -835,13 +881,13 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
 
 // ---- host side -----------------------------------------------------------------------------------
 static int pick_tiling(int B, int T, int sms, int *adv, int *tiles_per_b) {
-    // tiles of `adv` frames (multiple of 8, <= 128) per batch item; minimise waves x adv (the time of the slowest CTA)
-    const int nt_min = (T + 127) / 128;
+    // tiles of `adv` frames (multiple of 8, <= 120: 8 of the 128 rows are the halo) per batch item; minimise waves x adv
+    const int nt_min = (T + 119) / 120;
     long best_cost = -1;
-    int best_nt = nt_min, best_adv = 128;
+    int best_nt = nt_min, best_adv = 120;
     for (int nt = nt_min; nt <= nt_min * 4 + 4; ++nt) {
         int a = ((T + nt - 1) / nt + 7) / 8 * 8;
-        if (a > 128) continue;
+        if (a > 120) continue;
         if (a < 8) a = 8;
         const int nt_eff = (T + a - 1) / a;
         const long tiles = (long)B * nt_eff;
@@ -871,7 +917,7 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
     pick_tiling(a->B, a->T, sms, &P.adv, &P.tiles_per_b);
     if (const char *dbg = getenv("VRVQ_DEBUG_TILE_FRAMES")) {  // profiling knob
         const int v = atoi(dbg);
-        if (v >= 8 && v <= 128 && v % 8 == 0) { P.adv = v; P.tiles_per_b = (a->T + v - 1) / v; }
+        if (v >= 8 && v <= 120 && v % 8 == 0) { P.adv = v; P.tiles_per_b = (a->T + v - 1) / v; }
     }
     P.n_tiles = P.tiles_per_b * a->B;
     P.dbg = getenv("VRVQ_DEBUG_TC") ? atoi(getenv("VRVQ_DEBUG_TC")) : 0;
