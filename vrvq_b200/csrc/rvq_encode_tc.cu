@@ -38,9 +38,9 @@ constexpr int TCK = 1024;      // codebook size
 constexpr int TC_NTH = 480;    // 15 warps: 8 search/load, 4 epilogue, MMA issuer, copy producer, search-MMA issuer
 constexpr int TC_NSEARCH = 256;
 
-// shared memory map (bytes).  Phase L uses [0, 147456); phase S re-uses that region.
-constexpr int SM_LR = 0;           // phase L ring, 3 slots x 48 KB: A hi [8 kg][128 frames][4] | A lo | W_in [8 kg][128 rows][4]
-constexpr int L_SLOT = 49152, L_SLOTS = 3;  // (W_in rows 0-63 heads, 64-127 remainders)
+// shared memory map (bytes).  Phase L uses [0, 49152); phase S re-uses that region.
+constexpr int SM_LR = 0;           // phase L ring, 3 slots x 16 KB: W_in [8 kg][128 rows][4] (rows 0-63 heads, 64-127 remainders);
+constexpr int L_SLOT = 16384, L_SLOTS = 3;  // the matching A operand (the split latent chunk) lives in tensor memory
 constexpr int SM_AT = 0;           // phase S: per-stage A tiles, 8 x (hi 4 KB | lo 4 KB): [2 kg][128 frames][4]
 constexpr int SM_AM = 65536;       // phase S: mask tile (A operand of the bias rows of the final GEMM) [2 kg][128][4]
 constexpr int SM_WO = 69632;       // phase S: W_out ring, 4 slots x 12 KB (hi | lo | bias tile)
@@ -73,6 +73,7 @@ enum {
 // phase S out_proj ring at 64 + 128*buf.
 constexpr uint32_t TM_COLS = 512;
 constexpr uint32_t TM_RUN = 0, TM_SET = 64, TM_SCORE = 320;  // search scores: 3 x 64 columns at TM_SCORE (chunk g -> buffer g % 3)
+constexpr uint32_t TM_AL = 320;  // phase L: A-operand ring, 3 slots x (32 columns heads | 32 columns remainders) of one 32-channel chunk
 constexpr float SEARCH_MARGIN = 0.012f;  // > 2 x the TF32 score error bound 2^-9 * sum|2 e_k c_k| <= 2^-8 (unit vectors)
 
 // Every wait in this kernel is bounded: a protocol bug traps (and reports which barrier) instead of hanging the GPU.
@@ -122,7 +123,7 @@ __device__ __forceinline__ uint32_t base_mod8(const float *ptr, long long off) {
     return (uint32_t)(((reinterpret_cast<uintptr_t>(ptr) >> 2) + (unsigned long long)off) & 7ull);
 }
 
-template <int D, bool ZQIS>
+template <int D, bool ZQIS, bool PROFILE>
 __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P) {
     constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;  // 32-channel chunks, accumulator drained every 4 chunks
     static_assert(NCH % 4 == 0, "D must be a multiple of 128");
@@ -180,11 +181,11 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     // profiling only (VRVQ_DEBUG_PHASES=1): clock64 totals per phase for one thread of each role
     const int ph_role = tid == 0 ? 0 : tid == 256 ? 1 : tid == 384 ? 2 : tid == 416 ? 3 : -1;
     uint32_t gstage = 0;  // stages processed so far by this CTA (search-score ring / E_READY phase bookkeeping)
-    const bool ph_on = p.phase_cycles != nullptr && ph_role >= 0;
+    const bool ph_on = PROFILE && p.phase_cycles != nullptr && ph_role >= 0;
     long long ph_last = 0, ph_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (ph_on) ph_last = clock64();
     auto ph_mark = [&](int k) {
-        if (ph_on) {
+        if (PROFILE && ph_on) {
             const long long t = clock64();
             ph_acc[k] += t - ph_last;
             ph_last = t;
@@ -207,6 +208,35 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         const int n_stage_steps = ZQIS ? n_run * NJ : 0;
         const int n_final_steps = (p.z_q != nullptr) ? NJ * ((n_run + F_ITEMS) / F_ITEMS) : 0;  // ceil((n_run + 1) / F_ITEMS) per 128-channel chunk
 
+// Fold the phase-L accumulator set of channel group g into the running fp32 sums (also in TMEM); run by the epilogue warps,
+// which have nothing to store yet (tq = the warp's TMEM lane quarter)
+auto drain = [&](int g, uint32_t tq) {
+            const uint32_t gg = gbase + (uint32_t)g, set = gg & 1u;
+            TC_WAIT(&bars[B_SET_FULL + set], (gg >> 1) & 1u);
+            tmem_fence_after_sync();
+            const uint32_t ts = tq + TM_SET + 128u * set;
+#pragma unroll 2
+            for (int c8 = 0; c8 < 8; ++c8) {
+                uint32_t hh[8], lo[8], run[8];
+                tmem_ld8(ts + 8 * c8, hh);
+                tmem_ld8(ts + 64 + 8 * c8, lo);
+                if (g > 0) tmem_ld8(tq + TM_RUN + 8 * c8, run);
+                tmem_wait_ld(hh);
+                tmem_wait_ld(lo);
+                if (g > 0) tmem_wait_ld(run);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float v = __fadd_rn(__uint_as_float(hh[i]), __uint_as_float(lo[i]));
+                    if (g > 0) v = __fadd_rn(__uint_as_float(run[i]), v);
+                    run[i] = __float_as_uint(v);
+                }
+                tmem_st8(tq + TM_RUN + 8 * c8, run);
+            }
+            tmem_wait_st();
+            tmem_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_SET_EMPTY + set]);
+        };
         if (w < 8) {
             // =====================================================================================================
             // Search group.  Frame threads (warps 0-3): f = tid = TMEM lane.
@@ -243,44 +273,18 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                 const bool valid = inb;
                 const float *zp = p.z + (long long)b * p.z_sb + fr + (long long)(16 * q) * p.z_sd;
                 const long long zstep = 32 * p.z_sd;
-                float x[2][16];
+                constexpr int PF = 2;  // chunks of latent in flight per thread (2 x 16 loads; 3 spills and is slower)
+                float x[PF][16];
                 auto ldchunk = [&](const float *src, float (&v)[16]) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = valid ? __ldcs(src + (long long)i * p.z_sd) : 0.0f;
                 };
-                auto drain = [&](int g) {  // frame threads: fold accumulator set of group g into the running sums
-                    const uint32_t gg = gbase + (uint32_t)g, set = gg & 1u;
-                    TC_WAIT(&bars[B_SET_FULL + set], (gg >> 1) & 1u);
-                    tmem_fence_after_sync();
-                    const uint32_t ts = tq + TM_SET + 128u * set;
-#pragma unroll 2
-                    for (int c8 = 0; c8 < 8; ++c8) {
-                        uint32_t hh[8], lo[8], run[8];
-                        tmem_ld8(ts + 8 * c8, hh);
-                        tmem_ld8(ts + 64 + 8 * c8, lo);
-                        if (g > 0) tmem_ld8(tq + TM_RUN + 8 * c8, run);
-                        tmem_wait_ld(hh);
-                        tmem_wait_ld(lo);
-                        if (g > 0) tmem_wait_ld(run);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float v = __fadd_rn(__uint_as_float(hh[i]), __uint_as_float(lo[i]));
-                            if (g > 0) v = __fadd_rn(__uint_as_float(run[i]), v);
-                            run[i] = __float_as_uint(v);
-                        }
-                        tmem_st8(tq + TM_RUN + 8 * c8, run);
-                    }
-                    tmem_wait_st();
-                    tmem_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars[B_SET_EMPTY + set]);
-                };
                 const float *zc = zp;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) { ldchunk(zc, x[u]); zc += zstep; }
-                for (int c0 = 0; c0 < NCH; c0 += 2) {
+                for (int u = 0; u < PF; ++u) { ldchunk(zc, x[u]); zc += zstep; }
+                for (int c0 = 0; c0 < NCH; c0 += PF) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < PF; ++u) {
                         const int c = c0 + u;
                         float h[16], l[16];
 #pragma unroll
@@ -288,23 +292,27 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                             h[i] = tf32_hi(x[u][i]);
                             l[i] = __fsub_rn(x[u][i], h[i]);
                         }
-                        if (c + 2 < NCH) { ldchunk(zc, x[u]); zc += zstep; }
+                        if (c + PF < NCH) { ldchunk(zc, x[u]); zc += zstep; }
                         const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS, use = n / L_SLOTS;
-                        if (use >= 1) TC_WAIT(&bars[B_L_EMPTY + sl], (use - 1) & 1u);
-                        unsigned char *slot = smem + SM_LR + sl * L_SLOT + (4 * q) * 2048 + f * 16;
-#pragma unroll
-                        for (int g4 = 0; g4 < 4; ++g4) {
-                            *reinterpret_cast<float4 *>(slot + g4 * 2048) = make_float4(h[4 * g4], h[4 * g4 + 1], h[4 * g4 + 2], h[4 * g4 + 3]);
-                            *reinterpret_cast<float4 *>(slot + 16384 + g4 * 2048) = make_float4(l[4 * g4], l[4 * g4 + 1], l[4 * g4 + 2], l[4 * g4 + 3]);
+                        if (use >= 1) {
+                            TC_WAIT(&bars[B_L_EMPTY + sl], (use - 1) & 1u);
+                            tmem_fence_after_sync();
                         }
-                        // No fence.proxy.async here: it would also wait for this thread's prefetched global loads (a full
-                        // memory latency per chunk).  The release-arrive orders the stores; the MMA thread fences after its wait.
+                        // A operand straight into tensor memory: this thread's row (= lane), columns = its 16 channels of the chunk
+                        {
+                            uint32_t hv[16], lv[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { hv[i] = __float_as_uint(h[i]); lv[i] = __float_as_uint(l[i]); }
+                            const uint32_t ta = tq + TM_AL + 64u * sl + 16u * (uint32_t)q;
+                            tmem_st16(ta, hv);
+                            tmem_st16(ta + 32, lv);
+                        }
+                        tmem_wait_st();
+                        tmem_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars[B_L_FULL + sl]);
-                        if (w < 4 && (c & 3) == 1 && c >= 5) drain((c - 5) >> 2);
                     }
                 }
-                if (w < 4) drain(NG - 1);
             }
             ph_mark(1);
             tmem_fence_before_sync();
@@ -562,6 +570,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
             // =====================================================================================================
             // Epilogue warps: TMEM -> global.  Lane quarter q4 = w - 8, frame f = 32*q4 + lane.
             // =====================================================================================================
+            for (int g = 0; g < NG; ++g) drain(g, tmem + ((uint32_t)(32 * (w - 8)) << 16));
             tmem_fence_before_sync();
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
@@ -634,16 +643,15 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                     TC_WAIT(&bars[B_L_FULL + sl], (n / L_SLOTS) & 1u);
                     const uint32_t gg = gbase + (uint32_t)(c >> 2), set = gg & 1u;
                     if ((c & 3) == 0 && gg >= 2) TC_WAIT(&bars[B_SET_EMPTY + set], ((gg >> 1) - 1) & 1u);
-                    fence_proxy_async();  // generic-proxy stores of the loader warps (acquired above) -> async proxy
                     tmem_fence_after_sync();
-                    const uint64_t a_hi = desc128(smem_base + SM_LR + sl * L_SLOT);  // lo tile at +16 KB, W_in tile at +32 KB
-                    const uint64_t a_lo = a_hi + (16384 >> 4), bw = a_hi + (32768 >> 4);
+                    const uint32_t a_hi = tmem + TM_AL + 64u * sl, a_lo = a_hi + 32;  // A in tensor memory: 8 columns per k-step
+                    const uint64_t bw = desc128(smem_base + SM_LR + sl * L_SLOT);
                     const uint32_t d = tmem + TM_SET + 128u * set;
                     // [hi*hi | hi*lo] in one N = 128 MMA (B rows 0-63 heads, 64-127 remainders), lo*hi added to the second half
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        umma_tf32(d, a_hi + ks * (4096 >> 4), bw + ks * (4096 >> 4), ID_128, (c & 3) != 0 || ks != 0);
-                        umma_tf32(d + 64, a_lo + ks * (4096 >> 4), bw + ks * (4096 >> 4), ID_64, true);
+                        umma_tf32_ts(d, a_hi + 8 * ks, bw + ks * (4096 >> 4), ID_128, (c & 3) != 0 || ks != 0);
+                        umma_tf32_ts(d + 64, a_lo + 8 * ks, bw + ks * (4096 >> 4), ID_64, true);
                     }
                     umma_commit(&bars[B_L_EMPTY + sl]);
                     if ((c & 3) == 3) umma_commit(&bars[B_SET_FULL + set]);
@@ -792,7 +800,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
                     const uint32_t m = lbase + (uint32_t)c, slot = m % L_SLOTS, use = m / L_SLOTS;
                     if (use >= 1) TC_WAIT(&bars[B_L_EMPTY + slot], (use - 1) & 1u);
                     mbar_arrive_expect_tx(&bars[B_L_FULL + slot], 16384);
-                    bulk_g2s(smem + SM_LR + slot * L_SLOT + 32768, win + (size_t)c * 4096, 16384, &bars[B_L_FULL + slot]);
+                    bulk_g2s(smem + SM_LR + slot * L_SLOT, win + (size_t)c * 4096, 16384, &bars[B_L_FULL + slot]);
                 }
             }
             ph_mark(0);
@@ -865,7 +873,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         tmem_fence_after_sync();
         ph_mark(7);
     }
-    if (ph_on)
+    if (PROFILE && ph_on)
         for (int k = 0; k < 16; ++k) p.phase_cycles[((size_t)blockIdx.x * 4 + ph_role) * 16 + k] = ph_acc[k];
 
     // ---- teardown ----
@@ -925,17 +933,22 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
     return VRVQ_OK;
 }
 
-template <int D, bool ZQIS>
-static int launch_tc(const TcParams &P, int grid, cudaStream_t st) {
+template <int D, bool ZQIS, bool PROFILE>
+static int launch_tc_one(const TcParams &P, int grid, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        int rc = check_cuda(cudaFuncSetAttribute(rvq_encode_tc_kernel<D, ZQIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL),
+        int rc = check_cuda(cudaFuncSetAttribute(rvq_encode_tc_kernel<D, ZQIS, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL),
                             "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
         if (rc) return rc;
         attr_done = true;
     }
-    rvq_encode_tc_kernel<D, ZQIS><<<grid, TC_NTH, SM_TOTAL, st>>>(P);
+    rvq_encode_tc_kernel<D, ZQIS, PROFILE><<<grid, TC_NTH, SM_TOTAL, st>>>(P);
     return check_cuda(cudaGetLastError(), "rvq_encode_tc_kernel launch");
+}
+template <int D, bool ZQIS>
+static int launch_tc(const TcParams &P, int grid, cudaStream_t st) {
+    // the phase-counter build (VRVQ_DEBUG_PHASES=1) is a separate instantiation: the production kernel carries no counters
+    return P.e.phase_cycles != nullptr ? launch_tc_one<D, ZQIS, true>(P, grid, st) : launch_tc_one<D, ZQIS, false>(P, grid, st);
 }
 
 int encode_tc_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem) {
