@@ -120,3 +120,64 @@ def test_module_surface_matches_reference_signatures():
     m.train()
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 512, 4))
+
+
+def test_tensor_core_blob_section_layout():
+    """The tensor-core section of the packed blob (csrc/common.cuh TcLayout): TF32 head/remainder split is exact, tiles are in
+    the canonical K-major UMMA layout, the 8x8 correction matrices equal W_in[s] @ W_out[j] in binary64."""
+    Nq, D, K = 3, 256, 1024
+    sd = gi.torch_state_dict(gi.make_state_dict(11, Nq, D))
+    pw = ops.PackedWeights.from_state_dict(sd, "cpu")
+    blob = pw.host_blob
+    hdr = blob[:16].view(np.int32)
+    tc_off, tc_floats = int(hdr[6]), int(hdr[7])
+    assert tc_off > 0 and tc_off + tc_floats == blob.size, "TC section is appended after the per-stage sections"
+    tc = blob[tc_off:]
+    w_in = np.stack([ops.fold_weight_norm(sd[f"quantizers.{s}.in_proj.weight_v"], sd[f"quantizers.{s}.in_proj.weight_g"])[:, :, 0].numpy() for s in range(Nq)])
+    w_out = np.stack([ops.fold_weight_norm(sd[f"quantizers.{s}.out_proj.weight_v"], sd[f"quantizers.{s}.out_proj.weight_g"])[:, :, 0].numpy() for s in range(Nq)])
+    b_out = np.stack([sd[f"quantizers.{s}.out_proj.bias"].numpy() for s in range(Nq)])
+    nch, nj = D // 32, D // 128
+    off_win, off_wout = 0, nch * 4096
+    off_bout = off_wout + Nq * nj * 3072
+    off_gg = off_bout + nj * 2048
+    gg_floats = (Nq * (Nq - 1) // 2 * 72 + 3) // 4 * 4
+    off_bin = off_gg + gg_floats
+    off_cbk = off_bin + Nq * 8
+    assert off_cbk + Nq * 9216 == tc_floats
+
+    def tile_get(tile, rows, r, k):  # canonical K-major, no swizzle: 8-row x 16-byte core matrices
+        return tile[((k // 4) * rows + r) * 4 + (k % 4)]
+
+    # WIN chunk 1: rows 0..63 heads, 64..127 remainders of W_in[s][oc][32 + k]
+    tile = tc[off_win + 4096: off_win + 2 * 4096]
+    for s, oc, k in [(0, 0, 0), (1, 3, 17), (2, 7, 31)]:
+        x = w_in[s, oc, 32 + k]
+        h, l = tile_get(tile, 128, 8 * s + oc, k), tile_get(tile, 128, 64 + 8 * s + oc, k)
+        assert (np.float32(h).view(np.uint32) & 0x1FFF) == 0, "head must be a TF32 value (13 low mantissa bits zero)"
+        assert np.float32(h) + np.float32(l) == x and abs(l) <= abs(x) * 2.0 ** -11
+    assert tile_get(tile, 128, 8 * Nq, 0) == 0.0, "rows above 8*Nq are zero"
+    # WOUT chunk (s=1, j=1): row i <-> channel 128 j + 4 (i % 32) + i // 32; bias tile k=0 head, k=1 remainder
+    chunk = tc[off_wout + (1 * nj + 1) * 3072: off_wout + (1 * nj + 2) * 3072]
+    for i, k in [(0, 0), (33, 5), (127, 7)]:
+        ch = 128 + 4 * (i % 32) + i // 32
+        assert np.float32(tile_get(chunk[:1024], 128, i, k)) + np.float32(tile_get(chunk[1024:2048], 128, i, k)) == w_out[1, ch, k]
+        assert np.float32(tile_get(chunk[2048:], 128, i, 0)) + np.float32(tile_get(chunk[2048:], 128, i, 1)) == b_out[1, ch]
+        assert tile_get(chunk[2048:], 128, i, 2) == 0.0
+    # GG pair (j=0, s=2): G = W_in[2] @ W_out[0], g = W_in[2] @ b_out[0]
+    pair = 0 * Nq - 0 + (2 - 0 - 1)
+    G = tc[off_gg + pair * 72: off_gg + pair * 72 + 72]
+    ref = w_in[2].astype(np.float64) @ w_out[0].astype(np.float64)
+    np.testing.assert_array_equal(G[:64].reshape(8, 8), ref.astype(np.float32))
+    np.testing.assert_array_equal(G[64:], (w_in[2].astype(np.float64) @ b_out[0].astype(np.float64)).astype(np.float32))
+    # CBK stage 2: the normalised codebook as a [2][K][4] tile + c2
+    cb, c2 = pw.normalized_codebook(2)
+    cbk = tc[off_cbk + 2 * 9216: off_cbk + 3 * 9216]
+    assert np.array_equal(cbk[:4096].reshape(K, 4), cb[:, :4]) and np.array_equal(cbk[4096:8192].reshape(K, 4), cb[:, 4:])
+    assert np.array_equal(cbk[8192:], c2)
+
+
+def test_blob_without_tensor_core_section_for_large_nq():
+    sd = gi.torch_state_dict(gi.make_state_dict(12, 9, 256))
+    pw = ops.PackedWeights.from_state_dict(sd, "cpu")
+    hdr = pw.host_blob[:16].view(np.int32)
+    assert int(hdr[6]) == 0 and int(hdr[7]) == 0, "Nq > 8 keeps the CUDA-core kernel: no TC section"

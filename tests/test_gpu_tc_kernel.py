@@ -1,0 +1,149 @@
+"""The tensor-core encode kernel (csrc/rvq_encode_tc.cu) against the CUDA-core kernel (csrc/rvq_encode.cu) and the oracle.
+
+Both kernels sit behind the same C-ABI entry point (vrvq_rvq_encode_f32); VRVQ_ENCODE_IMPL=cuda forces the CUDA-core
+kernel.  They decide codes with the same exact fp32 search, so codes may differ only through the rounding of z_e
+(projected-residual GEMM vs. residual FMA chains): audited near-ties, as for any two conv implementations.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from tests import helpers as H
+from tests.golden import gen_inputs as gi
+
+pytestmark = pytest.mark.gpu
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def run_impl(impl, fn):
+    old = os.environ.get("VRVQ_ENCODE_IMPL")
+    if impl is None:
+        os.environ.pop("VRVQ_ENCODE_IMPL", None)
+    else:
+        os.environ["VRVQ_ENCODE_IMPL"] = impl
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("VRVQ_ENCODE_IMPL", None)
+        else:
+            os.environ["VRVQ_ENCODE_IMPL"] = old
+
+
+def test_tc_kernel_is_the_default_path():
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(5, 8, 1024))
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    tc = run_impl(None, lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda"))
+    cc = run_impl("cuda", lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda"))
+    assert tc["block"] == 480 and cc["block"] == 512, (tc, cc)
+    assert tc["grid"] == 144  # 9 tiles of 96 frames per item: one wave on 148 SMs
+
+
+@pytest.mark.parametrize("D,Nq,B,T,n_run,vbr", [
+    (1024, 8, 3, 87, 8, True),      # configs[0]-like, ragged
+    (1024, 8, 2, 431, 8, True),     # several tiles per item, odd T (no sector shift: odd row pitch)
+    (1024, 8, 2, 250, 5, False),    # CBR early exit (quantize.py:183-184)
+    (512, 4, 2, 130, 4, True),
+    (256, 3, 5, 33, 3, True),
+    (1024, 8, 1, 1, 8, True),
+    (1024, 1, 2, 64, 1, False),
+])
+def test_tc_matches_cuda_core_kernel_and_oracle(D, Nq, B, T, n_run, vbr):
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(100 + Nq, Nq, D))
+    w = c_oracle.OracleWeights.from_state_dict(sd)
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    z_np = gi.make_latents(200 + T, B, D, T, 1.0)
+    imp_np = gi.make_imp_map(300 + T, B, T) if vbr else None
+    z = torch.from_numpy(z_np).cuda()
+    imp = torch.from_numpy(imp_np).cuda() if vbr else None
+    level = 0.6 if vbr else None
+
+    def call():
+        return ops.rvq_encode(pw, z, n_run, imp, level, want_z_q_is=True, want_loss_pf=True)
+
+    a = run_impl(None, call)
+    c = run_impl("cuda", call)
+    o = c_oracle.encode(w, z_np, n_run if not vbr else None, imp_np, level, want_z_q_is=True)
+    excused, skip = H.assert_codes_match(w, o, npy(a.codes), max_excused_frac=0.02)
+    assert np.array_equal(npy(a.mask), npy(c.mask)) and np.array_equal(npy(a.mask), o["mask"])
+    assert np.array_equal(npy(a.kept), o["kept"])
+    H.assert_close_frames(npy(a.z_q), o["z_q"], skip=skip, what="z_q vs oracle")
+    H.assert_close_frames(npy(a.latents), o["latents"], skip=skip, what="latents vs oracle")
+    H.assert_close_frames(npy(a.z_q_is).reshape(B, -1, T), o["z_q_is"].reshape(B, -1, T), skip=skip, what="z_q_is vs oracle")
+    same = (npy(a.codes) == npy(c.codes)).all(axis=1)  # frames on which the two kernels agree on every stage
+    assert same.mean() >= 0.98
+    sk = ~same
+    H.assert_close_frames(npy(a.z_q), npy(c.z_q), skip=sk, what="z_q: tensor-core vs CUDA-core kernel")
+    H.assert_close_frames(npy(a.z_q_is).reshape(B, -1, T), npy(c.z_q_is).reshape(B, -1, T), skip=sk, what="z_q_is: tc vs cuda-core")
+    np.testing.assert_allclose(npy(a.loss_pf)[~sk[:, None, :].repeat(n_run, 1)], npy(c.loss_pf)[~sk[:, None, :].repeat(n_run, 1)], rtol=2e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("t_lo,t_hi", [(0, 200), (1, 201), (3, 117), (40, 296)])
+def test_tc_frame_views_any_alignment(t_lo, t_hi):
+    """Frame-range views of larger tensors (the multi-GPU / chunked shard): every start alignment of the
+    outputs (the sector-shift classes of the epilogue) reproduces the full call bit-for-bit, and nothing is written outside."""
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(77, 8, 1024))
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    B, T = 2, 300
+    g = torch.Generator().manual_seed(78)
+    z = torch.randn(B, 1024, T, generator=g).cuda()
+    imp = torch.rand(B, 1, T, generator=g).cuda()
+    full = ops.rvq_encode(pw, z, None, imp, 0.7, want_z_q_is=True)
+    n = t_hi - t_lo
+    out = ops.EncodeOutputs(B, 1024, T, 8, "cuda", z_q=True, z_q_is=True, latents=True, mask=True)
+    for t in (out.z_q, out.z_q_is, out.latents, out.mask):
+        t.fill_(-7.0)
+    out.codes.fill_(-7)
+    view = ops.EncodeOutputs.__new__(ops.EncodeOutputs)
+    view.codes, view.z_q, view.z_q_is = out.codes[:, :, t_lo:t_hi], out.z_q[:, :, t_lo:t_hi], out.z_q_is[:, :, :, t_lo:t_hi]
+    view.latents, view.mask, view.loss_pf = out.latents[:, :, t_lo:t_hi], out.mask[:, :, t_lo:t_hi], None
+    view.accum, view.n_run, view.frames = out.accum, 8, B * n
+    ops.rvq_encode_into(pw, z[:, :, t_lo:t_hi], view, 8, imp[:, :, t_lo:t_hi], 0.7)
+    torch.cuda.synchronize()
+    for name in ("codes", "z_q", "z_q_is", "latents", "mask"):
+        got, ref = getattr(out, name), getattr(full, name)
+        assert torch.equal(got[..., t_lo:t_hi], ref[..., t_lo:t_hi]), f"{name}: view [{t_lo},{t_hi}) differs from the full call"
+        outside = torch.cat([got[..., :t_lo].reshape(-1), got[..., t_hi:].reshape(-1)])
+        assert bool((outside == -7).all()), f"{name}: wrote outside the view"
+
+
+def test_tc_optional_outputs_and_nan_latent():
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(55, 8, 1024))
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    B, T = 2, 140
+    g = torch.Generator().manual_seed(56)
+    z = torch.randn(B, 1024, T, generator=g).cuda()
+    imp = torch.rand(B, 1, T, generator=g).cuda()
+    ref = ops.rvq_encode(pw, z, None, imp, 0.5, want_z_q_is=True)
+    only_codes = ops.EncodeOutputs(B, 1024, T, 8, "cuda", z_q=False, z_q_is=False, latents=False, mask=False)
+    ops.rvq_encode_into(pw, z, only_codes, 8, imp, 0.5)
+    assert torch.equal(only_codes.codes, ref.codes) and torch.equal(only_codes.kept, ref.kept)
+    no_zq = ops.EncodeOutputs(B, 1024, T, 8, "cuda", z_q=False, z_q_is=True, latents=True, mask=True)
+    ops.rvq_encode_into(pw, z, no_zq, 8, imp, 0.5)
+    assert torch.equal(no_zq.z_q_is, ref.z_q_is) and torch.equal(no_zq.codes, ref.codes)
+    # an all-zero frame (degenerate search: every score ties) and a NaN frame must not disturb their neighbours
+    z2 = z.clone()
+    z2[0, :, 5] = 0.0
+    z2[1, :, 9] = float("nan")
+    r2 = ops.rvq_encode(pw, z2, None, imp, 0.5, want_z_q_is=False)
+    keep = torch.ones(B, T, dtype=torch.bool, device="cuda")
+    keep[0, 5] = False
+    keep[1, 9] = False
+    assert torch.equal(r2.codes.permute(0, 2, 1)[keep], ref.codes.permute(0, 2, 1)[keep])
+    assert torch.equal(r2.z_q.permute(0, 2, 1)[keep], ref.z_q.permute(0, 2, 1)[keep])
+    zf = c_oracle.encode(c_oracle.OracleWeights.from_state_dict(sd), npy(z2[0:1, :, 5:6]), None, npy(imp[0:1, :, 5:6]), 0.5)
+    assert np.array_equal(npy(r2.codes[0:1, :, 5:6]), zf["codes"]), "all-zero latent: exact fallback scan must match the oracle"

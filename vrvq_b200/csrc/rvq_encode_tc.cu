@@ -96,7 +96,6 @@ struct TcParams {
     const float *tc;  // TC section of the blob
     int adv;          // frames per tile (multiple of 8, <= 120)
     int tiles_per_b, n_tiles;
-    int dbg;  // VRVQ_DEBUG_TC bit mask (profiling experiments only; results become invalid)
 };
 
 // all K-major no-swizzle tiles of this kernel have 128 rows: LBO = 2048 B (next 4-wide k group), SBO = 128 B (next 8 rows)
@@ -418,7 +417,7 @@ auto drain = [&](int g, uint32_t tq) {
                         }
                         ph_mark(10);
                     }
-                    if (!(P.dbg & 2)) TC_WAIT(&bars[B_CB_FULL + (s & 1)], cbuse & 1u);  // (long complete: the score MMAs read the same buffer)
+                    TC_WAIT(&bars[B_CB_FULL + (s & 1)], cbuse & 1u);  // (long complete: the score MMAs read the same buffer)
                     {
                         // Work list of 8-code groups to re-score exactly.  Normal case: the (<= 3) groups still within the margin of
                         // the final maximum (the stored maximum lost its low 8 bits: 1e-4 of slack), compacted first so that a warp
@@ -437,7 +436,7 @@ auto drain = [&](int g, uint32_t tq) {
                             nc += hit ? 1 : 0;
                         }
                         const int mode = cnt > 16 ? 2 : nc > 3 ? 1 : 0;
-                        const int total = (P.dbg & 1) ? 0 : mode == 2 ? 64 : mode == 1 ? cnt : nc;
+                        const int total = mode == 2 ? 64 : mode == 1 ? cnt : nc;
                         for (int wi = 0; wi < total; ++wi) {
                             int gid;
                             if (mode == 0) {
@@ -928,7 +927,6 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
         if (v >= 8 && v <= 120 && v % 8 == 0) { P.adv = v; P.tiles_per_b = (a->T + v - 1) / v; }
     }
     P.n_tiles = P.tiles_per_b * a->B;
-    P.dbg = getenv("VRVQ_DEBUG_TC") ? atoi(getenv("VRVQ_DEBUG_TC")) : 0;
     *grid = P.n_tiles < sms ? P.n_tiles : sms;
     return VRVQ_OK;
 }
