@@ -15,6 +15,6 @@ os.environ.pop("VRVQ_DEBUG_PHASES", None)
 for _ in range(3):
     ops.rvq_encode_into(pw, z, out, Nq, imp, 0.5)
 torch.cuda.synchronize()
-os.environ["VRVQ_DEBUG_PHASES"] = "1"
+os.environ["VRVQ_DEBUG_PHASES"] = os.environ.get("PHASE_MODE", "1")  # "2": production instantiation, three timestamps per CTA
 ops.rvq_encode_into(pw, z, out, Nq, imp, 0.5)
 torch.cuda.synchronize()

@@ -181,6 +181,9 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     const int ph_role = tid == 0 ? 0 : tid == 256 ? 1 : tid == 384 ? 2 : tid == 416 ? 3 : -1;
     uint32_t gstage = 0;  // stages processed so far by this CTA (search-score ring / E_READY phase bookkeeping)
     const bool ph_on = PROFILE && p.phase_cycles != nullptr && ph_role >= 0;
+    const bool lite = !PROFILE && p.phase_cycles != nullptr && tid == 0;  // VRVQ_DEBUG_PHASES=2: three timestamps, production code
+    long long lite_t0 = 0, lite_l = 0;
+    if (lite) lite_t0 = clock64();
     long long ph_last = 0, ph_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (ph_on) ph_last = clock64();
     auto ph_mark = [&](int k) {
@@ -288,7 +291,8 @@ auto drain = [&](int g, uint32_t tq) {
                         float h[16], l[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            h[i] = tf32_hi(x[u][i]);
+                            // TF32 head by truncation (one LOP3; the remainder x - head stays exact); W_in heads are rounded to nearest
+                            h[i] = __uint_as_float(__float_as_uint(x[u][i]) & 0xffffe000u);
                             l[i] = __fsub_rn(x[u][i], h[i]);
                         }
                         if (c + PF < NCH) { ldchunk(zc, x[u]); zc += zstep; }
@@ -318,6 +322,7 @@ auto drain = [&](int g, uint32_t tq) {
             __syncthreads();  // L -> S: every phase-L MMA has completed (the last drain waited for them); region re-usable
             tmem_fence_after_sync();
             ph_mark(2);
+            if (lite) lite_l += clock64() - lite_t0;
 
             // ---- phase S ----
             float zev[8];  // frame threads: z_e of the current stage
@@ -871,6 +876,13 @@ auto drain = [&](int g, uint32_t tq) {
         __syncthreads();  // end of tile: every MMA of the tile has completed (the epilogue waited for the last one)
         tmem_fence_after_sync();
         ph_mark(7);
+        if (lite) {  // [0] += time to the L->S barrier, [1] += whole tile
+            const long long t = clock64();
+            p.phase_cycles[(size_t)blockIdx.x * 64 + 0] += lite_l;
+            p.phase_cycles[(size_t)blockIdx.x * 64 + 1] += t - lite_t0;
+            lite_t0 = t;
+            lite_l = 0;
+        }
     }
     if (PROFILE && ph_on)
         for (int k = 0; k < 16; ++k) p.phase_cycles[((size_t)blockIdx.x * 4 + ph_role) * 16 + k] = ph_acc[k];
@@ -946,7 +958,9 @@ static int launch_tc_one(const TcParams &P, int grid, cudaStream_t st) {
 template <int D, bool ZQIS>
 static int launch_tc(const TcParams &P, int grid, cudaStream_t st) {
     // the phase-counter build (VRVQ_DEBUG_PHASES=1) is a separate instantiation: the production kernel carries no counters
-    return P.e.phase_cycles != nullptr ? launch_tc_one<D, ZQIS, true>(P, grid, st) : launch_tc_one<D, ZQIS, false>(P, grid, st);
+    const char *dbg = getenv("VRVQ_DEBUG_PHASES");
+    const bool full = P.e.phase_cycles != nullptr && !(dbg != nullptr && dbg[0] == '2');  // "2": production code + 3 timestamps per CTA
+    return full ? launch_tc_one<D, ZQIS, true>(P, grid, st) : launch_tc_one<D, ZQIS, false>(P, grid, st);
 }
 
 int encode_tc_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem) {
@@ -973,6 +987,7 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
     const bool dbg = getenv("VRVQ_DEBUG_PHASES") != nullptr;  // profiling only: synchronises and prints per-phase cycles
     P.e.phase_cycles = nullptr;
     if (dbg && cudaMalloc(&P.e.phase_cycles, sizeof(long long) * 64 * (size_t)grid) != cudaSuccess) P.e.phase_cycles = nullptr;
+    if (P.e.phase_cycles != nullptr) cudaMemsetAsync(P.e.phase_cycles, 0, sizeof(long long) * 64 * (size_t)grid, st);
     switch (a->input_dim) {
         case 1024: rc = zqis ? launch_tc<1024, true>(P, grid, st) : launch_tc<1024, false>(P, grid, st); break;
         case 512: rc = zqis ? launch_tc<512, true>(P, grid, st) : launch_tc<512, false>(P, grid, st); break;
@@ -990,6 +1005,14 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
         cudaStreamSynchronize(st);
         cudaMemcpy(h, P.e.phase_cycles, sizeof(long long) * 64 * (size_t)grid, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[vrvq tc phases] grid %d, tile %d frames, %d tiles; mean cycles per CTA\n", grid, P.adv, P.n_tiles);
+        if (getenv("VRVQ_DEBUG_PHASES")[0] == '2') {
+            double a0 = 0, a1 = 0;
+            for (int g = 0; g < grid; ++g) { a0 += (double)h[g * 64 + 0] / grid; a1 += (double)h[g * 64 + 1] / grid; }
+            fprintf(stderr, "  production instantiation: to the L->S barrier %.0f, whole tiles %.0f\n", a0, a1);
+            free(h);
+            cudaFree(P.e.phase_cycles);
+            return rc;
+        }
         for (int r = 0; r < 4; ++r) {
             double acc[16] = {0}, tot = 0;
             for (int g = 0; g < grid; ++g)
