@@ -920,7 +920,12 @@ static int pick_tiling(int B, int T, int sms, int *adv, int *tiles_per_b) {
 }
 
 int encode_tc_usable(const vrvq_encode_args *a) {
-    return tc_shape_ok(a->input_dim, a->codebook_size, a->n_codebooks) ? 1 : 0;
+    if (!tc_shape_ok(a->input_dim, a->codebook_size, a->n_codebooks)) return 0;
+    // the epilogue forms store addresses as base + i * (16 * row pitch) with a 32-bit step
+    const long long lim = 1ll << 27;
+    if (a->z_q_is != nullptr && (a->z_q_is_stride_d < 0 || a->z_q_is_stride_d >= lim)) return 0;
+    if (a->z_q != nullptr && (a->z_q_stride_d < 0 || a->z_q_stride_d >= lim)) return 0;
+    return 1;
 }
 
 static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParams &P, int *grid) {
