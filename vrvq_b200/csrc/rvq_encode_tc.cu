@@ -5,27 +5,33 @@
 // pre-normalisation latents of ALL stages are one skinny GEMM of the input plus 8x8 corrections:
 //     z_e[s] = W_in[s] (z - sum_{j<s} (W_out[j] q_j + b_out[j])) + b_in[s]
 //            = (W_in[s] z + b_in[s]) - sum_{j<s} (G[s][j] q_j + g[s][j]),   G[s][j] = W_in[s] W_out[j],  g = W_in[s] b_out[j]
-// so the residual never exists.  One CTA owns a tile of up to 128 consecutive frames of one batch item (frame = TMEM
-// lane = MMA row) and runs:
-//   phase L  z tile -> registers -> (hi, lo) TF32 split -> shared memory (canonical UMMA layout), tcgen05.mma kind::tf32
-//            with the 3xTF32 split (hi*hi + hi*lo + lo*hi), M = 128 frames, N = 64 = 8 x Nq, K = D.  The tensor core
-//            rounds its fp32 accumulator toward zero on every k-step, so the accumulator is drained into a running
-//            fp32 sum (also in TMEM) every 128 channels; measured error 3.5e-7 rms / 1.3e-6 max relative, better than
-//            an fp32 FMA chain (profiles/r1_micro_tc3x.txt).
-//   phase S  per stage: bias + L2-normalise + exact fp32 search on the CUDA cores (same op order as the CUDA-core
-//            kernel / the oracle), argmin merge, raw-row gather, straight-through q, per-frame loss, codes; 8x8 corrections
-//            of the later stages' latents through TMEM; q (hi, lo) written as the next MMA's A operand.
-//            out_proj of the stage = tcgen05.mma M = 128 frames, N = 128 channels, K = 8 (x3 split) per 128-channel chunk
-//            into a two-deep TMEM ring that dedicated epilogue warps drain to global memory (lane = frame, so every
-//            warp-level store writes 128 contiguous bytes of one channel row), overlapping the next stage's search.
+// so the residual never exists.  One CTA owns a tile of up to 120 consecutive frames of one batch item plus the 8 frames
+// before it (halo); tile row r = TMEM lane r = MMA row r <-> frame t0 - 8 + r.
+//   phase L  warps 0-7 load the tile (lane = frame), split every value into a TF32 head and an exact fp32 remainder and write
+//            both straight into tensor memory as the A operand; tcgen05.mma kind::tf32 (A in TMEM, W_in chunks in shared
+//            memory by cp.async.bulk) with the 3xTF32 split hi*hi + hi*lo + lo*hi, M = 128 frames, N = 64 = 8 x Nq, K = D.
+//            The tensor core rounds its fp32 accumulator toward zero on every k-step, so the accumulators are drained into
+//            running fp32 sums (also in TMEM) every 128 channels; measured error 3.5e-7 rms / 1.3e-6 max relative, better
+//            than an fp32 FMA chain (profiles/r1_micro_tc3x.txt).
+//   phase S  per stage: bias + L2-normalise (torch's op order); search = TF32 score MMAs (128 frames x 64 codes per MMA) into
+//            rotating TMEM buffers, a branch-free scan for the 8-code groups within a rigorous margin of the running
+//            maximum, and exact fp32 re-scoring of those candidates with the reference's expression (first index on ties):
+//            codes are decided by exactly the arithmetic of the CUDA-core kernel and the oracle.  Then raw-row gather,
+//            straight-through q, per-frame loss, codes, the 8x8 corrections of the later stages through TMEM, and q (head,
+//            remainder) as the A operand of the stage's out_proj: tcgen05.mma M = 128 frames x 128 channels x K = 8 (x3 split,
+//            + a ones-tile x bias-tile MMA) into a two-deep TMEM ring that dedicated epilogue warps drain to global memory
+//            (lane = frame: every warp-level store writes 128 contiguous bytes of one channel row), overlapping the next
+//            stage's search.  Per channel class (channel % 4) the A descriptor is shifted by 1..8 rows so that every store
+//            starts on a 32-byte sector whatever the row alignment is (that is what the halo is for).
 //   final    z_q = sum_s mask_s (W_out[s] q_s + b_out[s]) as one GEMM over K = 8 Nq (+ the mask-weighted bias rows) from
 //            the masked A tiles kept in shared memory.
-// Warp roles: warps 0-7 load/split (phase L) and search (phase S), warps 0-3 additionally own one frame per thread
-// (drains, normalise, merge, gather); warps 8-11 are the epilogue; lane 0 of warp 12 issues every tcgen05.mma and every
-// cp.async.bulk weight copy.  Everything is synchronised with mbarriers; two CTA-wide barriers per tile.
+// Warp roles: 0-7 load/split (phase L) and search (phase S), warps 0-3 additionally own one tile row per thread (normalise,
+// merge, gather); 8-11 epilogue (TMEM -> global) and the phase-L accumulator drains; lane 0 of warp 12 issues the in_proj /
+// out_proj / final MMAs, lane 0 of warp 13 every cp.async.bulk, lane 0 of warp 14 the search-score MMAs.  Everything is
+// synchronised with mbarriers (bounded waits: a protocol bug traps instead of hanging); two CTA-wide barriers per tile.
 //
-// Exactness: codes are decided by the same fp32 search as before; only z_e differs from the reference's conv1d by
-// rounding (as any two conv implementations do), so codes can differ only at fp32 near-ties (audited in tests).
+// Exactness: only z_e differs from the reference's conv1d by rounding (as any two conv implementations do), so codes can
+// differ only at fp32 near-ties (audited in tests); z_q / z_q_is carry the tensor core's accumulation rounding (<= 2e-6).
 #include <cstdio>
 #include <cstdlib>
 

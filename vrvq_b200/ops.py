@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import CD, EncodeArgs, FromCodesArgs, VrvqError, check, current_stream_ptr, ptr, require_cuda_f32
 
-TILE_FRAMES = 32  # frames per CTA tile of the encode kernel (rvq_encode.cu: TF)
+TILE_FRAMES = 32  # shard/padding granularity in frames (the CUDA-core kernel's tile; the tensor-core kernel picks multiples of 8)
 
 
 def fold_weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
