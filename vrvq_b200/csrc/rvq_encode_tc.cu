@@ -131,6 +131,10 @@ __device__ __forceinline__ uint32_t base_mod8(const float *ptr, long long off) {
 template <int D, bool ZQIS, bool PROFILE>
 __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P) {
     constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;  // 32-channel chunks, accumulator drained every 4 chunks
+    // search-score chunks: 64 codes per MMA into 3 x 64 TMEM columns; without z_q_is the out_proj ring is idle during the
+    // searches, so the scores take 3 x 128 columns from TM_SET on and half as many (170-cycle) barrier hand-overs
+    constexpr int SCW = ZQIS ? 64 : 128, NSC = TCK / SCW;
+    constexpr uint32_t TM_SC = ZQIS ? TM_SCORE : TM_SET;
     static_assert(NCH % 4 == 0, "D must be a multiple of 128");
     const EncodeParams &p = P.e;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -380,20 +384,25 @@ auto drain = [&](int g, uint32_t tq) {
                     int bidx = 0x7fffffff;
                     float runmax = __int_as_float(0xff800000);
                     int cnt = 0;
-                    for (int ci = 0; ci < 8; ++ci) {
-                        const uint32_t gc = (gstage + (uint32_t)s) * 16u + (uint32_t)(2 * ci + h), sbuf = gc % 3u;
-                        const uint32_t tsc = tq + TM_SCORE + 64u * sbuf;
-                        TC_WAIT(&bars[B_SB_FULL + sbuf], (gc / 3u) & 1u);
-                        tmem_fence_after_sync();
+                    for (int c64 = 0; c64 < 8; ++c64) {  // this thread's eight 64-code pieces: code chunks 2*ci + h of width SCW
+                        const int ci = c64 / (SCW / 64), sub = c64 % (SCW / 64);
+                        const uint32_t gc = (gstage + (uint32_t)s) * (uint32_t)NSC + (uint32_t)(2 * ci + h), sbuf = gc % 3u;
+                        const uint32_t tsc = tq + TM_SC + (uint32_t)SCW * sbuf + 64u * (uint32_t)sub;
+                        if (sub == 0) {
+                            TC_WAIT(&bars[B_SB_FULL + sbuf], (gc / 3u) & 1u);
+                            tmem_fence_after_sync();
+                        }
                         ph_mark(8);
                         uint32_t va[32], vb[32];
                         tmem_ld32(tsc, va);
                         tmem_ld32(tsc + 32, vb);
                         tmem_wait_ld32(va);
                         tmem_wait_ld32(vb);
-                        tmem_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars[B_SB_EMPTY + sbuf]);
+                        if (sub == SCW / 64 - 1) {
+                            tmem_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bars[B_SB_EMPTY + sbuf]);
+                        }
                         ph_mark(9);
                         // maxima of the eight 8-code groups of this chunk (FMNMX3)
                         float g[8];
@@ -414,7 +423,7 @@ auto drain = [&](int g, uint32_t tq) {
                         asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(cm), "f"(g[5]), "f"(g[6]));
                         runmax = fmaxf(runmax, fmaxf(cm, g[7]));
                         const float thr = runmax - SEARCH_MARGIN;
-                        const uint32_t gid0 = (uint32_t)(2 * ci + h) * 8u;  // group id = code / 8
+                        const uint32_t gid0 = (uint32_t)((2 * ci + h) * (SCW / 8) + sub * 8);  // group id = code / 8
                         // branch-free append of every group whose maximum is within the margin: entry = (max & ~0xff) | group id
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -456,7 +465,7 @@ auto drain = [&](int g, uint32_t tq) {
                                 const uint32_t entry = list[wi * 256];
                                 gid = (__uint_as_float(entry & 0xffffff00u) >= thr) ? (int)(entry & 0xffu) : -1;
                             } else {
-                                gid = (2 * (wi >> 3) + h) * 8 + (wi & 7);
+                                gid = (2 * (wi / (SCW / 8)) + h) * (SCW / 8) + wi % (SCW / 8);  // wi-th group of this thread's half
                             }
                             if (gid >= 0) {
                                 const float4 *r0 = reinterpret_cast<const float4 *>(CB + gid * 32), *r1 = reinterpret_cast<const float4 *>(CB + 4096 + gid * 32);
@@ -768,15 +777,15 @@ auto drain = [&](int g, uint32_t tq) {
             __syncwarp();
         } else if (w == 14) {
             // =====================================================================================================
-            // Search-MMA issuer: lane 0 of warp 14.  Per stage, 16 MMAs of M = 128 frames x N = 64 codes x K = 8 (plain TF32)
-            // into three rotating 64-column score buffers; chunk c is scanned by warps 4(c%2) .. 4(c%2)+3.
+            // Search-MMA issuer: lane 0 of warp 14.  Per stage, NSC MMAs of M = 128 frames x N = SCW codes x K = 8 (plain TF32)
+            // into three rotating SCW-column score buffers; chunk c is scanned by warps 4(c%2) .. 4(c%2)+3.
             // =====================================================================================================
             __syncwarp();
             tmem_fence_before_sync();
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
             if (lane == 0) {
-                constexpr uint32_t ID_S = umma_idesc_tf32(128, 64);
+                constexpr uint32_t ID_S = umma_idesc_tf32(128, SCW);
                 // codebook tile: 1024 rows -> LBO = 16384 B, SBO = 128 B
                 constexpr uint64_t DESC_CB = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)(16384 >> 4) << 16);
                 const uint64_t ae = desc128(smem_base + SM_ES);
@@ -787,11 +796,11 @@ auto drain = [&](int g, uint32_t tq) {
                     TC_WAIT(&bars[B_CB_FULL + (s & 1)], cbuse & 1u);
                     fence_proxy_async();
                     const uint64_t cb = DESC_CB | (uint64_t)((smem_base + ((s & 1) ? SM_CB1 : SM_CB0)) >> 4);
-                    for (int c = 0; c < 16; ++c) {
-                        const uint32_t gc = gs * 16u + (uint32_t)c, sbuf = gc % 3u, use = gc / 3u;
+                    for (int c = 0; c < NSC; ++c) {
+                        const uint32_t gc = gs * (uint32_t)NSC + (uint32_t)c, sbuf = gc % 3u, use = gc / 3u;
                         if (use >= 1) TC_WAIT(&bars[B_SB_EMPTY + sbuf], (use - 1) & 1u);
                         tmem_fence_after_sync();
-                        umma_tf32(tmem + TM_SCORE + 64u * sbuf, ae, cb + (uint64_t)(c * (64 * 16 >> 4)), ID_S, false);
+                        umma_tf32(tmem + TM_SC + (uint32_t)SCW * sbuf, ae, cb + (uint64_t)(c * (SCW * 16 >> 4)), ID_S, false);
                         umma_commit(&bars[B_SB_FULL + sbuf]);
                     }
                 }
