@@ -106,7 +106,10 @@ def test_cbr_against_reference_fixture(name):
             B, T = case["B"], case["T"]
             H.assert_close_frames(npy(zqis)[:, :, ::16, :].reshape(B, -1, T), g["from_codes_z_q_is_sub"].reshape(B, -1, T), what="from_codes z_q_is")
             ozq, _, _ = c_oracle.from_codes(w, g[f"codes_{qi}"])
-            assert np.array_equal(npy(zq), ozq), "from_codes has no reduction-order freedom: bit-exact vs the oracle"
+            if case["Nq"] > 8:  # CUDA-core decode kernel: the oracle's fp32 op order, bit for bit
+                assert np.array_equal(npy(zq), ozq), "from_codes (CUDA cores) is bit-exact vs the oracle"
+            else:  # tensor-core decode path: same gather, 3xTF32 GEMM accumulation
+                H.assert_close_frames(npy(zq), ozq, rtol=5e-6, what="from_codes (tensor cores) vs the oracle")
             lat = torch.from_numpy(g[f"latents_{qi}"]).cuda()
             zq2, zp2, codes2 = m.from_latents(lat)
             assert np.array_equal(npy(codes2), g["from_latents_codes"]), "search on the reference's own z_e must be bit-exact"

@@ -147,3 +147,35 @@ def test_tc_optional_outputs_and_nan_latent():
     assert torch.equal(r2.z_q.permute(0, 2, 1)[keep], ref.z_q.permute(0, 2, 1)[keep])
     zf = c_oracle.encode(c_oracle.OracleWeights.from_state_dict(sd), npy(z2[0:1, :, 5:6]), None, npy(imp[0:1, :, 5:6]), 0.5)
     assert np.array_equal(npy(r2.codes[0:1, :, 5:6]), zf["codes"]), "all-zero latent: exact fallback scan must match the oracle"
+
+
+@pytest.mark.parametrize("D,Nq,n,B,T,masked", [(1024, 8, 8, 2, 131, False), (1024, 8, 8, 2, 300, True), (1024, 8, 3, 1, 87, False),
+                                              (512, 4, 4, 3, 40, True), (256, 3, 2, 2, 1, False)])
+def test_from_codes_on_the_tensor_core_path(D, Nq, n, B, T, masked):
+    """vrvq_from_codes_f32 (quantize.py:217-249) for <= 8 codebooks runs the encode kernel's gather + out_proj GEMMs (FC
+    instantiation): against the CUDA-core decode kernel (bit-exact vs the oracle) -- z_p identical, z_q / z_q_is within the GEMM
+    accumulation tolerance, arbitrary 0/1 masks, frame-range views, out-of-range codes reported."""
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(600 + Nq, Nq, D))
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    g = torch.Generator().manual_seed(601 + T)
+    codes = torch.randint(0, 1024, (B, n, T), generator=g).cuda()
+    mask = (torch.rand(B, n, T, generator=g) < 0.6).float().cuda() if masked else None
+
+    def call(c=codes, m=mask):
+        return ops.from_codes(pw, c, m, want_z_q_is=True, want_z_p=True)
+
+    zq, zp, zqis = run_impl(None, call)
+    zq_c, zp_c, zqis_c = run_impl("cuda", call)
+    assert torch.equal(zp, zp_c), "z_p = the gathered codebook rows"
+    H.assert_close_frames(npy(zq), npy(zq_c), rtol=5e-6, what="from_codes z_q: tensor cores vs CUDA cores")
+    H.assert_close_frames(npy(zqis).reshape(B, -1, T), npy(zqis_c).reshape(B, -1, T), rtol=5e-6, what="from_codes z_q_is")
+    if T >= 40:  # a frame-range view reproduces the full call bit for bit
+        sl = slice(5, T - 3)
+        zq_v, zp_v, _ = run_impl(None, lambda: call(codes[:, :, sl], None if mask is None else mask[:, :, sl]))
+        assert torch.equal(zq_v, zq[:, :, sl]) and torch.equal(zp_v, zp[:, :, sl])
+    bad = codes.clone()
+    bad[0, 0, 0] = 1024
+    with pytest.raises(IndexError):
+        ops.from_codes(pw, bad)

@@ -39,5 +39,8 @@ int fill_encode_params(const vrvq_encode_args *a, EncodeParams &p);
 int encode_tc_usable(const vrvq_encode_args *a);
 int encode_tc(const vrvq_encode_args *a, const EncodeParams &p, void *stream);
 int encode_tc_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem);
+// from_codes on the same kernel (FC instantiation)
+int from_codes_tc_usable(const vrvq_from_codes_args *a);
+int from_codes_tc(const vrvq_from_codes_args *a, void *stream);
 
 }  // namespace vrvq

@@ -1,6 +1,7 @@
 // Companion kernels of the fused encode: decode-from-codes, mask utilities, level-sweep re-mask.
 // All are streaming, HBM-bound kernels: coalesced along T, grid sized in multiples of the SM count.
 #include "common.cuh"
+#include "encode_params.cuh"
 
 namespace vrvq {
 
@@ -415,6 +416,7 @@ int launch_from_codes(const vrvq_from_codes_args *a, cudaStream_t st) {
         return VRVQ_EINVAL;
     }
     if ((long long)a->B * a->T == 0) return VRVQ_OK;
+    if (from_codes_tc_usable(a)) return from_codes_tc(a, st);  // <= 8 codebooks: the encode kernel's gather + out_proj GEMMs
     const BlobLayout L(a->input_dim, a->codebook_size);
     FromCodesParams p{};
     p.blob = static_cast<const float *>(a->blob);

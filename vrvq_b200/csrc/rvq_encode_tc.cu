@@ -102,6 +102,13 @@ struct TcParams {
     const float *tc;  // TC section of the blob
     int adv;          // frames per tile (multiple of 8, <= 120)
     int tiles_per_b, n_tiles;
+    // from_codes mode (FC): codes [B][n_run][T] are an input, mask_in an optional 0/1 mask [B][n_run][T], error_flag is set when
+    // a code lies outside [0, K)
+    const long long *codes_in;
+    long long cin_sb, cin_sq;
+    const float *mask_in;
+    long long min_sb, min_sq;
+    int *error_flag;
 };
 
 // all K-major no-swizzle tiles of this kernel have 128 rows: LBO = 2048 B (next 4-wide k group), SBO = 128 B (next 8 rows)
@@ -128,7 +135,9 @@ __device__ __forceinline__ uint32_t base_mod8(const float *ptr, long long off) {
     return (uint32_t)(((reinterpret_cast<uintptr_t>(ptr) >> 2) + (unsigned long long)off) & 7ull);
 }
 
-template <int D, bool ZQIS, bool PROFILE>
+// FC = from_codes mode (models/quantize.py:217-249): no latent, no in_proj, no search -- the codes are an input; the gather, the
+// out_proj units, the masking and the final GEMM are the encode path's own.
+template <int D, bool ZQIS, bool PROFILE, bool FC>
 __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P) {
     constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;  // 32-channel chunks, accumulator drained every 4 chunks
     // search-score chunks: 64 codes per MMA into 3 x 64 TMEM columns; without z_q_is the out_proj ring is idle during the
@@ -258,6 +267,7 @@ auto drain = [&](int g, uint32_t tq) {
             const bool own = f >= 8 && f - 8 < fv;              // frames whose per-frame outputs this tile writes
             const bool inb = fr >= 0 && (f < 8 || f - 8 < fv);  // rows that hold a real frame (halo rows of the first tile do not)
             const uint32_t tq = tmem + ((uint32_t)(32 * (w & 3)) << 16);  // this warp's lane quarter
+            if constexpr (!FC) {
             if (w < 4) {
                 // ---- keep counts, mask, kept-frame counts (quantize.py:389, utils.py:59-60) ----
                 int nk = 0;
@@ -327,6 +337,7 @@ auto drain = [&](int g, uint32_t tq) {
                     }
                 }
             }
+            }  // !FC
             ph_mark(1);
             tmem_fence_before_sync();
             __syncthreads();  // L -> S: every phase-L MMA has completed (the last drain waited for them); region re-usable
@@ -334,6 +345,63 @@ auto drain = [&](int g, uint32_t tq) {
             ph_mark(2);
             if (lite) lite_l += clock64() - lite_t0;
 
+            if constexpr (FC) {
+                if (w < 4) {
+                    const bool rowok = fr >= 0 && fr < p.T && f < 8 + fv;  // the row holds a real frame (own or halo)
+                    for (int s = 0; s < n_run; ++s) {
+                        long long code = rowok ? P.codes_in[(long long)b * P.cin_sb + (long long)s * P.cin_sq + fr] : 0;
+                        if (code < 0 || code >= TCK) {  // F.embedding raises on such an index (quantize.py:82): report it
+                            if (P.error_flag != nullptr) *P.error_flag = 1;
+                            code = 0;
+                        }
+                        const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)s * L.stage_floats() + L.off_raw() + (size_t)code * 8);
+                        const float4 ra = __ldg(rawp), rb = __ldg(rawp + 1);
+                        const float qv[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                        if (p.latents != nullptr && own) {  // z_p: the gathered un-normalised rows
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)(s * 8 + k) * p.lat_sc + fr] = qv[k];
+                        }
+                        float h[8], l[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { h[k] = tf32_hi(qv[k]); l[k] = __fsub_rn(qv[k], h[k]); }
+                        unsigned char *at = smem + SM_AT + s * 8192 + f * 16;
+                        *reinterpret_cast<float4 *>(at) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4 *>(at + 2048) = make_float4(h[4], h[5], h[6], h[7]);
+                        *reinterpret_cast<float4 *>(at + 4096) = make_float4(l[0], l[1], l[2], l[3]);
+                        *reinterpret_cast<float4 *>(at + 4096 + 2048) = make_float4(l[4], l[5], l[6], l[7]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars[B_A_READY + s]);
+                    }
+                    // masked A tiles for the final GEMM: row <- m * q (exact for 0/1 masks), mask tile <- m
+                    TC_WAIT(&bars[B_MMA_DONE], tpar);
+                    float mv[8];
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)
+                        mv[s] = s >= n_run ? 0.0f : (P.mask_in != nullptr && rowok) ? P.mask_in[(long long)b * P.min_sb + (long long)s * P.min_sq + fr] : 1.0f;
+                    for (int s = 0; s < n_run; ++s) {
+                        if (mv[s] != 1.0f) {
+                            unsigned char *at = smem + SM_AT + s * 8192 + f * 16;
+#pragma unroll
+                            for (int kg = 0; kg < 2; ++kg) {
+                                const float4 hv = *reinterpret_cast<const float4 *>(at + kg * 2048), lv = *reinterpret_cast<const float4 *>(at + 4096 + kg * 2048);
+                                const float qm[4] = {__fmul_rn(mv[s], __fadd_rn(hv.x, lv.x)), __fmul_rn(mv[s], __fadd_rn(hv.y, lv.y)),
+                                                     __fmul_rn(mv[s], __fadd_rn(hv.z, lv.z)), __fmul_rn(mv[s], __fadd_rn(hv.w, lv.w))};
+                                const float hh[4] = {tf32_hi(qm[0]), tf32_hi(qm[1]), tf32_hi(qm[2]), tf32_hi(qm[3])};
+                                *reinterpret_cast<float4 *>(at + kg * 2048) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                                *reinterpret_cast<float4 *>(at + 4096 + kg * 2048) =
+                                    make_float4(__fsub_rn(qm[0], hh[0]), __fsub_rn(qm[1], hh[1]), __fsub_rn(qm[2], hh[2]), __fsub_rn(qm[3], hh[3]));
+                            }
+                        }
+                    }
+                    unsigned char *am = smem + SM_AM + f * 16;
+                    *reinterpret_cast<float4 *>(am) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+                    *reinterpret_cast<float4 *>(am + 2048) = make_float4(mv[4], mv[5], mv[6], mv[7]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[B_ZQ_READY]);
+                }
+            } else {
             // ---- phase S ----
             float zev[8];  // frame threads: z_e of the current stage
             for (int s = 0; s < n_run; ++s) {
@@ -584,12 +652,14 @@ auto drain = [&](int g, uint32_t tq) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[B_ZQ_READY]);
             }
+            }  // !FC
             ph_mark(6);
         } else if (w < 12) {
             // =====================================================================================================
             // Epilogue warps: TMEM -> global.  Lane quarter q4 = w - 8, frame f = 32*q4 + lane.
             // =====================================================================================================
-            for (int g = 0; g < NG; ++g) drain(g, tmem + ((uint32_t)(32 * (w - 8)) << 16));
+            if constexpr (!FC)
+                for (int g = 0; g < NG; ++g) drain(g, tmem + ((uint32_t)(32 * (w - 8)) << 16));
             tmem_fence_before_sync();
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
@@ -656,7 +726,7 @@ auto drain = [&](int g, uint32_t tq) {
             // MMA issuer: lane 0 of warp 12.
             // =====================================================================================================
             constexpr uint32_t ID_128 = umma_idesc_tf32(128, 128), ID_64 = umma_idesc_tf32(128, 64), ID_32 = umma_idesc_tf32(128, 32);
-            if (lane == 0) {
+            if (!FC && lane == 0) {
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS;
                     TC_WAIT(&bars[B_L_FULL + sl], (n / L_SLOTS) & 1u);
@@ -784,7 +854,7 @@ auto drain = [&](int g, uint32_t tq) {
             tmem_fence_before_sync();
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
-            if (lane == 0) {
+            if (!FC && lane == 0) {
                 constexpr uint32_t ID_S = umma_idesc_tf32(128, SCW);
                 // codebook tile: 1024 rows -> LBO = 16384 B, SBO = 128 B
                 constexpr uint64_t DESC_CB = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)(16384 >> 4) << 16);
@@ -810,7 +880,7 @@ auto drain = [&](int g, uint32_t tq) {
             // =====================================================================================================
             // Copy producer: lane 0 of warp 13 issues every cp.async.bulk (W_in ring, W_out ring, search codebooks).
             // =====================================================================================================
-            if (lane == 0) {
+            if (!FC && lane == 0) {
                 const float *win = P.tc + TL.off_win();
                 // codebook of stage 0 (its buffer is outside the phase-L region)
                 mbar_arrive_expect_tx(&bars[B_CB_FULL + 0], 36864);
@@ -828,14 +898,14 @@ auto drain = [&](int g, uint32_t tq) {
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
             if (lane == 0) {
-                if (n_run > 1) {  // codebook of stage 1 (its buffer is inside the phase-L region)
+                if (!FC && n_run > 1) {  // codebook of stage 1 (its buffer is inside the phase-L region)
                     mbar_arrive_expect_tx(&bars[B_CB_FULL + 1], 36864);
                     bulk_g2s(smem + SM_CB1, P.tc + TL.off_cbk() + 9216, 36864, &bars[B_CB_FULL + 1]);
                 }
                 // W_out ring of the per-stage out_proj: chunk (s, j), row-major; refills of the search codebooks interleaved
                 const float *wout = P.tc + TL.off_wout();
                 const float *bout = P.tc + TL.off_bout();
-                int wi = 0, cs = 0;
+                int wi = 0, cs = FC ? n_run : 0;  // (from_codes: no search codebooks to refill)
                 uint32_t spins = 0;
                 while (wi < n_stage_steps || cs < n_run) {
                     bool progressed = false;
@@ -963,16 +1033,16 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
     return VRVQ_OK;
 }
 
-template <int D, bool ZQIS, bool PROFILE>
+template <int D, bool ZQIS, bool PROFILE, bool FC = false>
 static int launch_tc_one(const TcParams &P, int grid, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        int rc = check_cuda(cudaFuncSetAttribute(rvq_encode_tc_kernel<D, ZQIS, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL),
+        int rc = check_cuda(cudaFuncSetAttribute(rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL),
                             "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
         if (rc) return rc;
         attr_done = true;
     }
-    rvq_encode_tc_kernel<D, ZQIS, PROFILE><<<grid, TC_NTH, SM_TOTAL, st>>>(P);
+    rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC><<<grid, TC_NTH, SM_TOTAL, st>>>(P);
     return check_cuda(cudaGetLastError(), "rvq_encode_tc_kernel launch");
 }
 template <int D, bool ZQIS>
@@ -1046,6 +1116,48 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
         cudaFree(P.e.phase_cycles);
     }
     return rc;
+}
+
+
+// ---- from_codes on the tensor-core path (vrvq_from_codes_f32 for models with <= 8 codebooks) ------------------------
+int from_codes_tc_usable(const vrvq_from_codes_args *a) {
+    const long long lim = 1ll << 27;
+    if (!tc_shape_ok(a->input_dim, a->codebook_size, a->n_codebooks)) return 0;
+    if (a->z_q_stride_d < 0 || a->z_q_stride_d >= lim) return 0;
+    if (a->z_q_is != nullptr && (a->z_q_is_stride_d < 0 || a->z_q_is_stride_d >= lim)) return 0;
+    const char *impl = getenv("VRVQ_ENCODE_IMPL");
+    return !(impl != nullptr && impl[0] == 'c');
+}
+
+int from_codes_tc(const vrvq_from_codes_args *a, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TcParams P{};
+    EncodeParams &e = P.e;
+    e.blob = static_cast<const float *>(a->blob);
+    e.B = a->B; e.T = a->T; e.Nq = a->n_codebooks; e.n_run = a->n_run;
+    e.z_q = a->z_q; e.zq_sb = a->z_q_stride_b; e.zq_sd = a->z_q_stride_d;
+    e.z_q_is = a->z_q_is; e.zqis_sb = a->z_q_is_stride_b; e.zqis_sq = a->z_q_is_stride_q; e.zqis_sd = a->z_q_is_stride_d;
+    e.latents = a->z_p; e.lat_sb = a->z_p_stride_b; e.lat_sc = a->z_p_stride_c;  // z_p = the gathered rows, latents layout
+    const BlobLayout L(a->input_dim, a->codebook_size);
+    P.tc = e.blob + (size_t)BLOB_HDR_FLOATS + (size_t)a->n_codebooks * (size_t)L.stage_floats();
+    P.codes_in = reinterpret_cast<const long long *>(a->codes); P.cin_sb = a->codes_stride_b; P.cin_sq = a->codes_stride_q;
+    P.mask_in = a->mask; P.min_sb = a->mask_stride_b; P.min_sq = a->mask_stride_q;
+    P.error_flag = a->error_flag;
+    int dev = 0, sms = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    rc = check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+    if (rc) return rc;
+    pick_tiling(a->B, a->T, sms, &P.adv, &P.tiles_per_b);
+    P.n_tiles = P.tiles_per_b * a->B;
+    const int grid = P.n_tiles < sms ? P.n_tiles : sms;
+    const bool zqis = a->z_q_is != nullptr;
+    switch (a->input_dim) {
+        case 1024: return zqis ? launch_tc_one<1024, true, false, true>(P, grid, st) : launch_tc_one<1024, false, false, true>(P, grid, st);
+        case 512: return zqis ? launch_tc_one<512, true, false, true>(P, grid, st) : launch_tc_one<512, false, false, true>(P, grid, st);
+        case 256: return zqis ? launch_tc_one<256, true, false, true>(P, grid, st) : launch_tc_one<256, false, false, true>(P, grid, st);
+        default: return VRVQ_EUNSUPPORTED;
+    }
 }
 
 }  // namespace vrvq
