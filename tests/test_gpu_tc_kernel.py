@@ -45,6 +45,10 @@ def test_tc_kernel_is_the_default_path():
     cc = run_impl("cuda", lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda"))
     assert tc["block"] == 480 and cc["block"] == 512, (tc, cc)
     assert tc["grid"] == 144  # 9 tiles of 96 frames per item: one wave on 148 SMs
+    small = run_impl(None, lambda: ops.encode_launch_info(pw, 1, 87, 8, "cuda"))
+    assert small["block"] == 512, "calls that fit one wave of the CUDA-core kernel stay on it (lower latency)"
+    forced = run_impl("tc", lambda: ops.encode_launch_info(pw, 1, 87, 8, "cuda"))
+    assert forced["block"] == 480
 
 
 @pytest.mark.parametrize("D,Nq,B,T,n_run,vbr", [
@@ -71,7 +75,7 @@ def test_tc_matches_cuda_core_kernel_and_oracle(D, Nq, B, T, n_run, vbr):
     def call():
         return ops.rvq_encode(pw, z, n_run, imp, level, want_z_q_is=True, want_loss_pf=True)
 
-    a = run_impl(None, call)
+    a = run_impl("tc", call)
     c = run_impl("cuda", call)
     o = c_oracle.encode(w, z_np, n_run if not vbr else None, imp_np, level, want_z_q_is=True)
     excused, skip = H.assert_codes_match(w, o, npy(a.codes), max_excused_frac=0.02)
@@ -100,6 +104,7 @@ def test_tc_frame_views_any_alignment(t_lo, t_hi):
     g = torch.Generator().manual_seed(78)
     z = torch.randn(B, 1024, T, generator=g).cuda()
     imp = torch.rand(B, 1, T, generator=g).cuda()
+    os.environ["VRVQ_ENCODE_IMPL"] = "tc"  # small shapes default to the CUDA-core kernel; this test is about the tensor-core one
     full = ops.rvq_encode(pw, z, None, imp, 0.7, want_z_q_is=True)
     n = t_hi - t_lo
     out = ops.EncodeOutputs(B, 1024, T, 8, "cuda", z_q=True, z_q_is=True, latents=True, mask=True)
@@ -117,6 +122,7 @@ def test_tc_frame_views_any_alignment(t_lo, t_hi):
         assert torch.equal(got[..., t_lo:t_hi], ref[..., t_lo:t_hi]), f"{name}: view [{t_lo},{t_hi}) differs from the full call"
         outside = torch.cat([got[..., :t_lo].reshape(-1), got[..., t_hi:].reshape(-1)])
         assert bool((outside == -7).all()), f"{name}: wrote outside the view"
+    os.environ.pop("VRVQ_ENCODE_IMPL", None)
 
 
 def test_tc_optional_outputs_and_nan_latent():
@@ -128,6 +134,7 @@ def test_tc_optional_outputs_and_nan_latent():
     g = torch.Generator().manual_seed(56)
     z = torch.randn(B, 1024, T, generator=g).cuda()
     imp = torch.rand(B, 1, T, generator=g).cuda()
+    os.environ["VRVQ_ENCODE_IMPL"] = "tc"
     ref = ops.rvq_encode(pw, z, None, imp, 0.5, want_z_q_is=True)
     only_codes = ops.EncodeOutputs(B, 1024, T, 8, "cuda", z_q=False, z_q_is=False, latents=False, mask=False)
     ops.rvq_encode_into(pw, z, only_codes, 8, imp, 0.5)
@@ -146,6 +153,7 @@ def test_tc_optional_outputs_and_nan_latent():
     assert torch.equal(r2.codes.permute(0, 2, 1)[keep], ref.codes.permute(0, 2, 1)[keep])
     assert torch.equal(r2.z_q.permute(0, 2, 1)[keep], ref.z_q.permute(0, 2, 1)[keep])
     zf = c_oracle.encode(c_oracle.OracleWeights.from_state_dict(sd), npy(z2[0:1, :, 5:6]), None, npy(imp[0:1, :, 5:6]), 0.5)
+    os.environ.pop("VRVQ_ENCODE_IMPL", None)
     assert np.array_equal(npy(r2.codes[0:1, :, 5:6]), zf["codes"]), "all-zero latent: exact fallback scan must match the oracle"
 
 
@@ -166,14 +174,14 @@ def test_from_codes_on_the_tensor_core_path(D, Nq, n, B, T, masked):
     def call(c=codes, m=mask):
         return ops.from_codes(pw, c, m, want_z_q_is=True, want_z_p=True)
 
-    zq, zp, zqis = run_impl(None, call)
+    zq, zp, zqis = run_impl("tc", call)
     zq_c, zp_c, zqis_c = run_impl("cuda", call)
     assert torch.equal(zp, zp_c), "z_p = the gathered codebook rows"
     H.assert_close_frames(npy(zq), npy(zq_c), rtol=5e-6, what="from_codes z_q: tensor cores vs CUDA cores")
     H.assert_close_frames(npy(zqis).reshape(B, -1, T), npy(zqis_c).reshape(B, -1, T), rtol=5e-6, what="from_codes z_q_is")
     if T >= 40:  # a frame-range view reproduces the full call bit for bit
         sl = slice(5, T - 3)
-        zq_v, zp_v, _ = run_impl(None, lambda: call(codes[:, :, sl], None if mask is None else mask[:, :, sl]))
+        zq_v, zp_v, _ = run_impl("tc", lambda: call(codes[:, :, sl], None if mask is None else mask[:, :, sl]))
         assert torch.equal(zq_v, zq[:, :, sl]) and torch.equal(zp_v, zp[:, :, sl])
     bad = codes.clone()
     bad[0, 0, 0] = 1024

@@ -35,6 +35,8 @@ struct EncodeParams {
 
 // validates the ABI struct and fills the kernel parameters (rvq_encode.cu)
 int fill_encode_params(const vrvq_encode_args *a, EncodeParams &p);
+// true if a call of this size should go to the tensor-core kernel (rvq_encode.cu)
+bool prefer_tc_for_size(int B, int T);
 // tensor-core path (rvq_encode_tc.cu): 1 if this call can run on it
 int encode_tc_usable(const vrvq_encode_args *a);
 int encode_tc(const vrvq_encode_args *a, const EncodeParams &p, void *stream);

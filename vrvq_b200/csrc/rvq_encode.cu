@@ -720,11 +720,26 @@ static int pick_grid(const EncodeParams &p, int *grid) {
     return VRVQ_OK;
 }
 
-// VRVQ_ENCODE_IMPL=cuda forces the CUDA-core kernel (A/B comparisons); default: tensor-core kernel where it applies
+// Kernel choice.  The tensor-core kernel has a fixed cost per tile of ~130 us (in_proj stream, eight serial stages) whatever the
+// number of frames in it; the CUDA-core kernel finishes one wave of 32-frame tiles in ~95 us.  So calls that fit one such wave
+// (B * ceil(T / 32) <= #SMs, e.g. a single 1 s .. 60 s clip) stay on the CUDA-core kernel, everything larger goes to the tensor
+// cores.  VRVQ_ENCODE_IMPL=cuda / =tc force one or the other (A/B comparisons, tests).
+bool prefer_tc_for_size(int B, int T) {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
+        else { cudaGetLastError(); return true; }
+    }
+    const char *impl = getenv("VRVQ_ENCODE_IMPL");
+    if (impl != nullptr && impl[0] == 't') return true;
+    return (long long)B * ((T + 31) / 32) > sms;
+}
+
 static bool use_tc(const vrvq_encode_args *a) {
     const char *impl = getenv("VRVQ_ENCODE_IMPL");
     if (impl != nullptr && impl[0] == 'c') return false;
-    return encode_tc_usable(a) != 0;
+    return encode_tc_usable(a) != 0 && prefer_tc_for_size(a->B, a->T);
 }
 
 int encode_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem) {

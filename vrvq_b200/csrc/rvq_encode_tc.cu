@@ -1126,7 +1126,8 @@ int from_codes_tc_usable(const vrvq_from_codes_args *a) {
     if (a->z_q_stride_d < 0 || a->z_q_stride_d >= lim) return 0;
     if (a->z_q_is != nullptr && (a->z_q_is_stride_d < 0 || a->z_q_is_stride_d >= lim)) return 0;
     const char *impl = getenv("VRVQ_ENCODE_IMPL");
-    return !(impl != nullptr && impl[0] == 'c');
+    if (impl != nullptr && impl[0] == 'c') return 0;
+    return prefer_tc_for_size(a->B, a->T) ? 1 : 0;
 }
 
 int from_codes_tc(const vrvq_from_codes_args *a, void *stream) {
