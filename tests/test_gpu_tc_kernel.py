@@ -187,3 +187,15 @@ def test_from_codes_on_the_tensor_core_path(D, Nq, n, B, T, masked):
     bad[0, 0, 0] = 1024
     with pytest.raises(IndexError):
         ops.from_codes(pw, bad)
+
+
+def test_random_shapes_tensor_core_vs_cuda_core():
+    """Seeded random sweep (scripts/stress_tc.py): D, Nq, n_run, B, T (tile-boundary values), VBR/CBR, with/without z_q_is --
+    tensor-core kernel vs CUDA-core kernel: masks and kept counts identical, >= 97 % of the frames with identical codes,
+    z_q / z_q_is / latents within 1e-5 on those frames."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("stress_tc", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "stress_tc.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    worst = mod.run_cases(11, 14, verbose=False)
+    assert worst <= 1e-5
