@@ -176,6 +176,24 @@ int vrvq_remask_f32(const float *z_q_is, int64_t s_b, int64_t s_q, int64_t s_d, 
                     int64_t zq_stride_b, int64_t zq_stride_d, float *mask, int64_t mask_stride_b,
                     int64_t mask_stride_q, unsigned long long *kept, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Compact code / mask wire format.  codes_u16 is what the reference's DACFile.save writes
+ * (models/dac_base.py:34: codes.numpy().astype(np.uint16); read back with .astype(int), :52); counts replaces the Nq
+ * floats per frame of the hard importance mask (models/utils.py:55-61: a prefix of ones) by one byte per frame.
+ *   pack:   codes_u16[b,k,t] = k < counts[b,t] ? (uint16)codes[b,k,t] : 0;  counts[b,t] = number of leading ones of
+ *           mask[b,:,t] (mask == NULL: every stage kept, counts may be NULL).  codes_u16 is contiguous [B][nq][T],
+ *           counts contiguous [B][T].
+ *   unpack: codes[b,k,t] = codes_u16[b,k,t];  mask[b,k,t] = k < counts[b,t] ? 1 : 0  (counts == NULL: all ones).
+ * error_flag (device int32, caller-zeroed, may be NULL) gets bit 0 when a code is outside [0, 65535] and bit 1 when the mask is
+ * not a 0/1 prefix mask (pack) or a count exceeds nq (unpack).
+ * ------------------------------------------------------------------------------------------- */
+int vrvq_pack_codes_u16(const int64_t *codes, int64_t codes_stride_b, int64_t codes_stride_q, const float *mask,
+                        int64_t mask_stride_b, int64_t mask_stride_q, int B, int T, int nq, uint16_t *codes_u16,
+                        uint8_t *counts, int32_t *error_flag, void *stream);
+int vrvq_unpack_codes_u16(const uint16_t *codes_u16, const uint8_t *counts, int B, int T, int nq, int64_t *codes,
+                          int64_t codes_stride_b, int64_t codes_stride_q, float *mask, int64_t mask_stride_b,
+                          int64_t mask_stride_q, int32_t *error_flag, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,7 @@ def load():
     from models import quantize as q  # noqa: E402
     from models import utils as u  # noqa: E402
     from models import dac_vrvq as d  # noqa: E402
+    from models import dac_base as db  # noqa: E402
 
     ns = types.SimpleNamespace(
         VectorQuantize=q.VectorQuantize,
@@ -57,5 +58,6 @@ def load():
         cal_bpf_from_mask=u.cal_bpf_from_mask,
         DAC_VRVQ=d.DAC_VRVQ,
         Encoder=d.Encoder,
+        DACFile=db.DACFile,
     )
     return ns

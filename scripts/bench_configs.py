@@ -70,6 +70,17 @@ def main():
     res["companions"].append({"kernel": "generate_mask_hard", "us": t * 1e6})
     t = timeit(lambda: ops.mask_sums(enc.mask))
     res["companions"].append({"kernel": "mask_sums (cal_bpf numerator)", "us": t * 1e6})
+    # wire format (section 8(f) row 4): algorithmic bytes per frame = int64 codes + float mask in, uint16 codes + one count out
+    from vrvq_b200 import wire
+    for Bw, Tw in ((16, 862), (32, 5168)):
+        cw = torch.randint(0, 1024, (Bw, Nq, Tw), device="cuda")
+        mw = ops.generate_mask_hard(torch.rand(Bw, 1, Tw, device="cuda") * 8.0, Nq)
+        b = Bw * Tw * (12 * Nq + 2 * Nq + 1)
+        t = timeit(lambda: wire.pack_codes(cw, mw))
+        res["companions"].append({"kernel": f"pack_codes B={Bw} T={Tw} (incl. the error-flag read-back)", "us": t * 1e6, "GBps_algorithmic": b / t / 1e9, "frac_of_hbm_peak": b / t / 1e9 / PEAK})
+        u16, cnt = wire.pack_codes(cw, mw)
+        t = timeit(lambda: wire.unpack_codes(u16, cnt))
+        res["companions"].append({"kernel": f"unpack_codes B={Bw} T={Tw} (incl. the error-flag read-back)", "us": t * 1e6, "GBps_algorithmic": b / t / 1e9, "frac_of_hbm_peak": b / t / 1e9 / PEAK})
     # config 5: PyTorch encoder (+subnet) feeding the fused kernel, 4 items x 5 s per GPU
     import vrvq_b200
     torch.manual_seed(0)

@@ -84,3 +84,23 @@ def test_mirror_encoder_matches_reference(ref):
         zo, fo = ours.encoder(xo, return_feat=True)
     assert zr.shape == (1, 1024, 87)
     assert torch.allclose(zr, zo, rtol=1e-4, atol=1e-6) and torch.allclose(fr, fo, rtol=1e-4, atol=1e-5)
+
+
+def test_dac_file_interoperates_with_the_reference_container(ref, tmp_path):
+    """models/dac_base.py:18-58: files written by the reference's DACFile load through the mirror and vice versa, and the
+    oracle's packed codes are the uint16 array the reference stores."""
+    from oracle import wire as ow
+    from vrvq_b200 import wire
+
+    codes = torch.randint(0, 1024, (2, 8, 60))
+    meta = dict(chunk_length=60, original_length=30720, input_db=torch.tensor([-18.5]), channels=1, sample_rate=44100, padding=True,
+                dac_version="1.0.0")
+    p_ref = ref.DACFile(codes=codes, **meta).save(tmp_path / "from_ref")
+    stored = np.load(p_ref, allow_pickle=True)[()]["codes"]
+    assert stored.dtype == np.uint16 and np.array_equal(stored, ow.pack_codes(codes.numpy())[0])
+    ours = wire.DACFile.load(p_ref)
+    assert torch.equal(ours.codes, codes) and ours.counts is None and ours.original_length == 30720 and ours.padding is True
+    p_ours = wire.DACFile(codes=codes, **meta).save(tmp_path / "from_ours")
+    theirs = ref.DACFile.load(p_ours)
+    assert torch.equal(theirs.codes, codes) and theirs.chunk_length == 60 and theirs.sample_rate == 44100
+    assert open(p_ref, "rb").read() == open(p_ours, "rb").read(), "CBR files are byte-identical to the reference's"

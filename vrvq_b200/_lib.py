@@ -54,6 +54,7 @@ EXPORTS = [
     "vrvq_abi_version", "vrvq_last_error", "vrvq_supported", "vrvq_blob_bytes", "vrvq_pack_weights",
     "vrvq_blob_codebook", "vrvq_rvq_encode_f32", "vrvq_rvq_encode_launch_info", "vrvq_from_codes_f32",
     "vrvq_search_latents_f32", "vrvq_generate_mask_hard_f32", "vrvq_mask_sum_f32", "vrvq_remask_f32",
+    "vrvq_pack_codes_u16", "vrvq_unpack_codes_u16",
 ]
 
 _lib = None
@@ -94,6 +95,10 @@ def lib():
     L.vrvq_remask_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_void_p]
+    L.vrvq_pack_codes_u16.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vrvq_unpack_codes_u16.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                        C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     if L.vrvq_abi_version() != ABI_VERSION:
         raise ImportError(f"libvrvq.so ABI {L.vrvq_abi_version()} != binding ABI {ABI_VERSION}; rebuild with python -m vrvq_b200.build")
     _lib = L

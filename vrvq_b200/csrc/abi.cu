@@ -53,6 +53,10 @@ int launch_remask(const float *zis, long long s_b, long long s_q, long long s_d,
                   int B, int D, int T, int nq, float *zq, long long zq_sb, long long zq_sd, float *mask, long long m_sb, long long m_sq,
                   unsigned long long *kept, cudaStream_t st);
 int launch_from_codes(const vrvq_from_codes_args *a, cudaStream_t st);
+int launch_pack_codes(const long long *codes, long long c_sb, long long c_sq, const float *mask, long long m_sb, long long m_sq, int B, int T,
+                      int nq, unsigned short *out, unsigned char *counts, int *error_flag, cudaStream_t st);
+int launch_unpack_codes(const unsigned short *in, const unsigned char *counts, int B, int T, int nq, long long *codes, long long c_sb,
+                        long long c_sq, float *mask, long long m_sb, long long m_sq, int *error_flag, cudaStream_t st);
 int launch_search_latents(const float *blob, int D, int K, const float *lat, long long l_sb, long long l_sc, int B, int T, int n_run,
                           long long *codes, long long c_sb, long long c_sq, cudaStream_t st);
 
@@ -312,6 +316,33 @@ int vrvq_remask_f32(const float *z_q_is, int64_t s_b, int64_t s_q, int64_t s_d, 
     if (rc) return rc;
     return launch_remask(z_q_is, s_b, s_q, s_d, imp_map, imp_stride_b, level_times_nq, B, D, T, nq, z_q, zq_stride_b, zq_stride_d, mask,
                          mask_stride_b, mask_stride_q, kept, static_cast<cudaStream_t>(stream));
+}
+
+int vrvq_pack_codes_u16(const int64_t *codes, int64_t codes_stride_b, int64_t codes_stride_q, const float *mask, int64_t mask_stride_b,
+                        int64_t mask_stride_q, int B, int T, int nq, uint16_t *codes_u16, uint8_t *counts, int32_t *error_flag, void *stream) {
+    const bool work = (long long)B * T * nq > 0;
+    if (B < 0 || T < 0 || nq < 0 || nq > 255 || (work && (!codes || !codes_u16 || (mask && !counts)))) {
+        set_error("vrvq_pack_codes_u16: bad arguments (nq <= 255; counts is required with a mask)");
+        return VRVQ_EINVAL;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_pack_codes(reinterpret_cast<const long long *>(codes), codes_stride_b, codes_stride_q, mask, mask_stride_b, mask_stride_q, B,
+                             T, nq, codes_u16, counts, error_flag, static_cast<cudaStream_t>(stream));
+}
+
+int vrvq_unpack_codes_u16(const uint16_t *codes_u16, const uint8_t *counts, int B, int T, int nq, int64_t *codes, int64_t codes_stride_b,
+                          int64_t codes_stride_q, float *mask, int64_t mask_stride_b, int64_t mask_stride_q, int32_t *error_flag,
+                          void *stream) {
+    const bool work = (long long)B * T * nq > 0;
+    if (B < 0 || T < 0 || nq < 0 || nq > 255 || (work && (!codes_u16 || !codes))) {
+        set_error("vrvq_unpack_codes_u16: bad arguments (nq <= 255)");
+        return VRVQ_EINVAL;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_unpack_codes(codes_u16, counts, B, T, nq, reinterpret_cast<long long *>(codes), codes_stride_b, codes_stride_q, mask,
+                               mask_stride_b, mask_stride_q, error_flag, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
