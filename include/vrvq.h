@@ -194,6 +194,23 @@ int vrvq_unpack_codes_u16(const uint16_t *codes_u16, const uint8_t *counts, int 
                           int64_t codes_stride_b, int64_t codes_stride_q, float *mask, int64_t mask_stride_b,
                           int64_t mask_stride_q, int32_t *error_flag, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Importance subnet.  Replaces one `nn.Sequential(Snake1d(Cin), WNConv1d(Cin, Cout,
+ * kernel_size=3, padding=1))` block of models/importance_subnet.py:18-34 (forward :38-44); the caller chains the six
+ * blocks (1024 -> 1024 -> 512 -> 128 -> 32 -> 8 -> 1) and sets apply_sigmoid on the last one (:43).
+ *   y[b,co,t] = bias[co] + sum_{ci<Cin, k<3} w[co,ci,k] * snake(x[b,ci,t+k-1]),  zero outside [0,T)
+ *   snake(v)  = v + 1/(alpha[ci] + 1e-9) * sin(alpha[ci] * v)^2                   (models/layers.py:25-31)
+ * w is the weight-norm-folded conv weight (torch._weight_norm(v, g, 0), models/layers.py:17-18), re-laid out by
+ * vrvq_pack_conv3_weights (host buffers) as packed[(ci*3+k) * Cout_padded + co], Cout_padded = Cout rounded up to
+ * VRVQ_CONV3_COUT_ALIGN, zero filled.  alpha[Cin], bias[Cout], packed: device fp32.  Cin must be a multiple of 8.
+ * ------------------------------------------------------------------------------------------- */
+#define VRVQ_CONV3_COUT_ALIGN 128
+size_t vrvq_conv3_packed_floats(int Cout, int Cin);
+int vrvq_pack_conv3_weights(int Cout, int Cin, const float *w, float *packed, size_t packed_floats);
+int vrvq_snake_conv3_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, const float *alpha, const float *packed,
+                         const float *bias, int B, int Cin, int Cout, int T, int apply_sigmoid, float *y, int64_t y_stride_b,
+                         int64_t y_stride_c, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,3 +75,34 @@ CASES = {
     "vbr_t1": dict(kind="vbr", seed=16, D=1024, Nq=8, K=1024, B=3, T=1, sigma=0.007, levels=[1.0], imp_seed=26),
     "cbr_t3": dict(kind="cbr", seed=17, D=1024, Nq=8, K=1024, B=2, T=3, sigma=0.007, n_quantizers=[None, 1]),
 }
+
+
+def make_subnet_state_dict(seed: int, d_input: int, d_feat: int, widths=(512, 128, 32, 8), out_channels: int = 1):
+    """Importance-subnet parameters with the reference's keys (models/importance_subnet.py:18-34): per block
+    `<snake>.alpha [1,Cin,1]`, `<conv>.bias [Cout]`, `.weight_g [Cout,1,1]`, `.weight_v [Cout,Cin,3]`.  Rows of v have
+    about unit norm; alpha, g and the biases are randomised so that the Snake and the weight-norm fold are exercised."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f32 = np.float32
+    cin = [d_input, d_feat] + list(widths)
+    cout = [d_feat] + list(widths) + [out_channels]
+    names = [("in_block.0.", "in_block.1.")] + [(f"blocks.{i}.0.", f"blocks.{i}.1.") for i in range(len(widths) + 1)]
+    sd = {}
+    for (sk, ck), ci, co in zip(names, cin, cout):
+        v = (rng.uniform(-1.0, 1.0, (co, ci, 3)) / np.sqrt(ci)).astype(f32)
+        g = (np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)) * rng.uniform(0.5, 1.5, (co, 1, 1))).astype(f32)
+        sd[sk + "alpha"] = rng.uniform(0.5, 1.5, (1, ci, 1)).astype(f32)
+        sd[ck + "bias"] = rng.normal(0.0, 0.05, (co,)).astype(f32)
+        sd[ck + "weight_g"] = g
+        sd[ck + "weight_v"] = v
+    return sd
+
+
+# importance-subnet fixtures (tests/golden/subnet_*.npz hold the reference's imp_map only; inputs come from the seeds)
+SUBNET_CASES = {
+    # the shipped architecture (models/quantize.py:317-323: d_input = d_feat = 1024, widths 512/128/32/8), config-1 length
+    "subnet_d1024": dict(seed=31, d_input=1024, d_feat=1024, widths=(512, 128, 32, 8), B=2, T=87, sigma=1.0),
+    # narrow net, frame counts around the 128-frame tile edge and the degenerate lengths
+    "subnet_small_t130": dict(seed=32, d_input=64, d_feat=48, widths=(32, 16, 8, 8), B=3, T=130, sigma=1.5),
+    "subnet_small_t1": dict(seed=33, d_input=64, d_feat=48, widths=(32, 16, 8, 8), B=2, T=1, sigma=1.5),
+    "subnet_small_t3": dict(seed=34, d_input=64, d_feat=48, widths=(32, 16, 8, 8), B=1, T=3, sigma=1.5),
+}

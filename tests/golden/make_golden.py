@@ -110,11 +110,32 @@ def mask_cases(ref):
     print("mask_utils: wrote", path)
 
 
+def subnet_cases():
+    """imp_map of the UNMODIFIED reference ImportanceSubnet (models/importance_subnet.py) on seeded weights and features."""
+    if ref_import.REF_ROOT not in sys.path:
+        sys.path.insert(0, ref_import.REF_ROOT)
+    from models.importance_subnet import ImportanceSubnet
+
+    torch.set_num_threads(8)
+    for name, c in gi.SUBNET_CASES.items():
+        m = ImportanceSubnet(d_input=c["d_input"], d_feat=c["d_feat"], intermediate_channels=list(c["widths"]), out_channels=1).eval()
+        m.load_state_dict(gi.torch_state_dict(gi.make_subnet_state_dict(c["seed"], c["d_input"], c["d_feat"], c["widths"])), strict=True)
+        x = torch.from_numpy(gi.make_latents(c["seed"] + 1000, c["B"], c["d_input"], c["T"], c["sigma"]))
+        with torch.no_grad():
+            imp = m(x)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, imp_map=imp.numpy())
+        print(f"{name}: wrote {path}, imp_map in [{imp.min():.3f}, {imp.max():.3f}]")
+
+
 def main():
     ref = ref_import.load()
+    if "--subnet-only" in sys.argv:
+        return subnet_cases()
     for name, case in gi.CASES.items():
         run_case(ref, name, case)
     mask_cases(ref)
+    subnet_cases()
 
 
 if __name__ == "__main__":

@@ -61,7 +61,7 @@ def test_mirror_state_dict_keys_match_reference(ref):
     # the PyTorch importance subnet (upstream producer) must agree numerically with the reference's
     feat = torch.randn(2, 1024, 50)
     with torch.no_grad():
-        a, b = r.imp_subnet(feat), ours.imp_subnet(feat)
+        a, b = r.imp_subnet(feat), ours.imp_subnet.forward_torch(feat)
     assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
 
 

@@ -57,6 +57,8 @@ int launch_pack_codes(const long long *codes, long long c_sb, long long c_sq, co
                       int nq, unsigned short *out, unsigned char *counts, int *error_flag, cudaStream_t st);
 int launch_unpack_codes(const unsigned short *in, const unsigned char *counts, int B, int T, int nq, long long *codes, long long c_sb,
                         long long c_sq, float *mask, long long m_sb, long long m_sq, int *error_flag, cudaStream_t st);
+int launch_snake_conv3(const float *x, long long x_sb, long long x_sc, const float *alpha, const float *wp, int cout_pad, const float *bias,
+                       int B, int Cin, int Cout, int T, int sigmoid, float *y, long long y_sb, long long y_sc, cudaStream_t st);
 int launch_search_latents(const float *blob, int D, int K, const float *lat, long long l_sb, long long l_sc, int B, int T, int n_run,
                           long long *codes, long long c_sb, long long c_sq, cudaStream_t st);
 
@@ -343,6 +345,43 @@ int vrvq_unpack_codes_u16(const uint16_t *codes_u16, const uint8_t *counts, int 
     if (rc) return rc;
     return launch_unpack_codes(codes_u16, counts, B, T, nq, reinterpret_cast<long long *>(codes), codes_stride_b, codes_stride_q, mask,
                                mask_stride_b, mask_stride_q, error_flag, static_cast<cudaStream_t>(stream));
+}
+
+size_t vrvq_conv3_packed_floats(int Cout, int Cin) {
+    if (Cout <= 0 || Cin <= 0) return 0;
+    const size_t cp = (size_t)((Cout + VRVQ_CONV3_COUT_ALIGN - 1) / VRVQ_CONV3_COUT_ALIGN) * VRVQ_CONV3_COUT_ALIGN;
+    return (size_t)Cin * 3 * cp;
+}
+
+int vrvq_pack_conv3_weights(int Cout, int Cin, const float *w, float *packed, size_t packed_floats) {
+    const size_t need = vrvq_conv3_packed_floats(Cout, Cin);
+    if (need == 0 || !w || !packed || packed_floats < need) {
+        set_error("vrvq_pack_conv3_weights: bad arguments (Cout=%d Cin=%d, %zu floats given, %zu needed)", Cout, Cin, packed_floats, need);
+        return VRVQ_EINVAL;
+    }
+    const size_t cp = need / ((size_t)Cin * 3);
+    memset(packed, 0, need * sizeof(float));
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int k = 0; k < 3; ++k) packed[((size_t)ci * 3 + k) * cp + co] = w[((size_t)co * Cin + ci) * 3 + k];
+    return VRVQ_OK;
+}
+
+int vrvq_snake_conv3_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, const float *alpha, const float *packed, const float *bias,
+                         int B, int Cin, int Cout, int T, int apply_sigmoid, float *y, int64_t y_stride_b, int64_t y_stride_c, void *stream) {
+    if (B < 0 || T < 0 || Cin < 1 || Cout < 1 || !alpha || !packed || !bias || ((long long)B * T > 0 && (!x || !y))) {
+        set_error("vrvq_snake_conv3_f32: bad arguments");
+        return VRVQ_EINVAL;
+    }
+    if (Cin % 8 != 0) {
+        set_error("vrvq_snake_conv3_f32: Cin=%d must be a multiple of 8 (all reference subnet widths are)", Cin);
+        return VRVQ_EUNSUPPORTED;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    const int cp = (int)(vrvq_conv3_packed_floats(Cout, Cin) / ((size_t)Cin * 3));
+    return launch_snake_conv3(x, x_stride_b, x_stride_c, alpha, packed, cp, bias, B, Cin, Cout, T, apply_sigmoid, y, y_stride_b, y_stride_c,
+                              static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,157 @@
+// Importance subnet: one block of models/importance_subnet.py:18-34, i.e.
+//   y[b,co,t] = bias[co] + sum_{ci,k} W[co,ci,k] * snake(x[b,ci,t+k-1])        (Snake1d -> WNConv1d(k=3, padding=1))
+// with snake(v) = v + 1/(alpha+1e-9) * sin(alpha v)^2 (models/layers.py:25-31) and, for the last block, the
+// sigmoid of models/importance_subnet.py:43 fused into the epilogue.
+//
+// Formulation: an implicit GEMM per batch item, M = output channels, N = frames, K = 3*Cin, fp32 on the CUDA cores
+// (first correct version of this row; the two big layers, 1024->1024 and 1024->512, are the tensor-core candidates).
+//   * CTA tile 128 output channels x 128 frames, 256 threads, 8x8 accumulators per thread;
+//   * K runs in chunks of 8 input channels (24 K-rows): the weight chunk [24][128] comes from the host-packed
+//     [Cin*3][Cout_padded] layout with coalesced 16-byte loads; the activation chunk [8][130] (one halo frame each
+//     side) is loaded once, passed through Snake, and serves all three taps from shared memory;
+//   * global loads of chunk c+1 are issued before the FMAs of chunk c (register prefetch, two smem buffers,
+//     one barrier per chunk);
+//   * zero padding at the sequence ends is applied after Snake, as the reference's conv does (snake(0) = 0).
+#include "common.cuh"
+
+namespace vrvq {
+
+void set_error(const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);
+
+namespace {
+
+constexpr int SN_TM = 128;  // output channels per CTA (= VRVQ_CONV3_COUT_ALIGN)
+constexpr int SN_TN = 128;  // frames per CTA
+constexpr int SN_KC = 8;    // input channels per chunk
+constexpr int SN_XW = SN_TN + 2;
+constexpr int SN_XLD = 136;  // row stride of the activation chunk in shared memory
+static_assert(SN_TM == VRVQ_CONV3_COUT_ALIGN, "packed weight rows are padded to the CTA tile");
+
+__device__ __forceinline__ float snake_f32(float v, float a, float inv_a) {
+    const float s = sinf(a * v);
+    return v + inv_a * (s * s);
+}
+
+template <bool SIGMOID>
+__global__ void __launch_bounds__(256, 2)
+snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, const float *__restrict__ alpha,
+                   const float *__restrict__ wp, int cout_pad, const float *__restrict__ bias, float *__restrict__ y, long long y_sb,
+                   long long y_sc, int Cin, int Cout, int T) {
+    __shared__ __align__(16) float Ws[2][SN_KC * 3][SN_TM];
+    __shared__ __align__(16) float Xs[2][SN_KC][SN_XLD];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int t0 = blockIdx.x * SN_TN;
+    const int co0 = blockIdx.y * SN_TM;
+    const int b = blockIdx.z;
+    const float *xb = x + (long long)b * x_sb;
+
+    // loader roles: activations -- channel lci, columns lane + 32 m (m < 4) and 128 + lane (lane < 2);
+    //               weights     -- three float4 at flat index tid + 256 m of the [24][128] chunk
+    const int lci = tid >> 5, lane = tid & 31;
+    float xr[5];
+    float4 wr[3];
+
+    auto load_chunk = [&](int c) {
+        const int ci = c * SN_KC + lci;
+        const float a = __ldg(alpha + ci);
+        const float inv_a = 1.0f / (a + 1e-9f);
+        const float *xrow = xb + (long long)ci * x_sc;
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+            const int i = lane + 32 * m;
+            const int t = t0 - 1 + i;
+            float v = 0.0f;
+            if (i < SN_XW && t >= 0 && t < T) v = snake_f32(__ldg(xrow + t), a, inv_a);
+            xr[m] = v;
+        }
+        const float *wrow = wp + (long long)c * (SN_KC * 3) * cout_pad + co0;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int idx = tid + 256 * m;
+            wr[m] = __ldg(reinterpret_cast<const float4 *>(wrow + (long long)(idx >> 5) * cout_pad) + (idx & 31));
+        }
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+            const int i = lane + 32 * m;
+            if (i < SN_XW) Xs[buf][lci][i] = xr[m];
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int idx = tid + 256 * m;
+            *reinterpret_cast<float4 *>(&Ws[buf][idx >> 5][(idx & 31) * 4]) = wr[m];
+        }
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+    const int nchunks = Cin / SN_KC;
+    load_chunk(0);
+    store_chunk(0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunks) load_chunk(c + 1);
+#pragma unroll
+        for (int kk = 0; kk < SN_KC * 3; ++kk) {
+            const int ci = kk / 3, k = kk % 3;
+            const float4 a0 = *reinterpret_cast<const float4 *>(&Ws[buf][kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&Ws[buf][kk][ty * 8 + 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = Xs[buf][ci][tx + 16 * j + k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+        }
+        if (c + 1 < nchunks) store_chunk(buf ^ 1);
+        __syncthreads();
+    }
+
+    float *yb = y + (long long)b * y_sb;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int co = co0 + ty * 8 + i;
+        if (co >= Cout) break;
+        const float bi = __ldg(bias + co);
+        float *yrow = yb + (long long)co * y_sc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int t = t0 + tx + 16 * j;
+            if (t < T) {
+                float v = acc[i][j] + bi;
+                if (SIGMOID) v = 1.0f / (1.0f + expf(-v));
+                yrow[t] = v;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int launch_snake_conv3(const float *x, long long x_sb, long long x_sc, const float *alpha, const float *wp, int cout_pad, const float *bias,
+                       int B, int Cin, int Cout, int T, int sigmoid, float *y, long long y_sb, long long y_sc, cudaStream_t st) {
+    if ((long long)B * T == 0) return VRVQ_OK;
+    if (B > 65535) {
+        set_error("vrvq_snake_conv3_f32: B must be <= 65535");
+        return VRVQ_EUNSUPPORTED;
+    }
+    dim3 grid((T + SN_TN - 1) / SN_TN, (Cout + SN_TM - 1) / SN_TM, B);
+    if (sigmoid)
+        snake_conv3_kernel<true><<<grid, 256, 0, st>>>(x, x_sb, x_sc, alpha, wp, cout_pad, bias, y, y_sb, y_sc, Cin, Cout, T);
+    else
+        snake_conv3_kernel<false><<<grid, 256, 0, st>>>(x, x_sb, x_sc, alpha, wp, cout_pad, bias, y, y_sb, y_sc, Cin, Cout, T);
+    return check_cuda(cudaGetLastError(), "snake_conv3_kernel launch");
+}
+
+}  // namespace vrvq

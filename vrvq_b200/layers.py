@@ -100,7 +100,11 @@ class Encoder(nn.Module):
 
 
 class ImportanceSubnet(nn.Module):
-    """Importance map producer (models/importance_subnet.py:6-45): 6 x (Snake, k=3 conv) + sigmoid -> [B,1,T]."""
+    """Importance map producer (models/importance_subnet.py:6-45): 6 x (Snake, k=3 conv) + sigmoid -> [B,1,T].
+
+    Eval forward on a CUDA fp32 tensor runs the fused Snake+conv kernels of csrc/subnet.cu (SURVEY.md section 8(f) row 3,
+    six launches, no PyTorch op in between); there is no fallback on that path -- a missing libvrvq.so raises.
+    The differentiable PyTorch formulation (`forward_torch`) serves training, which is outside this package's scope."""
 
     def __init__(self, d_input, d_feat, intermediate_channels=(512, 128, 32, 8), out_channels=1, detach_input=False):
         super().__init__()
@@ -110,11 +114,36 @@ class ImportanceSubnet(nn.Module):
         self.blocks = nn.ModuleList(
             [nn.Sequential(Snake1d(i), WNConv1d(i, o, kernel_size=3, padding=1)) for i, o in zip(cin, cout)])
         self.detach_input = detach_input
+        self._packed = None
+        self._packed_key = None
 
-    def forward(self, x):
+    def _all_blocks(self):
+        return [self.in_block] + list(self.blocks)
+
+    def packed_blocks(self, device):
+        """Fold weight-norm on the CPU (as the reference's hook does, models/layers.py:17-18) and pack once per
+        parameter version."""
+        from . import ops
+
+        key = (tuple((p.data_ptr(), p._version) for p in self.parameters()), str(device))
+        if self._packed is None or self._packed_key != key:
+            self._packed = [ops.PackedConv3(snake.alpha, ops.fold_weight_norm(conv.weight_v, conv.weight_g), conv.bias, device)
+                            for snake, conv in self._all_blocks()]
+            self._packed_key = key
+        return self._packed
+
+    def forward_torch(self, x):
         if self.detach_input:
             x = x.detach()
         x = self.in_block(x)
         for blk in self.blocks:
             x = blk(x)
         return torch.sigmoid(x)
+
+    def forward(self, x):
+        if self.training:
+            return self.forward_torch(x)
+        from . import _lib, ops
+
+        _lib.require_cuda_f32(x, "feat_enc")
+        return ops.importance_subnet(self.packed_blocks(x.device), x.detach())

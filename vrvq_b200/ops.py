@@ -318,3 +318,54 @@ def remask(z_q_is: torch.Tensor, imp_map: torch.Tensor, level_scaled: float, wan
                                          kept.data_ptr(), current_stream_ptr(dev)), "vrvq_remask_f32")
     _lib.count_launch()
     return z_q, mask, kept
+
+
+class PackedConv3:
+    """Device-resident weights of one `Snake1d -> WNConv1d(k=3, padding=1)` block of the importance subnet
+    (models/importance_subnet.py:18-34): alpha [Cin], packed conv weight [Cin*3][Cout_padded], bias [Cout]."""
+
+    def __init__(self, alpha, weight, bias, device):
+        # CPU float32: alpha [Cin] (Snake1d.alpha flattened), weight [Cout,Cin,3] already weight-norm folded, bias [Cout]
+        L = _lib.lib()
+        weight = weight.detach().to("cpu", torch.float32).contiguous()
+        if weight.dim() != 3 or weight.shape[2] != 3:
+            raise VrvqError(f"conv weight must be [Cout, Cin, 3], got {tuple(weight.shape)}")
+        self.cout, self.cin = int(weight.shape[0]), int(weight.shape[1])
+        if self.cin % 8 != 0:
+            raise VrvqError(f"importance-subnet widths must be multiples of 8 (got Cin={self.cin})")
+        n = L.vrvq_conv3_packed_floats(self.cout, self.cin)
+        packed = torch.empty(n, dtype=torch.float32)
+        check(L.vrvq_pack_conv3_weights(self.cout, self.cin, weight.data_ptr(), packed.data_ptr(), n), "vrvq_pack_conv3_weights")
+        self.device = torch.device(device)
+        self.packed = packed.to(self.device)
+        self.alpha = alpha.detach().to("cpu", torch.float32).reshape(-1).contiguous().to(self.device)
+        self.bias = bias.detach().to("cpu", torch.float32).reshape(-1).contiguous().to(self.device)
+        if self.alpha.numel() != self.cin or self.bias.numel() != self.cout:
+            raise VrvqError("alpha must have Cin entries and bias Cout entries")
+
+
+def snake_conv3(w: PackedConv3, x: torch.Tensor, sigmoid: bool = False) -> torch.Tensor:
+    """vrvq_snake_conv3_f32 -- one block of the importance subnet: x [B,Cin,T] -> [B,Cout,T]."""
+    require_cuda_f32(x, "x")
+    if x.dim() != 3 or x.shape[1] != w.cin:
+        raise VrvqError(f"x must be [B, {w.cin}, T], got {tuple(x.shape)}")
+    if x.device != w.device:
+        raise VrvqError(f"x is on {x.device} but the packed weights are on {w.device}")
+    _check_view(x, "x")
+    B, _, T = x.shape
+    y = torch.empty((B, w.cout, T), dtype=torch.float32, device=x.device)
+    if B * T == 0:
+        return y
+    with torch.cuda.device(x.device):
+        check(_lib.lib().vrvq_snake_conv3_f32(x.data_ptr(), x.stride(0), x.stride(1), w.alpha.data_ptr(), w.packed.data_ptr(),
+                                              w.bias.data_ptr(), B, w.cin, w.cout, T, int(bool(sigmoid)), y.data_ptr(), y.stride(0),
+                                              y.stride(1), current_stream_ptr(x.device)), "vrvq_snake_conv3_f32")
+    _lib.count_launch()
+    return y
+
+
+def importance_subnet(blocks, x: torch.Tensor) -> torch.Tensor:
+    """models/importance_subnet.py:38-44 on packed blocks: chain of snake_conv3 launches, sigmoid fused into the last."""
+    for i, w in enumerate(blocks):
+        x = snake_conv3(w, x, sigmoid=(i == len(blocks) - 1))
+    return x

@@ -174,7 +174,7 @@ class VBRResidualVectorQuantize(ResidualVectorQuantize):
         if n_quantizers is None:  # ---- VBR mode
             assert level is not None, "level must be specified in VBR mode"
             if imp_map is None:
-                imp_map = self.imp_subnet(feat_enc)  # upstream producer, PyTorch (quantize.py:372)
+                imp_map = self.imp_subnet(feat_enc)  # csrc/subnet.cu: six fused Snake+conv launches (quantize.py:372)
             imp_in, lvl = imp_map.contiguous(), level
             if isinstance(level, torch.Tensor):
                 lv = level.to(device=z.device, dtype=torch.float32)
