@@ -5,7 +5,8 @@
 //
 // Formulation: an implicit GEMM per batch item, M = output channels, N = frames, K = 3*Cin, fp32 on the CUDA cores
 // (first correct version of this row; the two big layers, 1024->1024 and 1024->512, are the tensor-core candidates).
-//   * CTA tile 128 output channels x 128 frames, 256 threads, 8x8 accumulators per thread;
+//   * CTA tile 128 output channels x 128 frames, 256 threads, 8x8 accumulators per thread (8 channels x 4 frame pairs,
+//     so that a 4-value activation window per pair feeds all three taps: 14 shared-memory loads per 192 FMAs);
 //   * K runs in chunks of 8 input channels (24 K-rows): the weight chunk [24][128] comes from the host-packed
 //     [Cin*3][Cout_padded] layout with coalesced 16-byte loads; the activation chunk [8][130] (one halo frame each
 //     side) is loaded once, passed through Snake, and serves all three taps from shared memory;
@@ -101,18 +102,28 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
         const int buf = c & 1;
         if (c + 1 < nchunks) load_chunk(c + 1);
 #pragma unroll
-        for (int kk = 0; kk < SN_KC * 3; ++kk) {
-            const int ci = kk / 3, k = kk % 3;
-            const float4 a0 = *reinterpret_cast<const float4 *>(&Ws[buf][kk][ty * 8]);
-            const float4 a1 = *reinterpret_cast<const float4 *>(&Ws[buf][kk][ty * 8 + 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            float bv[8];
+        for (int ci = 0; ci < SN_KC; ++ci) {
+            // frames 32 j + 2 tx + {0,1}: the four window values per j serve all three taps (two 8-byte loads)
+            float xv[4][4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bv[j] = Xs[buf][ci][tx + 16 * j + k];
+            for (int j = 0; j < 4; ++j) {
+                const float2 lo = *reinterpret_cast<const float2 *>(&Xs[buf][ci][32 * j + 2 * tx]);
+                const float2 hi = *reinterpret_cast<const float2 *>(&Xs[buf][ci][32 * j + 2 * tx + 2]);
+                xv[j][0] = lo.x, xv[j][1] = lo.y, xv[j][2] = hi.x, xv[j][3] = hi.y;
+            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int k = 0; k < 3; ++k) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(&Ws[buf][ci * 3 + k][ty * 8]);
+                const float4 a1 = *reinterpret_cast<const float4 *>(&Ws[buf][ci * 3 + k][ty * 8 + 4]);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[i][2 * j] = fmaf(a[i], xv[j][k], acc[i][2 * j]);
+                        acc[i][2 * j + 1] = fmaf(a[i], xv[j][k + 1], acc[i][2 * j + 1]);
+                    }
+            }
         }
         if (c + 1 < nchunks) store_chunk(buf ^ 1);
         __syncthreads();
@@ -126,12 +137,15 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
         const float bi = __ldg(bias + co);
         float *yrow = yb + (long long)co * y_sc;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int t = t0 + tx + 16 * j;
-            if (t < T) {
-                float v = acc[i][j] + bi;
-                if (SIGMOID) v = 1.0f / (1.0f + expf(-v));
-                yrow[t] = v;
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int t = t0 + 32 * j + 2 * tx + e;
+                if (t < T) {
+                    float v = acc[i][2 * j + e] + bi;
+                    if (SIGMOID) v = 1.0f / (1.0f + expf(-v));
+                    yrow[t] = v;
+                }
             }
         }
     }
