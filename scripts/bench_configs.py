@@ -93,7 +93,7 @@ def main():
         t_sub = timeit(lambda: m.quantizer.imp_subnet(zf[1]), iters=5, warm=2)
     res["cfg5"] = {"B_per_gpu": 4, "T": 431, "encode_ms": t_all * 1e3, "encoder_ms": t_enc * 1e3, "subnet_ms": t_sub * 1e3,
                    "rvq_ms": (t_all - t_enc - t_sub) * 1e3, "frames_per_s_e2e": 4 * 431 / t_all,
-                   "note": "conv encoder and importance subnet are PyTorch/cuDNN (upstream producers); the fused RVQ kernel is the remainder"}
+                   "note": "conv encoder is PyTorch/cuDNN (upstream producer); importance subnet = six snake_conv3 launches (csrc/subnet.cu); the fused RVQ kernel is the remainder"}
     print(json.dumps(res, indent=1))
 
 
