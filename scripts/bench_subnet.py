@@ -45,7 +45,13 @@ def main():
     x = torch.from_numpy(gi.make_latents(5, B, 1024, T, 1.0)).to(dev)
     blocks = m.packed_blocks(dev)
     props = torch.cuda.get_device_properties(dev)
-    sm_mhz = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 1965
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        sm_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(pynvml.nvmlDeviceGetHandleByIndex(0), pynvml.NVML_CLOCK_SM))
+    except Exception:
+        sm_mhz = 1965  # B200 boost clock seen in every bench run of this repo (profiles/r1*_bench.json)
     peak_tf = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
     rows, cur = [], x
     for i, w in enumerate(blocks):
