@@ -55,18 +55,17 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
     float xr[5];
     float4 wr[3];
 
+    // global -> registers (raw values: nothing here waits on the loads, so they fly under the FMAs of the current chunk)
+    float sn_a = 0.0f, sn_inv = 0.0f;
     auto load_chunk = [&](int c) {
         const int ci = c * SN_KC + lci;
-        const float a = __ldg(alpha + ci);
-        const float inv_a = 1.0f / (a + 1e-9f);
+        sn_a = __ldg(alpha + ci);
         const float *xrow = xb + (long long)ci * x_sc;
 #pragma unroll
         for (int m = 0; m < 5; ++m) {
             const int i = lane + 32 * m;
             const int t = t0 - 1 + i;
-            float v = 0.0f;
-            if (i < SN_XW && t >= 0 && t < T) v = snake_f32(__ldg(xrow + t), a, inv_a);
-            xr[m] = v;
+            xr[m] = (i < SN_XW && t >= 0 && t < T) ? __ldg(xrow + t) : 0.0f;
         }
         const float *wrow = wp + (long long)c * (SN_KC * 3) * cout_pad + co0;
 #pragma unroll
@@ -75,11 +74,13 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
             wr[m] = __ldg(reinterpret_cast<const float4 *>(wrow + (long long)(idx >> 5) * cout_pad) + (idx & 31));
         }
     };
+    // registers -> shared memory, Snake applied on the way (snake(0) = 0 keeps the zero padding)
     auto store_chunk = [&](int buf) {
+        sn_inv = 1.0f / (sn_a + 1e-9f);
 #pragma unroll
         for (int m = 0; m < 5; ++m) {
             const int i = lane + 32 * m;
-            if (i < SN_XW) Xs[buf][lci][i] = xr[m];
+            if (i < SN_XW) Xs[buf][lci][i] = snake_f32(xr[m], sn_a, sn_inv);
         }
 #pragma unroll
         for (int m = 0; m < 3; ++m) {

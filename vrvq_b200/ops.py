@@ -336,8 +336,8 @@ class PackedConv3:
         n = L.vrvq_conv3_packed_floats(self.cout, self.cin)
         packed = torch.empty(n, dtype=torch.float32)
         check(L.vrvq_pack_conv3_weights(self.cout, self.cin, weight.data_ptr(), packed.data_ptr(), n), "vrvq_pack_conv3_weights")
-        self.device = torch.device(device)
-        self.packed = packed.to(self.device)
+        self.packed = packed.to(torch.device(device))
+        self.device = self.packed.device  # resolved ("cuda" -> "cuda:0")
         self.alpha = alpha.detach().to("cpu", torch.float32).reshape(-1).contiguous().to(self.device)
         self.bias = bias.detach().to("cpu", torch.float32).reshape(-1).contiguous().to(self.device)
         if self.alpha.numel() != self.cin or self.bias.numel() != self.cout:
