@@ -110,3 +110,25 @@ def test_vbr_forward_uses_the_subnet_kernels():
     assert imp.shape == (B, 1, T)
     assert np.abs(imp.cpu().numpy() - H.load_golden("subnet_d1024")["imp_map"]).max() <= IMP_ATOL
     assert torch.equal(r["mask_imp"], vrvq_b200.generate_mask_hard(imp * 0.5 * Nq, Nq))
+
+
+def test_every_tile_width_gives_identical_results(monkeypatch):
+    """The launcher picks 32/64/96/128-frame tiles by wave count (csrc/subnet.cu: pick_nj); VRVQ_SUBNET_NJ forces each
+    instantiation: all four must agree bit for bit (every output sums its terms in the same order)."""
+    from vrvq_b200 import ops
+
+    rng = np.random.Generator(np.random.PCG64(77))
+    w = (rng.normal(size=(200, 64, 3)) / 14).astype(np.float32)
+    pw = ops.PackedConv3(torch.from_numpy(rng.uniform(0.5, 1.5, 64).astype(np.float32)), torch.from_numpy(w),
+                         torch.from_numpy(rng.normal(size=200).astype(np.float32)), "cuda")
+    x = torch.from_numpy(rng.normal(size=(3, 64, 391)).astype(np.float32)).cuda()
+    outs = []
+    for nj in (1, 2, 3, 4):
+        monkeypatch.setenv("VRVQ_SUBNET_NJ", str(nj))
+        outs.append(ops.snake_conv3(pw, x))
+    monkeypatch.delenv("VRVQ_SUBNET_NJ")
+    ref = ops.snake_conv3(pw, x)
+    assert all(torch.equal(o, ref) for o in outs)
+    o = sp.conv3(sp.snake(x.cpu().numpy().astype(np.float64), pw.alpha.cpu().numpy(), np.float64), w.astype(np.float64),
+                 pw.bias.cpu().numpy().astype(np.float64))
+    assert np.abs(ref.cpu().numpy() - o).max() <= 1e-5 * np.abs(o).max()

@@ -5,14 +5,17 @@
 //
 // Formulation: an implicit GEMM per batch item, M = output channels, N = frames, K = 3*Cin, fp32 on the CUDA cores
 // (first correct version of this row; the two big layers, 1024->1024 and 1024->512, are the tensor-core candidates).
-//   * CTA tile 128 output channels x 128 frames, 256 threads, 8x8 accumulators per thread (8 channels x 4 frame pairs,
-//     so that a 4-value activation window per pair feeds all three taps: 14 shared-memory loads per 192 FMAs);
+//   * CTA tile 128 output channels x 32 NJ frames (NJ = 1..4 picked per launch to fill whole waves), 256 threads,
+//     8 x 2 NJ accumulators per thread (8 channels x NJ frame pairs, so that the 4-value activation window of a pair
+//     feeds all three taps: 14 shared-memory loads per 192 FMAs at NJ = 4);
 //   * K runs in chunks of 8 input channels (24 K-rows): the weight chunk [24][128] comes from the host-packed
-//     [Cin*3][Cout_padded] layout with coalesced 16-byte loads; the activation chunk [8][130] (one halo frame each
+//     [Cin*3][Cout_padded] layout with coalesced 16-byte loads; the activation chunk [8][32 NJ + 2] (one halo frame each
 //     side) is loaded once, passed through Snake, and serves all three taps from shared memory;
 //   * global loads of chunk c+1 are issued before the FMAs of chunk c (register prefetch, two smem buffers,
 //     one barrier per chunk);
 //   * zero padding at the sequence ends is applied after Snake, as the reference's conv does (snake(0) = 0).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vrvq {
@@ -23,10 +26,8 @@ int check_cuda(cudaError_t e, const char *what);
 namespace {
 
 constexpr int SN_TM = 128;  // output channels per CTA (= VRVQ_CONV3_COUT_ALIGN)
-constexpr int SN_TN = 128;  // frames per CTA
 constexpr int SN_KC = 8;    // input channels per chunk
-constexpr int SN_XW = SN_TN + 2;
-constexpr int SN_XLD = 136;  // row stride of the activation chunk in shared memory
+// frames per CTA = 32 NJ (NJ frame pairs per thread), chosen per launch so that the grid fills whole waves (pick_nj)
 static_assert(SN_TM == VRVQ_CONV3_COUT_ALIGN, "packed weight rows are padded to the CTA tile");
 
 __device__ __forceinline__ float snake_f32(float v, float a, float inv_a) {
@@ -34,12 +35,13 @@ __device__ __forceinline__ float snake_f32(float v, float a, float inv_a) {
     return v + inv_a * (s * s);
 }
 
-template <bool SIGMOID>
+template <bool SIGMOID, int NJ>
 __global__ void __launch_bounds__(256, 2)
 snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, const float *__restrict__ alpha,
                    const float *__restrict__ wp, int cout_pad, const float *__restrict__ bias, float *__restrict__ y, long long y_sb,
                    long long y_sc, int Cin, int Cout, int T) {
     __shared__ __align__(16) float Ws[2][SN_KC * 3][SN_TM];
+    constexpr int SN_TN = 32 * NJ, SN_XW = SN_TN + 2, SN_XLD = SN_TN + 8;
     __shared__ __align__(16) float Xs[2][SN_KC][SN_XLD];
 
     const int tid = threadIdx.x;
@@ -49,10 +51,10 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
     const int b = blockIdx.z;
     const float *xb = x + (long long)b * x_sb;
 
-    // loader roles: activations -- channel lci, columns lane + 32 m (m < 4) and 128 + lane (lane < 2);
+    // loader roles: activations -- channel lci, columns lane + 32 m (m < NJ) and 32 NJ + lane (lane < 2);
     //               weights     -- three float4 at flat index tid + 256 m of the [24][128] chunk
     const int lci = tid >> 5, lane = tid & 31;
-    float xr[5];
+    float xr[NJ + 1];
     float4 wr[3];
 
     // global -> registers (raw values: nothing here waits on the loads, so they fly under the FMAs of the current chunk)
@@ -62,7 +64,7 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
         sn_a = __ldg(alpha + ci);
         const float *xrow = xb + (long long)ci * x_sc;
 #pragma unroll
-        for (int m = 0; m < 5; ++m) {
+        for (int m = 0; m < NJ + 1; ++m) {
             const int i = lane + 32 * m;
             const int t = t0 - 1 + i;
             xr[m] = (i < SN_XW && t >= 0 && t < T) ? __ldg(xrow + t) : 0.0f;
@@ -78,7 +80,7 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
     auto store_chunk = [&](int buf) {
         sn_inv = 1.0f / (sn_a + 1e-9f);
 #pragma unroll
-        for (int m = 0; m < 5; ++m) {
+        for (int m = 0; m < NJ + 1; ++m) {
             const int i = lane + 32 * m;
             if (i < SN_XW) Xs[buf][lci][i] = snake_f32(xr[m], sn_a, sn_inv);
         }
@@ -89,11 +91,11 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
         }
     };
 
-    float acc[8][8];
+    float acc[8][2 * NJ];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+        for (int j = 0; j < 2 * NJ; ++j) acc[i][j] = 0.0f;
 
     const int nchunks = Cin / SN_KC;
     load_chunk(0);
@@ -105,9 +107,9 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
 #pragma unroll
         for (int ci = 0; ci < SN_KC; ++ci) {
             // frames 32 j + 2 tx + {0,1}: the four window values per j serve all three taps (two 8-byte loads)
-            float xv[4][4];
+            float xv[NJ][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 const float2 lo = *reinterpret_cast<const float2 *>(&Xs[buf][ci][32 * j + 2 * tx]);
                 const float2 hi = *reinterpret_cast<const float2 *>(&Xs[buf][ci][32 * j + 2 * tx + 2]);
                 xv[j][0] = lo.x, xv[j][1] = lo.y, xv[j][2] = hi.x, xv[j][3] = hi.y;
@@ -120,7 +122,7 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < NJ; ++j) {
                         acc[i][2 * j] = fmaf(a[i], xv[j][k], acc[i][2 * j]);
                         acc[i][2 * j + 1] = fmaf(a[i], xv[j][k + 1], acc[i][2 * j + 1]);
                     }
@@ -138,7 +140,7 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
         const float bi = __ldg(bias + co);
         float *yrow = yb + (long long)co * y_sc;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int t = t0 + 32 * j + 2 * tx + e;
@@ -152,6 +154,22 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
     }
 }
 
+// Frames per CTA (32 nj): the cost of a launch is (number of waves) x (tile time ~ nj); two CTAs are resident per SM.
+// 128-frame tiles at config 2 (B=16, T=862, 1024 output channels) are 896 CTAs = 3.03 waves of 296 -- a fourth, nearly
+// empty wave; 96-frame tiles are 1152 CTAs = 3.89 waves of 3/4 the length.  Ties go to the larger tile (fewer
+// shared-memory loads per FMA).  Results do not depend on the choice: every output sums its terms in the same order.
+int pick_nj(int T, long long ctas_per_frame_tile, long long slots) {
+    int best = 4;
+    long long best_cost = -1;
+    for (int nj = 4; nj >= 1; --nj) {
+        const long long tiles = (T + 32 * nj - 1) / (32 * nj);
+        const long long waves = (tiles * ctas_per_frame_tile + slots - 1) / slots;
+        const long long cost = waves * nj;
+        if (best_cost < 0 || cost < best_cost) best = nj, best_cost = cost;
+    }
+    return best;
+}
+
 }  // namespace
 
 int launch_snake_conv3(const float *x, long long x_sb, long long x_sc, const float *alpha, const float *wp, int cout_pad, const float *bias,
@@ -161,11 +179,34 @@ int launch_snake_conv3(const float *x, long long x_sb, long long x_sc, const flo
         set_error("vrvq_snake_conv3_f32: B must be <= 65535");
         return VRVQ_EUNSUPPORTED;
     }
-    dim3 grid((T + SN_TN - 1) / SN_TN, (Cout + SN_TM - 1) / SN_TM, B);
-    if (sigmoid)
-        snake_conv3_kernel<true><<<grid, 256, 0, st>>>(x, x_sb, x_sc, alpha, wp, cout_pad, bias, y, y_sb, y_sc, Cin, Cout, T);
-    else
-        snake_conv3_kernel<false><<<grid, 256, 0, st>>>(x, x_sb, x_sc, alpha, wp, cout_pad, bias, y, y_sb, y_sc, Cin, Cout, T);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int co_tiles = (Cout + SN_TM - 1) / SN_TM;
+    int nj = pick_nj(T, (long long)co_tiles * B, 2LL * sms);
+    if (const char *e = getenv("VRVQ_SUBNET_NJ")) {  // tests force every instantiation; results are identical by construction
+        const int v = atoi(e);
+        if (v >= 1 && v <= 4) nj = v;
+    }
+    dim3 grid((T + 32 * nj - 1) / (32 * nj), co_tiles, B);
+#define VRVQ_SN_LAUNCH(SG, NJ_) \
+    snake_conv3_kernel<SG, NJ_><<<grid, 256, 0, st>>>(x, x_sb, x_sc, alpha, wp, cout_pad, bias, y, y_sb, y_sc, Cin, Cout, T)
+#define VRVQ_SN_CASE(NJ_)               \
+    case NJ_:                           \
+        if (sigmoid)                    \
+            VRVQ_SN_LAUNCH(true, NJ_);  \
+        else                            \
+            VRVQ_SN_LAUNCH(false, NJ_); \
+        break;
+    switch (nj) {
+        VRVQ_SN_CASE(1)
+        VRVQ_SN_CASE(2)
+        VRVQ_SN_CASE(3)
+        default:
+            VRVQ_SN_CASE(4)
+    }
+#undef VRVQ_SN_CASE
+#undef VRVQ_SN_LAUNCH
     return check_cuda(cudaGetLastError(), "snake_conv3_kernel launch");
 }
 

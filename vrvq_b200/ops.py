@@ -351,11 +351,11 @@ def snake_conv3(w: PackedConv3, x: torch.Tensor, sigmoid: bool = False) -> torch
         raise VrvqError(f"x must be [B, {w.cin}, T], got {tuple(x.shape)}")
     if x.device != w.device:
         raise VrvqError(f"x is on {x.device} but the packed weights are on {w.device}")
-    _check_view(x, "x")
     B, _, T = x.shape
     y = torch.empty((B, w.cout, T), dtype=torch.float32, device=x.device)
     if B * T == 0:
         return y
+    _check_view(x, "x")
     with torch.cuda.device(x.device):
         check(_lib.lib().vrvq_snake_conv3_f32(x.data_ptr(), x.stride(0), x.stride(1), w.alpha.data_ptr(), w.packed.data_ptr(),
                                               w.bias.data_ptr(), B, w.cin, w.cout, T, int(bool(sigmoid)), y.data_ptr(), y.stride(0),
