@@ -73,7 +73,7 @@ def test_frame_range_view_equals_padded_recompute():
 
 def test_config2_size_shards_and_sampled_oracle():
     """B=16 x T=862 (BASELINE.json configs[1]) on the shipped architecture: batch shards are bit-identical to the full call
-    (the subnet shards by batch), results are deterministic, and two items agree with the oracle."""
+    (the subnet shards by batch), results are deterministic, and two items agree with the exact value."""
     c = dict(gi.SUBNET_CASES["subnet_d1024"], B=16, T=862)
     sd, x = case_inputs(c)
     m = build(c, sd)
@@ -83,7 +83,8 @@ def test_config2_size_shards_and_sampled_oracle():
     for world in (2, 8):
         parts = [m(p.contiguous()) for p in xd.chunk(world, dim=0)]
         assert torch.equal(torch.cat(parts, 0), y)
-    o = sp.importance_subnet(sd, x[[0, 15]], dtype=np.float32)
+    # against the binary64 evaluation: two fp32 evaluations (kernel and fp32 oracle) each carry ~2e-6 of their own
+    o = sp.importance_subnet(sd, x[[0, 15]], dtype=np.float64)
     assert np.abs(y[[0, 15]].cpu().numpy() - o).max() <= IMP_ATOL
     assert float(y.min()) > 0.0 and float(y.max()) < 1.0
 
