@@ -154,17 +154,19 @@ snake_conv3_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, 
     }
 }
 
-// Frames per CTA (32 nj): the cost of a launch is (number of waves) x (tile time ~ nj); two CTAs are resident per SM.
-// 128-frame tiles at config 2 (B=16, T=862, 1024 output channels) are 896 CTAs = 3.03 waves of 296 -- a fourth, nearly
-// empty wave; 96-frame tiles are 1152 CTAs = 3.89 waves of 3/4 the length.  Ties go to the larger tile (fewer
-// shared-memory loads per FMA).  Results do not depend on the choice: every output sums its terms in the same order.
-int pick_nj(int T, long long ctas_per_frame_tile, long long slots) {
+// Frames per CTA (32 nj), picked per launch from a cost model fitted to the config-2 sweep (profiles/r1q_subnet_tile_sweep.txt):
+//   time ~ f(CTAs on the busiest SM) x (nj + 1/2)
+// nj + 1/2: FMAs scale with nj, the weight loads of a tile do not; f(n) = 1.6 (n / 2) + (n % 2): two CTAs are resident per SM
+// and share its FMA pipes (a pair takes 1.6x a lone CTA).  128-frame tiles at config 2 (B=16, T=862, 1024 output channels) are
+// 896 CTAs -> 7 on the busiest SM; 96-frame tiles are 1152 -> 8, each 3/4 the length.  Ties go to the larger tile.  Results do
+// not depend on the choice: every output sums its terms in the same order.
+int pick_nj(int T, long long ctas_per_frame_tile, long long sms) {
     int best = 4;
     long long best_cost = -1;
     for (int nj = 4; nj >= 1; --nj) {
         const long long tiles = (T + 32 * nj - 1) / (32 * nj);
-        const long long waves = (tiles * ctas_per_frame_tile + slots - 1) / slots;
-        const long long cost = waves * nj;
+        const long long per_sm = (tiles * ctas_per_frame_tile + sms - 1) / sms;
+        const long long cost = (16 * (per_sm / 2) + 10 * (per_sm % 2)) * (2 * nj + 1);
         if (best_cost < 0 || cost < best_cost) best = nj, best_cost = cost;
     }
     return best;
@@ -183,7 +185,7 @@ int launch_snake_conv3(const float *x, long long x_sb, long long x_sc, const flo
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int co_tiles = (Cout + SN_TM - 1) / SN_TM;
-    int nj = pick_nj(T, (long long)co_tiles * B, 2LL * sms);
+    int nj = pick_nj(T, (long long)co_tiles * B, sms);
     if (const char *e = getenv("VRVQ_SUBNET_NJ")) {  // tests force every instantiation; results are identical by construction
         const int v = atoi(e);
         if (v >= 1 && v <= 4) nj = v;
