@@ -74,8 +74,8 @@ int vrvq_blob_codebook(const void *blob_host, size_t blob_bytes, int stage, floa
  *   VectorQuantize.forward / decode_latents    models/quantize.py:42-103
  *   generate_mask_ste (forward value) / generate_mask_hard    models/utils.py:45-61
  *   the numerator of cal_bpf_from_mask         models/utils.py:64-73
- * The importance map is an INPUT (the ImportanceSubnet, models/importance_subnet.py, is an upstream
- * producer and stays in PyTorch).
+ * The importance map is an INPUT of this call; its producer (ImportanceSubnet, models/importance_subnet.py) has
+ * its own entry point below, vrvq_snake_conv3_f32 (one fused Snake + k=3 conv block per launch).
  * ------------------------------------------------------------------------------------------- */
 typedef struct vrvq_encode_args {
     uint32_t struct_size; /* = sizeof(vrvq_encode_args); lets the ABI grow */
@@ -141,7 +141,7 @@ typedef struct vrvq_from_codes_args {
     int64_t z_p_stride_b, z_p_stride_c;
     float *z_q_is; /* [B][n_run][D][T] or NULL */
     int64_t z_q_is_stride_b, z_q_is_stride_q, z_q_is_stride_d;
-    int32_t *error_flag; /* optional device int: set to 1 if any code is outside [0, K) */
+    int32_t *error_flag; /* optional device int (caller-zeroed): bit 0 is OR-ed in if any code is outside [0, K) */
 } vrvq_from_codes_args;
 
 int vrvq_from_codes_f32(const vrvq_from_codes_args *args, void *stream);

@@ -106,3 +106,50 @@ SUBNET_CASES = {
     "subnet_small_t1": dict(seed=33, d_input=64, d_feat=48, widths=(32, 16, 8, 8), B=2, T=1, sigma=1.5),
     "subnet_small_t3": dict(seed=34, d_input=64, d_feat=48, widths=(32, 16, 8, 8), B=1, T=3, sigma=1.5),
 }
+
+
+def make_dac_state_dict(seed: int, shapes, imp_gain: float = 6.0, w_scale: float = 1.5):
+    """Seeded parameters for a whole (decoder-less) DAC_VRVQ: `shapes` is the ordered {key: shape} of the model's own
+    state dict (the reference's and the mirror's key lists are identical, tests/test_oracle_vs_reference.py), so the
+    22 M encoder weights never have to be stored.  weight_v ~ U(-1,1) * sqrt(w_scale / fan_in),
+    weight_g = ||v|| * U(0.8, 1.2), biases N(0, 0.02), Snake alpha U(0.5, 1.5), codebooks N(0, 1); the last conv of the
+    importance subnet gets `imp_gain` x larger g so that the map spreads over (0, 1) instead of hugging 0.5."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f32 = np.float32
+    sd = {}
+    last_v = None
+    for key, shape in shapes.items():
+        shape = tuple(shape)
+        if key.endswith("weight_v"):
+            fan_in = int(np.prod(shape[1:]))
+            last_v = (rng.uniform(-1.0, 1.0, shape) * np.sqrt(w_scale / fan_in)).astype(f32)
+            sd[key] = last_v
+        elif key.endswith("alpha"):
+            sd[key] = rng.uniform(0.5, 1.5, shape).astype(f32)
+        elif key.endswith("bias"):
+            sd[key] = rng.normal(0.0, 0.02, shape).astype(f32)
+        elif key.endswith("codebook.weight"):
+            sd[key] = rng.normal(0.0, 1.0, shape).astype(f32)
+        elif key.endswith("weight_g"):
+            sd[key] = None  # filled below (the reference orders g before v)
+        else:
+            raise KeyError(f"unexpected parameter {key}")
+    for key in list(sd):
+        if key.endswith("weight_g"):
+            v = sd[key[:-1] + "v"].astype(np.float64)
+            nrm = np.sqrt((v ** 2).sum(axis=tuple(range(1, v.ndim)), keepdims=True))
+            gain = imp_gain if key == "quantizer.imp_subnet.blocks.4.1.weight_g" else 1.0
+            sd[key] = (nrm * gain * rng.uniform(0.8, 1.2, nrm.shape)).astype(f32)
+    return sd
+
+
+def make_audio(seed: int, B: int, samples: int, scale: float = 0.5):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return (rng.normal(0.0, scale, (B, 1, samples))).astype(np.float32)
+
+
+# DAC_VRVQ.encode fixtures (models/dac_vrvq.py:176-213): BASELINE.json configs[0] -- 1 s of 44.1 kHz mono, level 1 -- and a CBR model
+DAC_CASES = {
+    "dac_vbr_1s": dict(seed=41, model_type="VBR", n_codebooks=8, B=1, samples=44100, level=1.0, n_quantizers=None),
+    "dac_cbr_1s": dict(seed=42, model_type="CBR", n_codebooks=8, B=2, samples=22050, level=None, n_quantizers=5),
+}

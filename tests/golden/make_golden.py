@@ -128,14 +128,53 @@ def subnet_cases():
         print(f"{name}: wrote {path}, imp_map in [{imp.min():.3f}, {imp.max():.3f}]")
 
 
+def dac_model_kwargs(c):
+    kw = dict(n_codebooks=c["n_codebooks"], model_type=c["model_type"])
+    if c["model_type"] == "VBR":
+        kw.update(level_min=0.125, level_max=6.0, imp2mask_alpha=2.0)
+    return kw
+
+
+def dac_cases(ref):
+    """DAC_VRVQ.encode(audio, n_quantizers, level) of the UNMODIFIED reference (models/dac_vrvq.py:176-213) on seeded weights
+    and audio: the API BASELINE.json's north_star names.  Stored: codes, mask, imp_map, latents, losses in full; z (the
+    encoder output the quantizer saw), feat and z_q for every 16th channel."""
+    torch.set_num_threads(8)
+    for name, c in gi.DAC_CASES.items():
+        m = ref.DAC_VRVQ(**dac_model_kwargs(c)).eval()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith("decoder.")}
+        full = dict(m.state_dict())
+        full.update(gi.torch_state_dict(gi.make_dac_state_dict(c["seed"], shapes)))
+        m.load_state_dict(full, strict=True)
+        x = torch.from_numpy(gi.make_audio(c["seed"] + 1, c["B"], c["samples"]))
+        with torch.no_grad():
+            xp = m.preprocess(x, 44100)
+            z, feat = m.encoder(xp, return_feat=True)
+            r = m.encode(xp, c["n_quantizers"], c["level"]) if c["model_type"] == "VBR" else m.encode(xp, c["n_quantizers"])
+        out = {"codes": r["codes"].numpy(), "latents": r["latents"].numpy(), "z_sub": z[:, ::ROW_STEP].contiguous().numpy(),
+               "feat_sub": feat[:, ::ROW_STEP].contiguous().numpy(), "z_q_sub": r["z_q"][:, ::ROW_STEP].contiguous().numpy(),
+               "commitment_loss": np.float32(r["commitment_loss"].item()), "codebook_loss": np.float32(r["codebook_loss"].item()),
+               "key_order": np.array(list(shapes.keys()))}
+        if c["model_type"] == "VBR":
+            out["imp_map"] = r["imp_map"].numpy()
+            out["mask_imp"] = r["mask_imp"].numpy()
+            out["bpf"] = np.float64(ref.cal_bpf_from_mask(r["mask_imp"], [10] * c["n_codebooks"]))
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {path} ({os.path.getsize(path)/1e6:.2f} MB), T={z.shape[-1]}, z std {z.std():.3f}")
+
+
 def main():
     ref = ref_import.load()
     if "--subnet-only" in sys.argv:
         return subnet_cases()
+    if "--dac-only" in sys.argv:
+        return dac_cases(ref)
     for name, case in gi.CASES.items():
         run_case(ref, name, case)
     mask_cases(ref)
     subnet_cases()
+    dac_cases(ref)
 
 
 if __name__ == "__main__":

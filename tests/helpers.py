@@ -13,7 +13,13 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # tensor (an element-wise relative test is meaningless for values that cancel to ~0; the
 # reference itself is not bit-stable across batch shapes, SURVEY.md section 7 hard part 4).
 ZQ_RTOL = 1e-5
-NEAR_TIE_EPS = 1e-5  # distance-gap below which a differing code is an audited near-tie
+# Distance gap below which a differing code is an audited near-tie.  The oracle's z_e is a binary64 dot product rounded
+# once (<= 6e-8 relative); the kernels' z_e carries up to 1.3e-6 relative error (3xTF32 GEMM, profiles/r1_micro_tc3x.txt;
+# an fp32 FMA chain: 4e-6), which moves a cosine distance 2 - 2 e.c by at most ~2.6e-6.  A flip with a larger gap is a bug.
+NEAR_TIE_EPS = 3e-6
+# Excused near-tie frames allowed per comparison: every GPU run so far printed 0 (profiles/r2_gpu_tests_tail.txt); the bound
+# is one frame or 1e-4 of the frames, whichever is larger.
+MAX_EXCUSED_FRAC = 1e-4
 
 
 def load_golden(name):
@@ -55,7 +61,7 @@ def assert_close_frames(a, ref, rtol=ZQ_RTOL, skip=None, what="tensor"):
     return worst
 
 
-def assert_codes_match(w, oracle_out, codes_other, max_excused_frac=2e-3, what="codes"):
+def assert_codes_match(w, oracle_out, codes_other, max_excused_frac=MAX_EXCUSED_FRAC, what="codes"):
     """Exact match, except frames whose first differing stage is an audited near-tie."""
     bad, excused, excused_mask = c_oracle.audit_code_mismatches(w, oracle_out, codes_other, eps=NEAR_TIE_EPS)
     nframes = max(excused_mask.size, 1)

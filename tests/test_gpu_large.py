@@ -14,8 +14,8 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
-def test_config3_nq28_against_oracle_subset():
-    """conf/base_24kbps.yml: Nq=28; B=64 x T=862 on the GPU, 4 items re-checked against the oracle."""
+def test_config3_nq28_against_oracle_every_item():
+    """conf/base_24kbps.yml: Nq=28; B=64 x T=862 on the GPU, every item audited against the (OpenMP) oracle."""
     from vrvq_b200 import ops
 
     sd = gi.torch_state_dict(gi.make_state_dict(71, 28, 1024))
@@ -24,9 +24,9 @@ def test_config3_nq28_against_oracle_subset():
     B, T = 64, 862
     z = torch.randn(B, 1024, T, generator=torch.Generator().manual_seed(72)).cuda()
     out = ops.rvq_encode(pw, z, None, None, None, want_z_q_is=False)
-    idx = [0, 17, 40, 63]
+    idx = list(range(B))
     o = c_oracle.encode(w, npy(z[idx]), None, want_z_q_is=False)
-    excused, skip = H.assert_codes_match(w, o, npy(out.codes[idx]), max_excused_frac=5e-3)
+    excused, skip = H.assert_codes_match(w, o, npy(out.codes[idx]))
     H.assert_close_frames(npy(out.z_q[idx]), o["z_q"], skip=skip, what="z_q")
     assert int(out.kept.sum().item()) == 28 * B * T and bool((out.mask == 1).all())
     # decode side round trip: from_codes(codes) reproduces z_q up to the straight-through rounding (quantize.py:73-75)
@@ -65,13 +65,16 @@ def test_config4_long_form_shard_properties():
             assert torch.equal(part.codes[sl], full.codes[sl]) and torch.equal(part.z_q[sl], full.z_q[sl])
         kept += part.kept
     assert torch.equal(kept, full.kept)
-    # (4) oracle spot check on two frame windows
+    # (4) every frame of every item against the oracle (41 k frames x 8 stages: seconds with OpenMP)
     w = c_oracle.OracleWeights.from_state_dict(sd)
-    for b, t0 in ((0, 0), (7, 5100)):
-        o = c_oracle.encode(w, npy(z[b:b + 1, :, t0:t0 + 68]), None, npy(imp[b:b + 1, :, t0:t0 + 68]), 0.7, want_z_q_is=False)
-        excused, skip = H.assert_codes_match(w, o, npy(full.codes[b:b + 1, :, t0:t0 + 68]), max_excused_frac=0.03)
-        assert np.array_equal(npy(full.mask[b:b + 1, :, t0:t0 + 68]), o["mask"])
-        H.assert_close_frames(npy(full.z_q[b:b + 1, :, t0:t0 + 68]), o["z_q"], skip=skip, what="z_q window")
+    total = 0
+    for b in range(B):
+        o = c_oracle.encode(w, npy(z[b:b + 1]), None, npy(imp[b:b + 1]), 0.7, want_z_q_is=False)
+        excused, skip = H.assert_codes_match(w, o, npy(full.codes[b:b + 1]))
+        total += excused
+        assert np.array_equal(npy(full.mask[b:b + 1]), o["mask"])
+        H.assert_close_frames(npy(full.z_q[b:b + 1]), o["z_q"], skip=skip, what=f"z_q item {b}")
+    print(f"config-4 shape: {total} audited near-tie frames of {B * T}")
 
 
 def test_remask_level_sweep_matches_fused_encode():

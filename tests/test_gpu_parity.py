@@ -37,6 +37,24 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
+@pytest.fixture(params=["cuda", "tc"])
+def impl(request, monkeypatch):
+    """Run a test once per fused encode kernel: `cuda` = rvq_encode_kernel (CUDA cores), `tc` = rvq_encode_tc_kernel
+    (tcgen05, the production kernel for every call larger than one wave).  The fixtures are small, so without the override
+    the size heuristic would send all of them to the CUDA-core kernel."""
+    monkeypatch.setenv("VRVQ_ENCODE_IMPL", request.param)
+    return request.param
+
+
+def assert_kernel(impl, m_or_pw, B, T, n_run):
+    """The kernel that actually serves the call is the one the test is named after."""
+    from vrvq_b200 import ops
+
+    pw = m_or_pw if isinstance(m_or_pw, ops.PackedWeights) else m_or_pw.packed_weights(torch.device("cuda", torch.cuda.current_device()))
+    info = ops.encode_launch_info(pw, B, T, n_run, "cuda")
+    assert info["block"] == (480 if impl == "tc" else 512), (impl, info)
+
+
 def test_extension_is_loaded():
     """The driver records which .so the test process loaded; make sure it is ours and that nothing falls back."""
     from vrvq_b200 import _lib
@@ -47,11 +65,12 @@ def test_extension_is_loaded():
 
 
 @pytest.mark.parametrize("name", VBR)
-def test_vbr_against_reference_fixture(name):
+def test_vbr_against_reference_fixture(name, impl):
     import vrvq_b200
 
     case, g = gi.CASES[name], H.load_golden(name)
     m = build_module(case)
+    assert_kernel(impl, m, case["B"], case["T"], case["Nq"])
     w = H.oracle_weights_for(case)
     z_np = H.latents_for(case)
     z = torch.from_numpy(z_np).cuda()
@@ -83,9 +102,10 @@ def test_vbr_against_reference_fixture(name):
 
 
 @pytest.mark.parametrize("name", CBR)
-def test_cbr_against_reference_fixture(name):
+def test_cbr_against_reference_fixture(name, impl):
     case, g = gi.CASES[name], H.load_golden(name)
     m = build_module(case)
+    assert_kernel(impl, m, case["B"], case["T"], case["Nq"])
     w = H.oracle_weights_for(case)
     z_np = H.latents_for(case)
     z = torch.from_numpy(z_np).cuda()
@@ -106,7 +126,7 @@ def test_cbr_against_reference_fixture(name):
             B, T = case["B"], case["T"]
             H.assert_close_frames(npy(zqis)[:, :, ::16, :].reshape(B, -1, T), g["from_codes_z_q_is_sub"].reshape(B, -1, T), what="from_codes z_q_is")
             ozq, _, _ = c_oracle.from_codes(w, g[f"codes_{qi}"])
-            if case["Nq"] > 8:  # CUDA-core decode kernel: the oracle's fp32 op order, bit for bit
+            if case["Nq"] > 8 or impl == "cuda":  # CUDA-core decode kernel: the oracle's fp32 op order, bit for bit
                 assert np.array_equal(npy(zq), ozq), "from_codes (CUDA cores) is bit-exact vs the oracle"
             else:  # tensor-core decode path: same gather, 3xTF32 GEMM accumulation
                 H.assert_close_frames(npy(zq), ozq, rtol=5e-6, what="from_codes (tensor cores) vs the oracle")
@@ -278,7 +298,7 @@ def test_other_input_dims_and_stage_counts_against_oracle(D, Nq):
     lv = torch.tensor([0.4, 1.3], device="cuda")
     o = c_oracle.encode(w, z_np, None, imp_np, np.array([0.4, 1.3], np.float32))
     out = ops.rvq_encode(pw, torch.from_numpy(z_np).cuda(), None, torch.from_numpy(imp_np).cuda(), lv, want_z_q_is=True)
-    excused, skip = H.assert_codes_match(w, o, npy(out.codes), max_excused_frac=0.02)
+    excused, skip = H.assert_codes_match(w, o, npy(out.codes))
     assert np.array_equal(npy(out.mask), o["mask"]) and np.array_equal(npy(out.kept), o["kept"])
     H.assert_close_frames(npy(out.z_q), o["z_q"], skip=skip, what="z_q")
     H.assert_close_frames(npy(out.z_q_is).reshape(B, -1, T), o["z_q_is"].reshape(B, -1, T), skip=skip, what="z_q_is")
@@ -317,3 +337,74 @@ def test_padded_z_q_is_rows_extension_gives_identical_values():
     assert b["z_q_is"].shape == a["z_q_is"].shape and b["z_q_is"].stride(2) % 32 == 0 and not b["z_q_is"].is_contiguous()
     for k in ("z_q", "z_q_is", "codes", "latents", "mask_imp"):
         assert torch.equal(a[k], b[k]), k
+
+
+def test_two_devices_in_one_process():
+    """the opt-in shared-memory limit is a per-device attribute; a process that drives two GPUs must get it on both
+    (the Python API selects the device per call).  Skipped on a one-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(61, 8, 1024))
+    z_np = gi.make_latents(62, 20, 1024, 300, 1.0)  # large enough for the tensor-core kernel (222 KB of dynamic shared memory)
+    imp_np = gi.make_imp_map(63, 20, 300)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        pw = ops.PackedWeights.from_state_dict(sd, dev)
+        for impl in ("tc", "cuda"):
+            import os
+            os.environ["VRVQ_ENCODE_IMPL"] = impl
+            try:
+                o = ops.rvq_encode(pw, torch.from_numpy(z_np).to(dev), None, torch.from_numpy(imp_np).to(dev), 0.5, want_z_q_is=True)
+                zq, _, _ = ops.from_codes(pw, o.codes)
+            finally:
+                os.environ.pop("VRVQ_ENCODE_IMPL", None)
+            torch.cuda.synchronize(dev)
+            outs.append((impl, o.codes.cpu(), o.z_q.cpu(), zq.cpu()))
+    for a, b in ((outs[0], outs[2]), (outs[1], outs[3])):
+        assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]), f"{a[0]}: device 1 differs from device 0"
+
+
+def test_packed_weight_cache_invalidation():
+    """load_state_dict / .to() / in-place optimiser-style updates repack; `.data` surgery needs invalidate_packed()."""
+    case = gi.CASES["cbr_t3"]
+    m = build_module(case)
+    z = torch.from_numpy(H.latents_for(case)).cuda()
+    a = m(z)["z_q"].clone()
+    with torch.no_grad():
+        m.quantizers[3].codebook.weight.mul_(1.5)  # bumps _version of a MIDDLE stage
+    b = m(z)["z_q"].clone()
+    assert not torch.equal(a, b), "an in-place update of a middle stage must repack"
+    m.quantizers[3].codebook.weight.data.mul_(1.0 / 1.5)  # .data: invisible to the version counter ...
+    m.invalidate_packed()  # ... hence the explicit hook
+    c = m(z)["z_q"]
+    assert torch.allclose(a, c, rtol=1e-4, atol=1e-5) and not torch.equal(b, c)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["quantizers.5.out_proj.bias"] += 1.0
+    m.load_state_dict(sd)
+    d = m(z)["z_q"]
+    assert not torch.equal(c, d), "load_state_dict must repack"
+
+
+def test_level_tensor_shapes_follow_the_reference_broadcast():
+    """quantize.py:389: `imp_map [B,1,T] * level`: [B,1,1] is per item, [1,1,T] per frame; a shape-[B] level with B != T is a
+    broadcast error in the reference and must not be silently taken as per-item levels."""
+    from vrvq_b200 import ops
+
+    case = gi.CASES["vbr_tensor_level"]  # B=3, T=21
+    m = build_module(case)
+    B, T, Nq = case["B"], case["T"], case["Nq"]
+    z = torch.from_numpy(H.latents_for(case)).cuda()
+    imp = torch.from_numpy(gi.make_imp_map(case["imp_seed"], B, T)).cuda()
+    per_frame = torch.linspace(0.2, 2.0, T, device="cuda").view(1, 1, T)
+    r = m(z, level=per_frame, imp_map=imp)
+    assert torch.equal(r["mask_imp"], ops.generate_mask_hard(imp * per_frame * Nq, Nq))
+    per_item = torch.tensor([0.3, 1.0, 2.5], device="cuda")
+    r3 = m(z, level=per_item.view(B, 1, 1), imp_map=imp)
+    assert torch.equal(r3["mask_imp"], ops.generate_mask_hard(imp * per_item.view(B, 1, 1) * Nq, Nq))
+    with pytest.raises(RuntimeError):
+        m(z, level=per_item, imp_map=imp)  # [3] against [3,1,21]: the reference's broadcast fails
+    sq = torch.linspace(0.5, 1.5, T, device="cuda")  # shape [T]: broadcasts along frames, like the reference
+    r1 = m(z, level=sq, imp_map=imp)
+    assert torch.equal(r1["mask_imp"], ops.generate_mask_hard(imp * sq * Nq, Nq))

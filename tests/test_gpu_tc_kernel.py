@@ -78,14 +78,15 @@ def test_tc_matches_cuda_core_kernel_and_oracle(D, Nq, B, T, n_run, vbr):
     a = run_impl("tc", call)
     c = run_impl("cuda", call)
     o = c_oracle.encode(w, z_np, n_run if not vbr else None, imp_np, level, want_z_q_is=True)
-    excused, skip = H.assert_codes_match(w, o, npy(a.codes), max_excused_frac=0.02)
+    excused, skip = H.assert_codes_match(w, o, npy(a.codes))
     assert np.array_equal(npy(a.mask), npy(c.mask)) and np.array_equal(npy(a.mask), o["mask"])
     assert np.array_equal(npy(a.kept), o["kept"])
     H.assert_close_frames(npy(a.z_q), o["z_q"], skip=skip, what="z_q vs oracle")
     H.assert_close_frames(npy(a.latents), o["latents"], skip=skip, what="latents vs oracle")
     H.assert_close_frames(npy(a.z_q_is).reshape(B, -1, T), o["z_q_is"].reshape(B, -1, T), skip=skip, what="z_q_is vs oracle")
     same = (npy(a.codes) == npy(c.codes)).all(axis=1)  # frames on which the two kernels agree on every stage
-    assert same.mean() >= 0.98
+    # both kernels round z_e differently, so they may part at an fp32 near-tie; every run so far: 0 frames
+    assert (~same).sum() <= max(1, int(1e-3 * same.size)), f"tensor-core and CUDA-core kernels disagree on {(~same).sum()} of {same.size} frames"
     sk = ~same
     H.assert_close_frames(npy(a.z_q), npy(c.z_q), skip=sk, what="z_q: tensor-core vs CUDA-core kernel")
     H.assert_close_frames(npy(a.z_q_is).reshape(B, -1, T), npy(c.z_q_is).reshape(B, -1, T), skip=sk, what="z_q_is: tc vs cuda-core")

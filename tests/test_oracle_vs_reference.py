@@ -104,3 +104,48 @@ def test_dac_file_interoperates_with_the_reference_container(ref, tmp_path):
     theirs = ref.DACFile.load(p_ours)
     assert torch.equal(theirs.codes, codes) and theirs.chunk_length == 60 and theirs.sample_rate == 44100
     assert open(p_ref, "rb").read() == open(p_ours, "rb").read(), "CBR files are byte-identical to the reference's"
+
+
+class _FixedImportance(torch.nn.Module):
+    """Stands in for the importance subnet (an upstream producer of the path) so that every mask edge is exercised."""
+
+    def __init__(self, imp):
+        super().__init__()
+        self.imp = imp
+
+    def forward(self, feat):
+        return self.imp
+
+
+@pytest.mark.parametrize("B", [4, 16])
+def test_torch_port_is_bit_identical_to_the_live_reference(ref, B):
+    """oracle/torch_port.py is what bench.py's `cpu_baseline` leg and `--impl reference` arm time when the reference checkout
+    is absent (the GPU box): it must be the reference's computation, bit for bit, at the bench's own shapes
+    (B in {4, 16} x T = 862, D = 1024, Nq = 8; VBR with the level sweep of configs[1], and CBR with early exit)."""
+    from oracle import torch_port
+
+    torch.set_num_threads(8)
+    T, D, Nq = 862, 1024, 8
+    sd = gi.torch_state_dict(gi.make_state_dict(0, Nq, D, 1024))  # the bench's weights (bench.py: make_state)
+    z = torch.randn(B, D, T, generator=torch.Generator().manual_seed(1234))
+    imp = torch.rand(B, 1, T, generator=torch.Generator().manual_seed(4321))
+    w = torch_port.TorchPortWeights(sd)
+    vbr = ref.VBRResidualVectorQuantize(input_dim=D, n_codebooks=Nq, codebook_size=1024, codebook_dim=8, level_min=0.125, level_max=6.0,
+                                        imp2mask_alpha=2.0).eval()
+    missing, unexpected = vbr.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("imp_subnet.") for k in missing)
+    vbr.imp_subnet = _FixedImportance(imp)
+    for level in (0.25, 1.0):
+        with torch.no_grad():
+            r = vbr(z, n_quantizers=None, feat_enc=z, level=level)
+        p = torch_port.rvq_forward(w, z, None, imp, level)
+        for k in ("codes", "z_q", "z_q_is", "latents", "mask_imp", "commitment_loss", "codebook_loss"):
+            assert torch.equal(p[k], r[k]), f"VBR level {level}: {k} differs from the reference"
+    cbr = ref.ResidualVectorQuantize(input_dim=D, n_codebooks=Nq, codebook_size=1024, codebook_dim=8).eval()
+    cbr.load_state_dict(sd, strict=True)
+    for nq in (None, 3):
+        with torch.no_grad():
+            r = cbr(z, n_quantizers=nq)
+        p = torch_port.rvq_forward(w, z, nq)
+        for k in ("codes", "z_q", "latents", "commitment_loss", "codebook_loss"):
+            assert torch.equal(p[k], r[k]), f"CBR n_quantizers={nq}: {k} differs from the reference"

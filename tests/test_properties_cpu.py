@@ -1,6 +1,7 @@
 """CPU property tests (hypothesis) of the oracle and the host logic: per-frame independence, mask monotonicity,
 CBR prefix property, shard plans."""
 import numpy as np
+import pytest
 from hypothesis import given, settings, strategies as st
 
 from oracle import c_oracle
@@ -66,3 +67,32 @@ def test_shard_plans_cover_exactly_once(B, T, world):
     assert (seen == 1).all()
     units = [sharding.merge_whole_items(segs, T) for segs in plan]
     assert sum((u[2] - u[1]) * T if u[0] == "items" else u[3] - u[2] for us in units for u in us) == B * T
+
+
+def test_dac_encoder_mirror_reproduces_the_reference_fixture_on_cpu():
+    """The mirror's conv encoder (vrvq_b200/layers.py, upstream of the kernels) on the CPU against the latent / feature tap the
+    unmodified reference produced for the DAC_VRVQ.encode fixtures (tests/golden/dac_*.npz): same ATen ops, bit for bit."""
+    import numpy as np
+    import torch
+
+    import vrvq_b200
+    from tests import helpers as H
+    from tests.golden import gen_inputs as gi
+
+    torch.set_num_threads(8)
+    for name, c in gi.DAC_CASES.items():
+        g = H.load_golden(name)
+        kw = dict(n_codebooks=c["n_codebooks"], model_type=c["model_type"])
+        if c["model_type"] == "VBR":
+            kw.update(level_min=0.125, level_max=6.0, imp2mask_alpha=2.0)
+        m = vrvq_b200.DAC_VRVQ(**kw).eval()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert list(shapes) == [str(k) for k in g["key_order"]]
+        m.load_state_dict(gi.torch_state_dict(gi.make_dac_state_dict(c["seed"], shapes)), strict=True)
+        x = torch.from_numpy(gi.make_audio(c["seed"] + 1, c["B"], c["samples"]))
+        with torch.no_grad():
+            z, feat = m.encoder(m.preprocess(x, 44100), return_feat=True)
+        H.assert_close_frames(z[:, ::16].numpy(), g["z_sub"], rtol=1e-6, what="encoder z")
+        H.assert_close_frames(feat[:, ::16].numpy(), g["feat_sub"], rtol=1e-6, what="encoder feature tap")
+        with pytest.raises(vrvq_b200.VrvqError):  # the quantizer itself has no CPU path
+            m.encode(m.preprocess(x, 44100), c["n_quantizers"], c["level"] if c["level"] is not None else 1)

@@ -224,4 +224,30 @@ void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 int check_device();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is set per (kernel, device): remember it per device ordinal, so that the first
+// launch on a second GPU of the same process raises the limit there too.  One table per kernel instantiation (`auto` template
+// parameter = the kernel's address); the race between host threads is benign (the attribute is idempotent).
+template <auto Kernel>
+int ensure_dynamic_smem(int bytes, const char *what) {
+    static int granted[64];
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && granted[dev] >= bytes) return 0;
+    rc = check_cuda(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), what);
+    if (rc) return rc;
+    if (tracked) granted[dev] = bytes;
+    return 0;
+}
+// number of SMs of the current device (queried per call: a process may drive several devices)
+inline int current_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 }  // namespace vrvq

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(FC_NT) from_codes_kernel(const FromCodesParams
     for (int s = w; s < p.n_run; s += FC_NT / 32) {
         long long idx = valid ? p.codes[(long long)b * p.c_sb + (long long)s * p.c_sq + t] : 0;
         if (idx < 0 || idx >= p.K) {
-            if (p.error_flag) atomicExch(p.error_flag, 1);
+            if (p.error_flag) atomicOr(p.error_flag, 1);
             idx = 0;
         }
         const float *raw = stages + (size_t)s * p.stage_floats + p.off_raw + (size_t)idx * CD;
@@ -436,12 +436,9 @@ int launch_from_codes(const vrvq_from_codes_args *a, cudaStream_t st) {
     }
     const int gy = (a->input_dim + FC_DCH - 1) / FC_DCH;
     const int smem = (int)sizeof(float) * (a->n_run * (CD * 32 + 32) + FC_SG * FC_DCH * (CD + 1));
-    static int smem_allowed = 48 * 1024;
-    if (smem > smem_allowed) {
-        int rc = check_cuda(cudaFuncSetAttribute(from_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024),
-                            "cudaFuncSetAttribute(from_codes_kernel)");
+    if (smem > 48 * 1024) {
+        int rc = ensure_dynamic_smem<from_codes_kernel>(96 * 1024, "cudaFuncSetAttribute(from_codes_kernel)");
         if (rc) return rc;
-        smem_allowed = 96 * 1024;
     }
     from_codes_kernel<<<dim3((unsigned)tiles, gy), FC_NT, smem, st>>>(p);
     return check_cuda(cudaGetLastError(), "from_codes_kernel launch");

@@ -617,13 +617,8 @@ __global__ void __launch_bounds__(NT, 1) rvq_encode_kernel(const EncodeParams p)
 template <int D, int K, int VEC_ST, bool ZQIS>
 static int launch_one(const EncodeParams &p, int grid, cudaStream_t stream) {
     using S = EncodeSmem<D, K>;
-    static bool attr_done = false;  // benign race: the attribute is idempotent
-    if (!attr_done) {
-        int rc = check_cuda(cudaFuncSetAttribute(rvq_encode_kernel<D, K, VEC_ST, ZQIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES),
-                            "cudaFuncSetAttribute(rvq_encode_kernel)");
-        if (rc) return rc;
-        attr_done = true;
-    }
+    int rc = ensure_dynamic_smem<rvq_encode_kernel<D, K, VEC_ST, ZQIS>>(S::BYTES, "cudaFuncSetAttribute(rvq_encode_kernel)");
+    if (rc) return rc;
     rvq_encode_kernel<D, K, VEC_ST, ZQIS><<<grid, NT, S::BYTES, stream>>>(p);
     return check_cuda(cudaGetLastError(), "rvq_encode_kernel launch");
 }
@@ -725,12 +720,8 @@ static int pick_grid(const EncodeParams &p, int *grid) {
 // (B * ceil(T / 32) <= #SMs, e.g. a single 1 s .. 60 s clip) stay on the CUDA-core kernel, everything larger goes to the tensor
 // cores.  VRVQ_ENCODE_IMPL=cuda / =tc force one or the other (A/B comparisons, tests).
 bool prefer_tc_for_size(int B, int T) {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
-        else { cudaGetLastError(); return true; }
-    }
+    const int sms = current_sm_count();  // of the current device, per call
+    if (sms == 0) return true;
     const char *impl = getenv("VRVQ_ENCODE_IMPL");
     if (impl != nullptr && impl[0] == 't') return true;
     return (long long)B * ((T + 31) / 32) > sms;

@@ -82,18 +82,33 @@ constexpr uint32_t TM_RUN = 0, TM_SET = 64, TM_SCORE = 320;  // search scores: 3
 constexpr uint32_t TM_AL = 320;  // phase L: A-operand ring, 3 slots x (32 columns heads | 32 columns remainders) of one 32-channel chunk
 constexpr float SEARCH_MARGIN = 0.012f;  // > 2 x the TF32 score error bound 2^-9 * sum|2 e_k c_k| <= 2^-8 (unit vectors)
 
-// Every wait in this kernel is bounded: a protocol bug traps (and reports which barrier) instead of hanging the GPU.
+// Every wait in this kernel is bounded in WALL-CLOCK time (%globaltimer, 20 s -- far beyond any slow-down a debugger, a
+// sanitizer, MPS time-slicing or memory contention can cause; a spin count would fire on correct runs there): a protocol bug
+// reports which barrier and traps instead of hanging the GPU until the watchdog.
+constexpr unsigned long long TC_WAIT_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 __device__ __noinline__ void tc_wait_timeout(const uint64_t *bar, const uint64_t *bars, uint32_t parity) {
     printf("[vrvq tc] mbarrier %d wait timed out (parity %u, block %d, thread %d)\n", (int)(bar - bars), parity, (int)blockIdx.x, (int)threadIdx.x);
     __trap();
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// true once `t0` (0 = not started) is older than the timeout; called every 2^14 failed polls
+__device__ __noinline__ bool tc_wait_expired(unsigned long long &t0) {
+    const unsigned long long now = global_timer_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    return now - t0 > TC_WAIT_TIMEOUT_NS;
 }
 #define TC_WAIT(bar_, parity_)                                                   \
     do {                                                                         \
         uint64_t *b__ = (bar_);                                                  \
         const uint32_t p__ = (parity_);                                          \
         uint32_t spins__ = 0;                                                    \
+        unsigned long long t0__ = 0;                                             \
         while (!mbar_try_wait(b__, p__)) {                                       \
-            if (++spins__ > (1u << 26)) tc_wait_timeout(b__, bars, p__);         \
+            if ((++spins__ & 0x3fffu) == 0 && tc_wait_expired(t0__)) tc_wait_timeout(b__, bars, p__); \
         }                                                                        \
     } while (0)
 
@@ -351,7 +366,7 @@ auto drain = [&](int g, uint32_t tq) {
                     for (int s = 0; s < n_run; ++s) {
                         long long code = rowok ? P.codes_in[(long long)b * P.cin_sb + (long long)s * P.cin_sq + fr] : 0;
                         if (code < 0 || code >= TCK) {  // F.embedding raises on such an index (quantize.py:82): report it
-                            if (P.error_flag != nullptr) *P.error_flag = 1;
+                            if (P.error_flag != nullptr) atomicOr(P.error_flag, 1);
                             code = 0;
                         }
                         const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)s * L.stage_floats() + L.off_raw() + (size_t)code * 8);
@@ -907,6 +922,7 @@ auto drain = [&](int g, uint32_t tq) {
                 const float *bout = P.tc + TL.off_bout();
                 int wi = 0, cs = FC ? n_run : 0;  // (from_codes: no search codebooks to refill)
                 uint32_t spins = 0;
+                unsigned long long spin_t0 = 0;
                 while (wi < n_stage_steps || cs < n_run) {
                     bool progressed = false;
                     if (wi < n_stage_steps) {
@@ -928,8 +944,8 @@ auto drain = [&](int g, uint32_t tq) {
                         ++cs;
                         progressed = true;
                     }
-                    if (progressed) spins = 0;
-                    else if (++spins > (1u << 26)) tc_wait_timeout(&bars[B_W_EMPTY], bars, 99);
+                    if (progressed) { spins = 0; spin_t0 = 0; }
+                    else if ((++spins & 0x3fffu) == 0 && tc_wait_expired(spin_t0)) tc_wait_timeout(&bars[B_W_EMPTY], bars, 99);
                 }
                 // final GEMM ring: for j: W_out (0..n_run-1, j) then the bias chunk j.  Its slots overlay the W_out ring and the
                 // codebook buffers, so it starts once every per-stage MMA has completed (and the last search is over).
@@ -1035,13 +1051,8 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
 
 template <int D, bool ZQIS, bool PROFILE, bool FC = false>
 static int launch_tc_one(const TcParams &P, int grid, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        int rc = check_cuda(cudaFuncSetAttribute(rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL),
-                            "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
-        if (rc) return rc;
-        attr_done = true;
-    }
+    int rc = ensure_dynamic_smem<rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC>>(SM_TOTAL, "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
+    if (rc) return rc;
     rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC><<<grid, TC_NTH, SM_TOTAL, st>>>(P);
     return check_cuda(cudaGetLastError(), "rvq_encode_tc_kernel launch");
 }

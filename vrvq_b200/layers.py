@@ -1,8 +1,7 @@
-"""PyTorch building blocks that sit UPSTREAM of the fused kernel (encoder conv stack, importance subnet).
-
-They are plain PyTorch/cuDNN on purpose: the hot path this package
-accelerates starts at the latent.  Their only contract is the reference's parameter layout so
-that a reference checkpoint loads unchanged:
+"""Building blocks UPSTREAM of the fused RVQ kernel: the DAC encoder conv stack (plain PyTorch/cuDNN on purpose, SURVEY.md
+section 2 rows 5, 6: the accelerated path starts at the latent) and the importance subnet, whose eval forward runs on the
+fused Snake + k=3 conv kernels of csrc/subnet.cu (`forward_torch` keeps the differentiable
+PyTorch formulation for training).  The parameter layout is the reference's, so a reference checkpoint loads unchanged:
   weight-normed convs expose `weight_g`, `weight_v`, `bias`   (models/layers.py:17-18, old-style weight_norm)
   Snake1d exposes `alpha` [1,C,1]                               (models/layers.py:35-41)
 """
@@ -116,6 +115,7 @@ class ImportanceSubnet(nn.Module):
         self.detach_input = detach_input
         self._packed = None
         self._packed_key = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.invalidate_packed())
 
     def _all_blocks(self):
         return [self.in_block] + list(self.blocks)
@@ -125,12 +125,21 @@ class ImportanceSubnet(nn.Module):
         parameter version."""
         from . import ops
 
+        # every parameter's storage address + in-place version; `.data` surgery is invisible to it: call invalidate_packed()
         key = (tuple((p.data_ptr(), p._version) for p in self.parameters()), str(device))
         if self._packed is None or self._packed_key != key:
             self._packed = [ops.PackedConv3(snake.alpha, ops.fold_weight_norm(conv.weight_v, conv.weight_g), conv.bias, device)
                             for snake, conv in self._all_blocks()]
             self._packed_key = key
         return self._packed
+
+    def invalidate_packed(self):
+        self._packed, self._packed_key = None, None
+
+    def _apply(self, fn, recurse=True):
+        r = super()._apply(fn, recurse)
+        self.invalidate_packed()
+        return r
 
     def forward_torch(self, x):
         if self.detach_input:

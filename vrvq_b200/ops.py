@@ -197,8 +197,12 @@ def rvq_encode(w: PackedWeights, z, n_run=None, imp_map=None, level=None, want_z
     return rvq_encode_into(w, z, out, n_run, imp_map, level, zero_accum=False)
 
 
-def from_codes(w: PackedWeights, codes: torch.Tensor, mask: Optional[torch.Tensor] = None, want_z_q_is=False, want_z_p=True):
-    """vrvq_from_codes_f32: codes [B,n,T] int64 CUDA -> (z_q [B,D,T], z_p [B,8n,T] | None, z_q_is | None)."""
+def from_codes(w: PackedWeights, codes: torch.Tensor, mask: Optional[torch.Tensor] = None, want_z_q_is=False, want_z_p=True,
+               error_flag: Optional[torch.Tensor] = None):
+    """vrvq_from_codes_f32: codes [B,n,T] int64 CUDA -> (z_q [B,D,T], z_p [B,8n,T] | None, z_q_is | None).
+    An out-of-range code raises IndexError as F.embedding does (one flag read-back = one sync per call); a streaming caller
+    passes `error_flag` (wire.new_error_flag) instead: the kernel sets bit 0 there, nothing synchronises, and the caller polls
+    it with wire.raise_on_flag when convenient."""
     if not codes.is_cuda or codes.dtype != torch.int64 or codes.dim() != 3:
         raise VrvqError("codes must be a CUDA int64 tensor [B, n, T] (no CPU fallback)")
     if w.blob is None or w.blob.device != codes.device:
@@ -211,7 +215,7 @@ def from_codes(w: PackedWeights, codes: torch.Tensor, mask: Optional[torch.Tenso
     z_q_is = torch.empty((B, n, w.input_dim, T), dtype=torch.float32, device=dev) if want_z_q_is else None
     if B * T == 0:
         return z_q, z_p, z_q_is
-    flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+    flag = error_flag if error_flag is not None else torch.zeros((1,), dtype=torch.int32, device=dev)
     a = FromCodesArgs()
     a.struct_size = C.sizeof(FromCodesArgs)
     a.B, a.T, a.input_dim, a.n_codebooks, a.codebook_size, a.n_run = B, T, w.input_dim, w.n_codebooks, w.codebook_size, n
@@ -233,7 +237,7 @@ def from_codes(w: PackedWeights, codes: torch.Tensor, mask: Optional[torch.Tenso
     with torch.cuda.device(dev):
         check(_lib.lib().vrvq_from_codes_f32(C.byref(a), current_stream_ptr(dev)), "vrvq_from_codes_f32")
     _lib.count_launch()
-    if int(flag.item()) != 0:  # F.embedding raises on out-of-range indices (quantize.py:82)
+    if error_flag is None and int(flag.item()) != 0:  # F.embedding raises on out-of-range indices (quantize.py:82)
         raise IndexError("codes contain an index outside [0, codebook_size)")
     return z_q, z_p, z_q_is
 

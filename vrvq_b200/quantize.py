@@ -19,10 +19,38 @@ from .layers import ImportanceSubnet, WNConv1d
 
 
 def _param_key(module: nn.Module):
-    return tuple((p.data_ptr(), p._version, str(p.device)) for p in module.parameters())
+    """Cache key of a module's packed weights: storage address and in-place version counter of EVERY parameter.
+    What it sees: optimizer steps / copy_ / load_state_dict (bump `_version`), `.to()` / `.data = new` (move the storage).
+    What it cannot see: writes through `.data` or under `torch.no_grad` views that bypass the counter (`p.data.mul_(2)`) --
+    after such surgery call `invalidate_packed()` (load_state_dict and `.to()/.cuda()/.float()` call it themselves)."""
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
 
 
-class VectorQuantize(nn.Module):
+class _PackedCacheMixin:
+    """Packed-weight cache shared by the quantizer mirrors: explicit invalidation + hooks on the nn.Module paths that
+    rewrite parameters wholesale."""
+
+    def _init_packed_cache(self):
+        self._packed = None
+        self._packed_key = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.invalidate_packed())
+
+    def invalidate_packed(self):
+        """Drop the device-side weight blob; the next forward folds and packs the current parameters again."""
+        self._packed = None
+        self._packed_key = None
+        for child in self.children():
+            for m in child.modules():
+                if isinstance(m, _PackedCacheMixin) and m is not self:
+                    m._packed, m._packed_key = None, None
+
+    def _apply(self, fn, recurse=True):
+        r = super()._apply(fn, recurse)
+        self.invalidate_packed()
+        return r
+
+
+class VectorQuantize(_PackedCacheMixin, nn.Module):
     """One RVQ stage (models/quantize.py:21-103).  forward() runs the fused kernel with a single stage."""
 
     def __init__(self, input_dim: int, codebook_size: int, codebook_dim: int):
@@ -32,8 +60,7 @@ class VectorQuantize(nn.Module):
         self.in_proj = WNConv1d(input_dim, codebook_dim, kernel_size=1)
         self.out_proj = WNConv1d(codebook_dim, input_dim, kernel_size=1)
         self.codebook = nn.Embedding(codebook_size, codebook_dim)
-        self._packed = None
-        self._packed_key = None
+        self._init_packed_cache()
 
     def folded(self):
         """(w_in [8,D], b_in [8], w_out [D,8], b_out [D], codebook [K,8]) on the CPU, fp32."""
@@ -69,7 +96,7 @@ class VectorQuantize(nn.Module):
         return self.embed_code(embed_id).transpose(1, 2)
 
 
-class ResidualVectorQuantize(nn.Module):
+class ResidualVectorQuantize(_PackedCacheMixin, nn.Module):
     """models/quantize.py:106-285."""
 
     def __init__(self, input_dim: int = 512, n_codebooks: int = 9, codebook_size: int = 1024,
@@ -85,19 +112,14 @@ class ResidualVectorQuantize(nn.Module):
         self.input_dim = input_dim
         self.quantizers = nn.ModuleList([VectorQuantize(input_dim, codebook_size, codebook_dim[i]) for i in range(n_codebooks)])
         self.quantizer_dropout = quantizer_dropout
-        self._packed = None
-        self._packed_key = None
+        self._init_packed_cache()
 
     # ---- weights ----
     def packed_weights(self, device) -> ops.PackedWeights:
-        """Fold weight-norm on the CPU (bit-identical to the reference's hook) and pack once per parameter version.
-        The per-call check is cheap: the in-place version counters of all stage parameters plus one storage address
-        (module.to() / load_state_dict move or rewrite all of them together)."""
-        plist = self.__dict__.get("_plist")
-        if plist is None or len(plist) != 7 * len(self.quantizers):
-            plist = [p for q in self.quantizers for p in q.parameters()]
-            self.__dict__["_plist"] = plist
-        key = (tuple(p._version for p in plist), plist[0].data_ptr(), plist[-1].data_ptr(), device)
+        """Fold weight-norm on the CPU (bit-identical to the reference's hook) and pack once per parameter version
+        (key: `_param_key`, every stage parameter's storage address and version counter; see there for what it cannot
+        detect and `invalidate_packed()`)."""
+        key = (tuple((p.data_ptr(), p._version) for q in self.quantizers for p in q.parameters()), device)
         if self._packed is None or self._packed_key != key:
             cols = list(zip(*[q.folded() for q in self.quantizers]))
             self._packed = ops.PackedWeights(*[torch.stack(c) for c in cols], device=device)
@@ -177,11 +199,18 @@ class VBRResidualVectorQuantize(ResidualVectorQuantize):
                 imp_map = self.imp_subnet(feat_enc)  # csrc/subnet.cu: six fused Snake+conv launches (quantize.py:372)
             imp_in, lvl = imp_map.contiguous(), level
             if isinstance(level, torch.Tensor):
+                # the reference broadcasts `imp_map [B,1,T] * level` (quantize.py:389): a scalar tensor or [B,1,1] is a
+                # per-item level (the kernel reads it); every other shape goes through the same torch broadcast, so e.g.
+                # [1,1,T] scales per frame and a shape the reference rejects is rejected here with the same error
                 lv = level.to(device=z.device, dtype=torch.float32)
-                if lv.numel() in (1, B) and lv.dim() <= 3:
+                if lv.numel() == 1 or tuple(lv.shape) == (B, 1, 1):
                     lvl = lv.reshape(-1)
-                else:  # general broadcastable level: pre-multiply (same fp32 product), then level = 1 is exact
-                    imp_in, lvl = (imp_map * lv).contiguous(), 1.0
+                else:  # pre-multiply (the same fp32 product the reference forms first), then level = 1 is exact
+                    scaled = imp_map * lv
+                    if scaled.shape != imp_map.shape:
+                        raise RuntimeError(f"level of shape {tuple(lv.shape)} does not broadcast against imp_map {tuple(imp_map.shape)} "
+                                           f"without changing its shape (quantize.py:389-395 would fail in generate_mask)")
+                    imp_in, lvl = scaled.contiguous(), 1.0
             out = ops.EncodeOutputs(B, D, T, Nq, z.device, z_q=True, z_q_is=self.return_z_q_is, latents=True, mask=True,
                                     pad_z_q_is_rows=self.pad_z_q_is_rows)
             if B * T:

@@ -21,11 +21,28 @@ from ._lib import VrvqError, check, current_stream_ptr
 SUPPORTED_VERSIONS = ["1.0.0"]  # models/dac_base.py:15
 
 
-def pack_codes(codes: torch.Tensor, mask: Optional[torch.Tensor] = None):
+def new_error_flag(device) -> torch.Tensor:
+    """A device-side error word for the streaming form of pack_codes / unpack_codes / ops.from_codes: pass it as
+    `error_flag=` and the calls OR their error bits into it WITHOUT synchronising; poll it with `raise_on_flag`
+    whenever a sync is convenient (e.g. once per file)."""
+    return torch.zeros((1,), dtype=torch.int32, device=device)
+
+
+def raise_on_flag(flag: torch.Tensor):
+    """Read the error word back (one sync) and raise what the eager calls would have raised."""
+    f = int(flag.item())
+    if f & 1:
+        raise IndexError("codes contain a value outside the valid range")
+    if f & 2:
+        raise ValueError("mask is not a 0/1 prefix mask (generate_mask_hard output) or a frame count exceeds the number of codebooks")
+
+
+def pack_codes(codes: torch.Tensor, mask: Optional[torch.Tensor] = None, error_flag: Optional[torch.Tensor] = None):
     """codes [B,Nq,T] int64 CUDA (+ mask [B,Nq,T] float32 0/1 prefix mask) -> (codes_u16 [B,Nq,T] uint16, counts [B,T] uint8 | None).
 
     Stages past a frame's count are not payload and come out as 0.  Raises IndexError for codes outside [0, 65535] and
-    ValueError for a mask that is not a prefix of ones (one device read-back, like from_codes)."""
+    ValueError for a mask that is not a prefix of ones (one device read-back, like from_codes) -- unless the caller passes
+    `error_flag` (see new_error_flag): then nothing synchronises and the caller polls the flag."""
     if not codes.is_cuda or codes.dtype != torch.int64 or codes.dim() != 3:
         raise VrvqError("codes must be a CUDA int64 tensor [B, Nq, T] (no CPU fallback)")
     B, nq, T = codes.shape
@@ -46,12 +63,14 @@ def pack_codes(codes: torch.Tensor, mask: Optional[torch.Tensor] = None):
         m_ptr, m_sb, m_sq = mask.data_ptr(), mask.stride(0), mask.stride(1)
     if out.numel() == 0:
         return out, counts
-    flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+    flag = error_flag if error_flag is not None else torch.zeros((1,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         check(_lib.lib().vrvq_pack_codes_u16(codes.data_ptr(), codes.stride(0), codes.stride(1), m_ptr, m_sb, m_sq, B, T, nq, out.data_ptr(),
                                              counts.data_ptr() if counts is not None else None, flag.data_ptr(), current_stream_ptr(dev)),
               "vrvq_pack_codes_u16")
     _lib.count_launch()
+    if error_flag is not None:
+        return out, counts
     f = int(flag.item())
     if f & 1:
         raise IndexError("codes contain a value outside [0, 65535]")
@@ -60,8 +79,9 @@ def pack_codes(codes: torch.Tensor, mask: Optional[torch.Tensor] = None):
     return out, counts
 
 
-def unpack_codes(codes_u16: torch.Tensor, counts: Optional[torch.Tensor] = None):
-    """(codes_u16 [B,Nq,T] uint16, counts [B,T] uint8 | None) CUDA -> (codes int64 [B,Nq,T], mask float32 [B,Nq,T] | None)."""
+def unpack_codes(codes_u16: torch.Tensor, counts: Optional[torch.Tensor] = None, error_flag: Optional[torch.Tensor] = None):
+    """(codes_u16 [B,Nq,T] uint16, counts [B,T] uint8 | None) CUDA -> (codes int64 [B,Nq,T], mask float32 [B,Nq,T] | None).
+    `error_flag`: as in pack_codes (no synchronisation; the caller polls)."""
     if not codes_u16.is_cuda or codes_u16.dtype != torch.uint16 or codes_u16.dim() != 3:
         raise VrvqError("codes_u16 must be a CUDA uint16 tensor [B, Nq, T] (no CPU fallback)")
     codes_u16 = codes_u16.contiguous()
@@ -78,7 +98,7 @@ def unpack_codes(codes_u16: torch.Tensor, counts: Optional[torch.Tensor] = None)
         mask = torch.empty((B, nq, T), dtype=torch.float32, device=dev)
     if codes.numel() == 0:
         return codes, mask
-    flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+    flag = error_flag if error_flag is not None else torch.zeros((1,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         check(_lib.lib().vrvq_unpack_codes_u16(codes_u16.data_ptr(), counts.data_ptr() if counts is not None else None, B, T, nq,
                                                codes.data_ptr(), codes.stride(0), codes.stride(1),
@@ -86,7 +106,7 @@ def unpack_codes(codes_u16: torch.Tensor, counts: Optional[torch.Tensor] = None)
                                                mask.stride(1) if mask is not None else 0, flag.data_ptr(), current_stream_ptr(dev)),
               "vrvq_unpack_codes_u16")
     _lib.count_launch()
-    if int(flag.item()) & 2:
+    if error_flag is None and int(flag.item()) & 2:
         raise ValueError("a frame count exceeds the number of codebooks")
     return codes, mask
 
