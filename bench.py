@@ -11,7 +11,8 @@ latents, mask_imp) plus the loss sum and the kept-frame counts.  Synthetic laten
 Keys (see the task contract): value = whole-job frames/s with inputs resident in HBM; e2e = the same through
 VBRResidualVectorQuantize.forward with pinned HOST buffers (H2D of z+imp_map and D2H of codes/mask/loss/kept inside
 the timed region); roofline = algorithmic bytes / measured launch time against the measured HBM copy peak;
-cpu_baseline = the eager-PyTorch CPU port of the reference (oracle/torch_port.py) on a bounded sample.
+cpu_baseline = the reference's CPU path (the live reference when its checkout is present, else the bit-identical eager-PyTorch
+port oracle/torch_port.py) on a bounded sample; e2e_full / e2e_full_dict = e2e with z_q / the whole output dict read back.
 Multi-GPU: one process per GPU (torchrun), independent batch shards, no data-path collective ("weak" scaling).
 """
 import argparse
@@ -114,6 +115,37 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(win), "window": window}
 
 
+_ORIG_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and with it the first-touch placement of the pinned host buffers) to the CPUs NVML reports as
+    local to GPU `index`; returns what was found, for the JSON line.  With every GPU of a box on one NUMA node (as on this
+    pool) this cannot help the N=8 host->device rate: the ranks then share that node's memory bandwidth."""
+    info = {"cpus_total": os.cpu_count()}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        try:
+            info["numa_node"] = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            info["numa_node"] = None
+        global _ORIG_AFFINITY
+        _ORIG_AFFINITY = os.sched_getaffinity(0)
+        allowed = sorted(set(cpus) & set(_ORIG_AFFINITY))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound_cpus"] = len(allowed)
+    except Exception as e:
+        info["affinity_error"] = str(e)[:80]
+    return info
+
+
 def make_state(device):
     import torch
 
@@ -139,28 +171,60 @@ def host_inputs(rank, n):
 
 
 def cpu_baseline_run(sd, steps, warmup, sample_B=4):
-    """Eager-PyTorch CPU port of the reference on a bounded sample: `sample_B` items x 862 frames of the same
-    workload per step, all host threads."""
+    """The reference's CPU path on a bounded sample: `sample_B` items x 862 frames of the cfg2 workload per step, all host
+    threads.  kind "reference": the UNMODIFIED reference classes imported from its checkout (oracle/ref_import.py; build
+    container only).  kind "port": oracle/torch_port.py, the same eager ATen op sequence, pinned bit-for-bit to the live
+    reference by tests/test_oracle_vs_reference.py::test_torch_port_is_bit_identical_to_the_live_reference -- what runs on the
+    GPU box, where the checkout does not exist.  B = 4 per step keeps the default run short and is the batch size the CPU
+    likes best (B = 16 per step is ~2x slower per frame), so ratios against it are conservative."""
     import torch
 
-    from oracle import torch_port
+    from oracle import ref_import, torch_port
 
     torch.set_num_threads(os.cpu_count() or 1)
-    w = torch_port.TorchPortWeights(sd)
     g = torch.Generator().manual_seed(1234)
     z = torch.randn(sample_B, CFG["D"], CFG["T"], generator=g)
     imp = torch.rand(sample_B, 1, CFG["T"], generator=torch.Generator().manual_seed(4321))
     lv = CFG["levels"]
+    kind = "port"
+    if ref_import.available() and os.environ.get("VRVQ_BENCH_FORCE_PORT") != "1":
+        try:
+            ref = ref_import.load()
+            m = ref.VBRResidualVectorQuantize(input_dim=CFG["D"], n_codebooks=CFG["Nq"], codebook_size=CFG["K"], codebook_dim=8,
+                                              level_min=0.125, level_max=6.0, imp2mask_alpha=2.0).eval()
+            m.load_state_dict(sd, strict=False)
+
+            class _Fixed(torch.nn.Module):  # the importance map is an input of this workload (SURVEY.md 8(d)), as on the GPU arm
+                def forward(self, feat):
+                    return imp
+
+            m.imp_subnet = _Fixed()
+
+            def fwd(level):
+                with torch.no_grad():
+                    return m(z, n_quantizers=None, feat_enc=z, level=level)
+
+            kind = "reference"
+        except Exception as e:  # fall back to the pinned port, and say so
+            sys.stderr.write(f"bench.py: live reference unusable ({e}); timing oracle/torch_port.py\n")
+    if kind == "port":
+        w = torch_port.TorchPortWeights(sd)
+
+        def fwd(level):
+            return torch_port.rvq_forward(w, z, None, imp, level)
+
     for i in range(warmup):
-        torch_port.rvq_forward(w, z, None, imp, lv[i % 3])
+        fwd(lv[i % 3])
     t0 = time.perf_counter()
     for i in range(steps):
-        torch_port.rvq_forward(w, z, None, imp, lv[i % 3])
+        fwd(lv[i % 3])
     dt = time.perf_counter() - t0
     frames = sample_B * CFG["T"] * steps
-    return {"value": frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} steps x B={sample_B} x T={CFG['T']} frames of the cfg2 workload (oracle/torch_port.py: the reference's eager "
-                      f"ATen op sequence on CPU, fp32, level cycling)", "ms_per_step": dt / steps * 1e3}
+    what = ("the unmodified reference VBRResidualVectorQuantize.forward (models/quantize.py:328-443) imported from its checkout"
+            if kind == "reference" else "oracle/torch_port.py, the reference's eager ATen op sequence (bit-identical to it, tests/test_oracle_vs_reference.py)")
+    return {"value": frames / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind, "sample_B": sample_B,
+            "sample": f"{steps} steps x B={sample_B} x T={CFG['T']} frames of the cfg2 workload on the host CPU, fp32, level cycling, "
+                      f"imp_map given: {what}", "ms_per_step": dt / steps * 1e3}
 
 
 def run_reference(args):
@@ -173,9 +237,16 @@ def run_reference(args):
 
     sd = gi.torch_state_dict(gi.make_state_dict(0, CFG["Nq"], CFG["D"], CFG["K"]))
     r = cpu_baseline_run(sd, args.steps, args.warmup)
-    line = {"impl": "reference", "metric": "rvq_latent_frames_per_sec", "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus,
+    cfg = config_dict()
+    # this arm is ONE CPU process whatever --gpus says: say what it ran, not what the GPU arm runs
+    cfg.update({"B_per_step": r["sample_B"], "parallelism": "one CPU process, all host threads (torch intra-op)",
+                "l2": "n/a (CPU)", "note": f"bounded sample: B={r['sample_B']} x T={CFG['T']} frames per step (the GPU arm runs B={CFG['B']} per GPU per step); "
+                                           "frames/s is per frame, so the arms compare per frame"})
+    cfg.pop("B_per_gpu", None)
+    line = {"impl": "reference", "metric": "rvq_latent_frames_per_sec", "value": r["value"], "unit": "frames/s", "n_gpus": 0,
+            "requested_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "torch": torch.__version__}
@@ -201,6 +272,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_info = bind_to_gpu_numa_node(local)
     saved_stdout = None
     if world > 1:
         # NCCL prints its version banner on stdout at communicator creation; keep stdout clean for the one JSON line
@@ -252,53 +324,69 @@ def run_ours(args):
     # ---- end-to-end through the public module API with pinned host buffers
     zs_p = [z.pin_memory() for z in zs_h]
     imps_p = [i.pin_memory() for i in imps_h]
-    h_codes = torch.empty((B, Nq, T), dtype=torch.int64).pin_memory()
-    h_mask = torch.empty((B, Nq, T), dtype=torch.float32).pin_memory()
-    h_small = torch.empty((Nq + 1,), dtype=torch.float64).pin_memory()
     h2d = zs_p[0].numel() * 4 + imps_p[0].numel() * 4
-    d2h = h_codes.numel() * 8 + h_mask.numel() * 4 + h_small.numel() * 8
-
     # Two streams alternate so that step i+1's host->device copy overlaps step i's kernel and read-back, as a
     # streaming caller would run it; every step still copies its own inputs in and its own results out.
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    h_codes = [h_codes, torch.empty_like(h_codes).pin_memory()]
-    h_mask = [h_mask, torch.empty_like(h_mask).pin_memory()]
-    h_small = [h_small, torch.empty_like(h_small).pin_memory()]
 
-    def e2e_step(i):
-        k = i % 2
-        with torch.cuda.stream(streams[k]):
-            z = zs_p[i % N_INPUT_BUFFERS].to(dev, non_blocking=True)
-            imp = imps_p[i % N_INPUT_BUFFERS].to(dev, non_blocking=True)
-            r = model(z, n_quantizers=None, feat_enc=None, level=levels[i % 3], imp_map=imp)
-            h_codes[k].copy_(r["codes"], non_blocking=True)
-            h_mask[k].copy_(r["mask_imp"], non_blocking=True)
-            h_small[k][:Nq].copy_(r["kept_frames"].to(torch.float64), non_blocking=True)
-            h_small[k][Nq:].copy_(r["commitment_loss"].to(torch.float64).reshape(1), non_blocking=True)
+    def pinned(shape, dtype):
+        return [torch.empty(shape, dtype=dtype).pin_memory() for _ in range(2)]
+
+    h_codes, h_mask, h_small = pinned((B, Nq, T), torch.int64), pinned((B, Nq, T), torch.float32), pinned((Nq + 1,), torch.float64)
+    d2h_small = h_codes[0].numel() * 8 + h_mask[0].numel() * 4 + h_small[0].numel() * 8
+
+    def measure_e2e(back, n_steps):
+        """back: "codes" = codes + mask + kept counts + loss come back (z_q / z_q_is stay on the device for the decoder);
+        "z_q" = additionally the quantised latent z_q; "dict" = the reference's whole output dict incl. z_q_is and latents."""
+        h_zq = pinned((B, D, T), torch.float32) if back in ("z_q", "dict") else None
+        h_zqis = pinned((B, Nq, D, T), torch.float32) if back == "dict" else None
+        h_lat = pinned((B, CD * Nq, T), torch.float32) if back == "dict" else None
+        d2h = d2h_small + (h_zq[0].numel() * 4 if h_zq else 0) + (h_zqis[0].numel() * 4 + h_lat[0].numel() * 4 if h_zqis else 0)
+
+        def e2e_step(i):
+            k = i % 2
+            with torch.cuda.stream(streams[k]):
+                z = zs_p[i % N_INPUT_BUFFERS].to(dev, non_blocking=True)
+                imp = imps_p[i % N_INPUT_BUFFERS].to(dev, non_blocking=True)
+                r = model(z, n_quantizers=None, feat_enc=None, level=levels[i % 3], imp_map=imp)
+                h_codes[k].copy_(r["codes"], non_blocking=True)
+                h_mask[k].copy_(r["mask_imp"], non_blocking=True)
+                h_small[k][:Nq].copy_(r["kept_frames"].to(torch.float64), non_blocking=True)
+                h_small[k][Nq:].copy_(r["commitment_loss"].to(torch.float64).reshape(1), non_blocking=True)
+                if h_zq is not None:
+                    h_zq[k].copy_(r["z_q"], non_blocking=True)
+                if h_zqis is not None:
+                    h_zqis[k].copy_(r["z_q_is"], non_blocking=True)
+                    h_lat[k].copy_(r["latents"], non_blocking=True)
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        cur = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for st in streams:
+            st.wait_stream(cur)
+        for i in range(n_steps):
+            e2e_step(i)
+        for st in streams:
+            cur.wait_stream(st)
+        e1.record(cur)
+        barrier()
+        return e0.elapsed_time(e1), d2h
 
     e2e_steps = max(4, min(args.steps, 50))
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    cur = torch.cuda.current_stream(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(cur)
-    for st in streams:
-        st.wait_stream(cur)
-    for i in range(e2e_steps):
-        e2e_step(i)
-    for st in streams:
-        cur.wait_stream(st)
-    e1.record(cur)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms, d2h = measure_e2e("codes", e2e_steps)
+    zq_steps, dict_steps = max(4, min(args.steps, 30)), max(4, min(args.steps, 8))
+    e2e_zq_ms, d2h_zq = measure_e2e("z_q", zq_steps)
+    e2e_dict_ms, d2h_dict = measure_e2e("dict", dict_steps)
     sampler.stop()
 
     # max over ranks
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms, e2e_zq_ms, e2e_dict_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0].item()), float(t[1].item())
+    ms_max, e2e_ms_max, e2e_zq_ms_max, e2e_dict_ms_max = (float(x) for x in t.tolist())
 
     if rank == 0:
         bytes_per_launch = algorithmic_bytes_per_frame(D, Nq, True) * frames
@@ -318,10 +406,21 @@ def run_ours(args):
                          "smem_bytes": info["smem_bytes"]},
             "e2e": {"value": world * frames * e2e_steps / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps,
-                    "api": "VBRResidualVectorQuantize.forward(z, level, imp_map) on pinned host buffers, two alternating CUDA streams; z_q/z_q_is stay on the device"},
+                    "api": "VBRResidualVectorQuantize.forward(z, level, imp_map) on pinned host buffers, two alternating CUDA streams; codes, mask, "
+                           "kept counts and loss come back, z_q/z_q_is stay on the device (an encoder hands them to the decoder there)"},
+            # the same call with more of the result read back: the quantised latent, and the reference's whole output dict
+            "e2e_full": {"value": world * frames * zq_steps / (e2e_zq_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                         "d2h_bytes_per_step": d2h_zq, "steps": zq_steps, "ms_per_step": e2e_zq_ms_max / zq_steps,
+                         "what": "e2e + z_q [B,D,T] copied back"},
+            "e2e_full_dict": {"value": world * frames * dict_steps / (e2e_dict_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                              "d2h_bytes_per_step": d2h_dict, "steps": dict_steps, "ms_per_step": e2e_dict_ms_max / dict_steps,
+                              "what": "e2e + z_q, z_q_is [B,Nq,D,T] and latents copied back (every key of the reference's dict); PCIe-bound"},
+            "host": host_info,
             "gpu_launches": launches * world, "clocks": clocks, "torch": torch.__version__,
         }
         if world == 1 and not args.no_cpu_baseline:
+            if _ORIG_AFFINITY is not None:
+                os.sched_setaffinity(0, _ORIG_AFFINITY)  # the CPU baseline gets every host core back
             cb = cpu_baseline_run(sd, steps=args.cpu_steps, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         sys.stdout.flush()
@@ -339,7 +438,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=4000)  # ~0.6 s of back-to-back launches: max-over-ranks jitter stays below 1 %
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=60, help="steps of the bounded CPU-baseline sample (N=1 only)")
