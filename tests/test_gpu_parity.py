@@ -46,13 +46,15 @@ def impl(request, monkeypatch):
     return request.param
 
 
-def assert_kernel(impl, m_or_pw, B, T, n_run):
+def assert_kernel(impl, m_or_pw, B, T, n_run, z_q_is=False):
     """The kernel that actually serves the call is the one the test is named after."""
     from vrvq_b200 import ops
 
     pw = m_or_pw if isinstance(m_or_pw, ops.PackedWeights) else m_or_pw.packed_weights(torch.device("cuda", torch.cuda.current_device()))
     info = ops.encode_launch_info(pw, B, T, n_run, "cuda")
-    assert info["block"] == (480 if impl == "tc" else 512), (impl, info)
+    if impl == "tc" and not ops.tc_kernel_available(pw, n_run, z_q_is=z_q_is):
+        pytest.skip("no tensor-core kernel for this shape (the call is served by the CUDA-core kernel, covered by the other parameter)")
+    assert (info["block"] != 512) == (impl == "tc"), (impl, info)
 
 
 def test_extension_is_loaded():

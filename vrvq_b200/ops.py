@@ -187,6 +187,12 @@ def encode_launch_info(w: PackedWeights, B: int, T: int, n_run: int, device):
     return {"grid": g.value, "block": b.value, "smem_bytes": s.value}
 
 
+def tc_kernel_available(w: PackedWeights, n_run: int, z_q_is: bool = False) -> bool:
+    """Whether a tensor-core (tcgen05) instantiation of the fused encode exists for this model / call shape: D in
+    {256, 512, 1024}, K = 1024 and at most 8 codebooks (csrc/common.cuh: tc_shape_ok)."""
+    return w.codebook_size == 1024 and w.input_dim in (256, 512, 1024) and 1 <= w.n_codebooks <= 8
+
+
 def rvq_encode(w: PackedWeights, z, n_run=None, imp_map=None, level=None, want_z_q_is=False, want_loss_pf=False):
     """Allocate outputs and run the fused encode.  Returns the EncodeOutputs."""
     n_run = w.n_codebooks if n_run is None else int(n_run)
