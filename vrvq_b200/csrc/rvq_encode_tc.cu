@@ -32,8 +32,12 @@
 //
 // Exactness: only z_e differs from the reference's conv1d by rounding (as any two conv implementations do), so codes can
 // differ only at fp32 near-ties (audited in tests); z_q / z_q_is carry the tensor core's accumulation rounding (<= 2e-6).
+#include <cuda.h>  // CUtensorMap (types only: the driver entry point is fetched through the runtime, no -lcuda)
+
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 #include "encode_params.cuh"
@@ -47,6 +51,12 @@ constexpr int TC_NSEARCH = 256;
 // shared memory map (bytes).  Phase L uses [0, 49152); phase S re-uses that region.
 constexpr int SM_LR = 0;           // phase L ring, 3 slots x 16 KB: W_in [8 kg][128 rows][4] (rows 0-63 heads, 64-127 remainders);
 constexpr int L_SLOT = 16384, L_SLOTS = 3;  // the matching A operand (the split latent chunk) lives in tensor memory
+// phase L latent staging ring (free in phase L: the per-stage A tiles, the W_out ring and codebook buffer 1 live there later):
+// 3 slots x [64 channels][132 floats].  A slot is filled by the TMA unit -- one cp.async.bulk.tensor box per slot when the row
+// pitch allows a tensor map (16-byte multiples), else one cp.async.bulk per channel row from the 16-byte aligned address at or
+// below the row's first frame (the row then sits `shift` = 0..3 floats into its 528-byte smem row) -- so the 256 loader threads
+// read the latent with conflict-free LDS (lane = frame) instead of issuing 128 misaligned LDGs per chunk and waiting on HBM.
+constexpr int SM_ZR = 49152, Z_CH = 64, Z_PITCH = 132, Z_SLOT = Z_CH * Z_PITCH * 4, Z_SLOTS = 3;
 constexpr int SM_AT = 0;           // phase S: per-stage A tiles, 8 x (hi 4 KB | lo 4 KB): [2 kg][128 frames][4]
 constexpr int SM_AM = 65536;       // phase S: mask tile (A operand of the bias rows of the final GEMM) [2 kg][128][4]
 constexpr int SM_WO = 69632;       // phase S: W_out ring, 4 slots x 12 KB (hi | lo | bias tile)
@@ -67,13 +77,15 @@ constexpr int F_SLOT = 40960, F_SLOTS = 3, F_ITEMS = 5;  // final-GEMM ring (<= 
 static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 static_assert(SM_WO + W_SLOTS * W_SLOT == SM_CB1 && SM_CB1 + 36864 == SM_CB0 && SM_CB0 + 36864 == SM_ES, "shared memory map");
 static_assert(SM_WO + F_SLOTS * F_SLOT == SM_ES, "final ring covers [SM_WO, SM_ES)");
-static_assert(L_SLOTS * L_SLOT <= SM_CB0, "phase-L ring must not reach codebook buffer 0");
+static_assert(L_SLOTS * L_SLOT <= SM_ZR && SM_ZR + Z_SLOTS * Z_SLOT <= SM_CB0, "phase-L rings must not reach codebook buffer 0");
+static_assert(SM_ZR % 128 == 0 && Z_SLOT % 128 == 0, "TMA destinations are 128-byte aligned");
 
 enum {
     B_L_FULL = 0, B_L_EMPTY = 4, B_SET_FULL = 24, B_SET_EMPTY = 26, B_W_FULL = 28, B_W_EMPTY = 32,
     B_D_FULL = 36, B_D_EMPTY = 38, B_CB_FULL = 40, B_A_READY = 42, B_ZQ_READY = 50, B_MMA_DONE = 51, B_F_FULL = 52, B_F_EMPTY = 56,
-    B_E_READY = 60, B_SB_FULL = 61, B_SB_EMPTY = 64, B_COUNT = 67
+    B_E_READY = 60, B_SB_FULL = 61, B_SB_EMPTY = 64, B_Z_FULL = 67, B_Z_EMPTY = 70, B_COUNT = 73
 };
+enum { ZMODE_LDG = 0, ZMODE_BULK = 1, ZMODE_TMA = 2 };  // how phase L fetches the latent
 
 // TMEM columns: [0,64) running z_e sums of all stages; phase L accumulator sets at 64 + 128*set (hi*hi | lo terms);
 // phase S out_proj ring at 64 + 128*buf.
@@ -95,11 +107,13 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// true once `t0` (0 = not started) is older than the timeout; called every 2^14 failed polls
-__device__ __noinline__ bool tc_wait_expired(unsigned long long &t0) {
+// called every 2^14 failed polls with the time of the first such call (0 = this is the first): returns that time, or reports
+// and traps once it is older than the timeout.  By value: nothing of the wait loop lives in local memory.
+__device__ __noinline__ unsigned long long tc_wait_check(unsigned long long t0, const uint64_t *bar, const uint64_t *bars, uint32_t parity) {
     const unsigned long long now = global_timer_ns();
-    if (t0 == 0) { t0 = now; return false; }
-    return now - t0 > TC_WAIT_TIMEOUT_NS;
+    if (t0 == 0) return now;
+    if (now - t0 > TC_WAIT_TIMEOUT_NS) tc_wait_timeout(bar, bars, parity);
+    return t0;
 }
 #define TC_WAIT(bar_, parity_)                                                   \
     do {                                                                         \
@@ -108,15 +122,32 @@ __device__ __noinline__ bool tc_wait_expired(unsigned long long &t0) {
         uint32_t spins__ = 0;                                                    \
         unsigned long long t0__ = 0;                                             \
         while (!mbar_try_wait(b__, p__)) {                                       \
-            if ((++spins__ & 0x3fffu) == 0 && tc_wait_expired(t0__)) tc_wait_timeout(b__, bars, p__); \
+            if ((++spins__ & 0x3fffu) == 0) t0__ = tc_wait_check(t0__, b__, bars, p__); \
         }                                                                        \
     } while (0)
+
+// one TMA box of a rank-3 tensor map into shared memory, completion on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_3d(void *dst_smem, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Tensor maps of the latent, one per channel class (channel % nc, nc = 1, 2 or 4): see pick_zmode
+struct ZMaps {
+    CUtensorMap m[4];
+};
 
 struct TcParams {
     EncodeParams e;
     const float *tc;  // TC section of the blob
     int adv;          // frames per tile (multiple of 8, <= 120)
     int tiles_per_b, n_tiles;
+    int zmode;        // ZMODE_*
+    int znc_log2;     // ZMODE_TMA: log2 of the number of channel classes (1, 2 or 4 tensor maps; see pick_zmode)
+    int zshift[4];    // ZMODE_TMA: x offset of frame 0 in the rows of class k
+    int trace;        // VRVQ_DEBUG_PHASES=3 (profiling instantiation only): block 0 records per-chunk timestamps of its first tile's phase L
     // from_codes mode (FC): codes [B][n_run][T] are an input, mask_in an optional 0/1 mask [B][n_run][T], error_flag is set when
     // a code lies outside [0, K)
     const long long *codes_in;
@@ -153,7 +184,7 @@ __device__ __forceinline__ uint32_t base_mod8(const float *ptr, long long off) {
 // FC = from_codes mode (models/quantize.py:217-249): no latent, no in_proj, no search -- the codes are an input; the gather, the
 // out_proj units, the masking and the final GEMM are the encode path's own.
 template <int D, bool ZQIS, bool PROFILE, bool FC>
-__global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P) {
+__global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P, const __grid_constant__ ZMaps zmaps) {
     constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;  // 32-channel chunks, accumulator drained every 4 chunks
     // search-score chunks: 64 codes per MMA into 3 x 64 TMEM columns; without z_q_is the out_proj ring is idle during the
     // searches, so the scores take 3 x 128 columns from TM_SET on and half as many (170-cycle) barrier hand-overs
@@ -194,6 +225,8 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         for (int i = 0; i < F_SLOTS; ++i) { mbar_init(&bars[B_F_FULL + i], 1); mbar_init(&bars[B_F_EMPTY + i], 1); }
         mbar_init(&bars[B_E_READY], 4);
         for (int i = 0; i < 3; ++i) { mbar_init(&bars[B_SB_FULL + i], 1); mbar_init(&bars[B_SB_EMPTY + i], 4); }
+        // latent staging slot: filled by the producer's expect_tx + the TMA bytes, released by the 8 loader warps
+        for (int i = 0; i < Z_SLOTS; ++i) { mbar_init(&bars[B_Z_FULL + i], 1); mbar_init(&bars[B_Z_EMPTY + i], 8); }
         fence_mbar_init();
     }
     if (w == 12) {
@@ -228,6 +261,13 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         }
     };
 
+    // VRVQ_DEBUG_PHASES=3: phase_cycles[1024 + 32 * event + chunk] = clock64 of block 0's first tile (events: 0 latent slot full,
+    // 1 split done, 2 A slot empty, 3 A slot handed over, 4 issuer saw the slot, 5 MMAs issued, 6 producer saw the W_in slot empty,
+    // 7 drains: [4g] accumulator set full, [4g+1] drained)
+    auto trace = [&](int ev, int idx) {
+        if (PROFILE && P.trace && blockIdx.x == 0 && p.phase_cycles != nullptr) p.phase_cycles[1024 + 32 * ev + idx] = clock64();
+    };
+
     double loss_acc = 0.0;               // frame threads
     unsigned long long kept_acc = 0ull;  // lane k of warps 0-3 counts stage k
     uint32_t wn = 0, fn = 0, dn = 0;     // W_out ring / final ring step counters, out_proj unit counter
@@ -239,7 +279,9 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         const int t0 = (tile % P.tiles_per_b) * P.adv;
         const int fv = min(P.adv, p.T - t0);  // frames this tile owns: tile rows 8 .. 8+fv-1 (rows 0-7: halo = the previous 8 frames)
         const bool last_tile = (tile % P.tiles_per_b) == P.tiles_per_b - 1;
-        const uint32_t lbase = (uint32_t)it * NCH, gbase = (uint32_t)it * NG;
+        const uint32_t lbase = (uint32_t)it * NCH, gbase = (uint32_t)it * NG, zbase = (uint32_t)it * (NCH / 2);
+        // latent staging geometry of this tile (ZMODE_BULK / ZMODE_TMA): smem column of frame fr in a staged row = fr - tstart + shift(row)
+        const int tstart = P.zmode == ZMODE_TMA ? t0 - 8 : max(t0 - 8, 0);
         const uint32_t tpar = (uint32_t)it & 1u;
         const int n_stage_steps = ZQIS ? n_run * NJ : 0;
         const int n_final_steps = (p.z_q != nullptr) ? NJ * ((n_run + F_ITEMS) / F_ITEMS) : 0;  // ceil((n_run + 1) / F_ITEMS) per 128-channel chunk
@@ -250,6 +292,7 @@ auto drain = [&](int g, uint32_t tq) {
             const uint32_t gg = gbase + (uint32_t)g, set = gg & 1u;
             TC_WAIT(&bars[B_SET_FULL + set], (gg >> 1) & 1u);
             tmem_fence_after_sync();
+            if (PROFILE && tid == 256 && it == 0) trace(7, 4 * g);
             const uint32_t ts = tq + TM_SET + 128u * set;
 #pragma unroll 2
             for (int c8 = 0; c8 < 8; ++c8) {
@@ -272,6 +315,7 @@ auto drain = [&](int g, uint32_t tq) {
             tmem_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[B_SET_EMPTY + set]);
+            if (PROFILE && tid == 256 && it == 0) trace(7, 4 * g + 1);
         };
         if (w < 8) {
             // =====================================================================================================
@@ -305,6 +349,71 @@ auto drain = [&](int g, uint32_t tq) {
             }
             ph_mark(0);
             // ---- phase L: load, split, stage (256 threads: frame f, half q of each 32-channel chunk) ----
+            if (P.zmode != ZMODE_LDG) {
+                // staged path: the chunk's rows are in shared memory (TMA); lane = frame, so every LDS is conflict-free
+                const int q = tid >> 7;
+                const bool valid = inb;
+                const int col = min(max(fr - tstart, 0), 127);
+                // row shift: (alignment of the row's first frame) mod 4 floats; rows 4 apart share it (32 and 16 rows apart too)
+                uint32_t shw[4];
+                if (P.zmode == ZMODE_TMA) {
+                    // boxes start at x = tstart (the TMA unit faults on an x that is not a 16-byte multiple): a frame of class
+                    // k = channel % nc sits zshift[k] elements further right in its staged row
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) shw[k] = (uint32_t)P.zshift[k & ((1 << P.znc_log2) - 1)];
+                } else {
+                    const uint32_t sh0 = (uint32_t)(((reinterpret_cast<uintptr_t>(p.z) >> 2) + (unsigned long long)((long long)b * p.z_sb + tstart)) & 3ull);
+                    const uint32_t zs4 = (uint32_t)(p.z_sd & 3);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) shw[k] = (sh0 + (uint32_t)k * zs4) & 3u;
+                }
+                // slot row of the i-th channel of this thread's 16: channel classes (channel % NC) are stored class-major; NC is a
+                // compile-time constant per instance of the loop so that every LDS has an immediate offset
+                auto stage = [&](auto nc_tag) {
+                    constexpr int NC = decltype(nc_tag)::value;
+                    for (int c = 0; c < NCH; ++c) {
+                        const uint32_t zn = zbase + (uint32_t)(c >> 1), zsl = zn % Z_SLOTS;
+                        if ((c & 1) == 0) TC_WAIT(&bars[B_Z_FULL + zsl], (zn / Z_SLOTS) & 1u);
+                        if (PROFILE && tid == 0 && it == 0) trace(0, c);
+                        const float *zr = reinterpret_cast<const float *>(smem + SM_ZR + zsl * Z_SLOT) + ((32 * (c & 1) + 16 * q) / NC) * Z_PITCH + col;
+                        float h[16], l[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float x = valid ? zr[((i % NC) * (Z_CH / NC) + i / NC) * Z_PITCH + shw[i & 3]] : 0.0f;
+                            h[i] = __uint_as_float(__float_as_uint(x) & 0xffffe000u);  // TF32 head by truncation; x - head is exact
+                            l[i] = __fsub_rn(x, h[i]);
+                        }
+                        if (c & 1) {  // both halves of the slot are in registers: hand it back to the producer
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bars[B_Z_EMPTY + zsl]);
+                        }
+                        if (PROFILE && tid == 0 && it == 0) trace(1, c);
+                        const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS, use = n / L_SLOTS;
+                        if (use >= 1) {
+                            TC_WAIT(&bars[B_L_EMPTY + sl], (use - 1) & 1u);
+                            tmem_fence_after_sync();
+                        }
+                        if (PROFILE && tid == 0 && it == 0) trace(2, c);
+                        {
+                            uint32_t hv[16], lv[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { hv[i] = __float_as_uint(h[i]); lv[i] = __float_as_uint(l[i]); }
+                            const uint32_t ta = tq + TM_AL + 64u * sl + 16u * (uint32_t)q;
+                            tmem_st16(ta, hv);
+                            tmem_st16(ta + 32, lv);
+                        }
+                        tmem_wait_st();
+                        tmem_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars[B_L_FULL + sl]);
+                        if (PROFILE && tid == 0 && it == 0) trace(3, c);
+                    }
+                };
+                const int lg = P.zmode == ZMODE_TMA ? P.znc_log2 : 0;
+                if (lg == 0) stage(std::integral_constant<int, 1>{});
+                else if (lg == 1) stage(std::integral_constant<int, 2>{});
+                else stage(std::integral_constant<int, 4>{});
+            } else
             {
                 const int q = tid >> 7;
                 const bool valid = inb;
@@ -745,6 +854,7 @@ auto drain = [&](int g, uint32_t tq) {
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS;
                     TC_WAIT(&bars[B_L_FULL + sl], (n / L_SLOTS) & 1u);
+                    if (PROFILE && it == 0) trace(4, c);
                     const uint32_t gg = gbase + (uint32_t)(c >> 2), set = gg & 1u;
                     if ((c & 3) == 0 && gg >= 2) TC_WAIT(&bars[B_SET_EMPTY + set], ((gg >> 1) - 1) & 1u);
                     tmem_fence_after_sync();
@@ -759,6 +869,7 @@ auto drain = [&](int g, uint32_t tq) {
                     }
                     umma_commit(&bars[B_L_EMPTY + sl]);
                     if ((c & 3) == 3) umma_commit(&bars[B_SET_FULL + set]);
+                    if (PROFILE && it == 0) trace(5, c);
                 }
             }
             ph_mark(0);
@@ -865,6 +976,42 @@ auto drain = [&](int g, uint32_t tq) {
             // Search-MMA issuer: lane 0 of warp 14.  Per stage, NSC MMAs of M = 128 frames x N = SCW codes x K = 8 (plain TF32)
             // into three rotating SCW-column score buffers; chunk c is scanned by warps 4(c%2) .. 4(c%2)+3.
             // =====================================================================================================
+            if (!FC && P.zmode != ZMODE_LDG) {
+                // ---- phase L: producer of the latent staging ring (this warp has nothing else to do before the searches) ----
+                const int fvz = t0 + fv - tstart;  // frames to stage per row (<= 128)
+                for (int zc = 0; zc < NCH / 2; ++zc) {
+                    const uint32_t m = zbase + (uint32_t)zc, slot = m % Z_SLOTS, use = m / Z_SLOTS;
+                    if (use >= 1) TC_WAIT(&bars[B_Z_EMPTY + slot], (use - 1) & 1u);
+                    unsigned char *dst = smem + SM_ZR + slot * Z_SLOT;
+                    if (P.zmode == ZMODE_TMA) {
+                        if (lane == 0) {  // nc boxes [1 item][64 / nc channels of one class][132 frames]; x outside the map arrives as zeros
+                            const int lg = P.znc_log2, rows = Z_CH >> lg;
+                            mbar_arrive_expect_tx(&bars[B_Z_FULL + slot], Z_SLOT);
+                            for (int k = 0; k < (1 << lg); ++k)
+                                tma_load_3d(dst + k * rows * (Z_PITCH * 4), &zmaps.m[k], tstart, rows * zc, b, &bars[B_Z_FULL + slot]);
+                        }
+                    } else {
+                        // one bulk copy per channel row, from the 16-byte aligned address at or below its first frame to the
+                        // 16-byte boundary at or above its last one (<= 12 bytes of over-read on either side, inside the same
+                        // 16-byte granule as a valid element); lane r copies rows r and r + 32 of the slot
+                        const float *row0 = p.z + (long long)b * p.z_sb + (long long)(Z_CH * zc) * p.z_sd + tstart;
+                        unsigned long long a0[2];
+                        uint32_t nb[2];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const unsigned long long a = reinterpret_cast<unsigned long long>(row0 + (long long)(lane + 32 * k) * p.z_sd);
+                            a0[k] = a & ~15ull;
+                            nb[k] = (uint32_t)(((a + 4ull * (unsigned long long)fvz + 15ull) & ~15ull) - a0[k]);
+                        }
+                        const uint32_t total = __reduce_add_sync(0xffffffffu, nb[0] + nb[1]);
+                        if (lane == 0) mbar_arrive_expect_tx(&bars[B_Z_FULL + slot], total);
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            bulk_g2s(dst + (lane + 32 * k) * (Z_PITCH * 4), reinterpret_cast<const void *>(a0[k]), nb[k], &bars[B_Z_FULL + slot]);
+                    }
+                }
+            }
             __syncwarp();
             tmem_fence_before_sync();
             __syncthreads();  // L -> S
@@ -903,6 +1050,7 @@ auto drain = [&](int g, uint32_t tq) {
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t m = lbase + (uint32_t)c, slot = m % L_SLOTS, use = m / L_SLOTS;
                     if (use >= 1) TC_WAIT(&bars[B_L_EMPTY + slot], (use - 1) & 1u);
+                    if (PROFILE && it == 0) trace(6, c);
                     mbar_arrive_expect_tx(&bars[B_L_FULL + slot], 16384);
                     bulk_g2s(smem + SM_LR + slot * L_SLOT, win + (size_t)c * 4096, 16384, &bars[B_L_FULL + slot]);
                 }
@@ -945,7 +1093,7 @@ auto drain = [&](int g, uint32_t tq) {
                         progressed = true;
                     }
                     if (progressed) { spins = 0; spin_t0 = 0; }
-                    else if ((++spins & 0x3fffu) == 0 && tc_wait_expired(spin_t0)) tc_wait_timeout(&bars[B_W_EMPTY], bars, 99);
+                    else if ((++spins & 0x3fffu) == 0) spin_t0 = tc_wait_check(spin_t0, &bars[B_W_EMPTY], bars, 99);
                 }
                 // final GEMM ring: for j: W_out (0..n_run-1, j) then the bias chunk j.  Its slots overlay the W_out ring and the
                 // codebook buffers, so it starts once every per-stage MMA has completed (and the last search is over).
@@ -985,7 +1133,7 @@ auto drain = [&](int g, uint32_t tq) {
             lite_l = 0;
         }
     }
-    if (PROFILE && ph_on)
+    if (PROFILE && ph_on && !P.trace)
         for (int k = 0; k < 16; ++k) p.phase_cycles[((size_t)blockIdx.x * 4 + ph_role) * 16 + k] = ph_acc[k];
 
     // ---- teardown ----
@@ -1029,39 +1177,115 @@ int encode_tc_usable(const vrvq_encode_args *a) {
     return 1;
 }
 
-static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParams &P, int *grid) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libvrvq.so does not link libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(ptr);
+        else
+            cudaGetLastError();
+        tried = true;
+    }
+    return fn;
+}
+
+// How phase L fetches the latent.  Default: TMA tensor maps for EVERY layout.  A tensor map needs a 16-byte aligned base and
+// 16-byte multiples for its pitches, which a [B, D, T] tensor with T = 862 does not offer (rows are 8-byte aligned).  But the
+// channels of one class k = channel % nc (nc = 1, 2 or 4) do: their rows are nc * pitch apart (a 16-byte multiple as soon as
+// nc * pitch % 4 == 0), and the 16-byte aligned address at or below the first row of the class is a legal base -- the row then
+// starts s_k = 0..3 elements into the map's row; boxes start at 16-byte multiples of x and the loader threads add s_k to their column.  So the latent is seen
+// through nc rank-3 maps (x = frame + s_k, row = channel / nc, item), class k staged class-major in the slot; frames outside
+// [0, T) come back as zeros (or as the neighbouring row's elements for the <= 3 positions before frame 0: those rows are never
+// valid frames).  VRVQ_LATENT_LOAD=ldg|bulk|tma overrides (ldg = per-thread loads, the round-1 path; bulk = one cp.async.bulk per
+// channel row; both kept for A/B runs).
+static int pick_zmode(const vrvq_encode_args *a, ZMaps *maps, TcParams &P) {
+    memset(maps, 0, sizeof(*maps));
+    P.znc_log2 = 0;
+    for (int k = 0; k < 4; ++k) P.zshift[k] = 0;
+    int want = ZMODE_TMA;
+    if (const char *env = getenv("VRVQ_LATENT_LOAD")) {
+        if (env[0] == 'l') return ZMODE_LDG;
+        if (env[0] == 'b') want = ZMODE_BULK;
+    }
+    if (a->z_stride_d <= 0 || a->z_stride_b < 0) return ZMODE_LDG;
+    const uintptr_t zaddr = reinterpret_cast<uintptr_t>(a->z);
+    const int al = (int)((zaddr >> 2) & 3);  // base misalignment in floats
+    const bool item_ok = a->z_stride_b % 4 == 0 || a->B == 1;
+    if (want == ZMODE_TMA && item_ok) {
+        if (encode_tiled_fn enc = get_encode_tiled()) {
+            int lg = (a->z_stride_d % 4 == 0 && al == 0) ? 0 : (a->z_stride_d % 2 == 0) ? 1 : 2;
+            if (const char *env = getenv("VRVQ_DEBUG_ZNC_LOG2")) lg = atoi(env) > lg && atoi(env) <= 2 ? atoi(env) : lg;  // more classes than needed is always legal
+            const int nc = 1 << lg;
+            bool ok = true;
+            for (int k = 0; k < nc && ok; ++k) {
+                const int sk = (int)((al + (long long)k * a->z_stride_d) & 3);
+                const float *base = a->z + (long long)k * a->z_stride_d - sk;
+                // x extent rounded up to a 16-byte multiple: an extent of e.g. 86 floats makes the TMA unit fault at run time (found on
+                // B200, not rejected by cuTensorMapEncodeTiled).  The <= 3 extra elements are the next row's first ones (or lie in the
+                // 16-byte granule of the tensor's last element): frames >= T, which the kernel never uses.
+                const cuuint64_t dims[3] = {((cuuint64_t)a->T + (cuuint64_t)sk + 3ull) & ~3ull, (cuuint64_t)(a->input_dim / nc), (cuuint64_t)a->B};
+                const cuuint64_t strides[2] = {(cuuint64_t)nc * (cuuint64_t)a->z_stride_d * 4ull,
+                                               a->B == 1 ? (cuuint64_t)nc * (cuuint64_t)a->z_stride_d * 4ull * (cuuint64_t)(a->input_dim / nc) : (cuuint64_t)a->z_stride_b * 4ull};
+                const cuuint32_t box[3] = {(cuuint32_t)Z_PITCH, (cuuint32_t)(Z_CH / nc), 1u};
+                const cuuint32_t estr[3] = {1u, 1u, 1u};
+                ok = enc(&maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                P.zshift[k] = sk;
+                if (getenv("VRVQ_DEBUG_ZMAP"))
+                    fprintf(stderr, "[vrvq zmap] class %d/%d: ok=%d shift=%d base%%16=%d dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)\n", k, nc, (int)ok, sk,
+                            (int)(reinterpret_cast<uintptr_t>(base) % 16), (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                            (unsigned long long)strides[0], (unsigned long long)strides[1], box[0], box[1], box[2]);
+            }
+            if (ok) {
+                P.znc_log2 = lg;
+                return ZMODE_TMA;
+            }
+        }
+    }
+    for (int k = 0; k < 4; ++k) P.zshift[k] = 0;
+    return ZMODE_BULK;
+}
+
+static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParams &P, int *grid, ZMaps *zmap) {
     P.e = e;
     const BlobLayout L(a->input_dim, a->codebook_size);
     const size_t tc_off = (size_t)BLOB_HDR_FLOATS + (size_t)a->n_codebooks * (size_t)L.stage_floats();
     P.tc = static_cast<const float *>(a->blob) + tc_off;
-    int dev = 0, sms = 0;
-    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
-    if (rc) return rc;
-    rc = check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
-    if (rc) return rc;
+    const int sms = current_sm_count();
+    if (sms <= 0) {
+        set_error("cannot query the SM count of the current device");
+        return VRVQ_ECUDA;
+    }
     pick_tiling(a->B, a->T, sms, &P.adv, &P.tiles_per_b);
     if (const char *dbg = getenv("VRVQ_DEBUG_TILE_FRAMES")) {  // profiling knob
         const int v = atoi(dbg);
         if (v >= 8 && v <= 120 && v % 8 == 0) { P.adv = v; P.tiles_per_b = (a->T + v - 1) / v; }
     }
     P.n_tiles = P.tiles_per_b * a->B;
+    P.zmode = pick_zmode(a, zmap, P);
     *grid = P.n_tiles < sms ? P.n_tiles : sms;
     return VRVQ_OK;
 }
 
 template <int D, bool ZQIS, bool PROFILE, bool FC = false>
-static int launch_tc_one(const TcParams &P, int grid, cudaStream_t st) {
+static int launch_tc_one(const TcParams &P, const ZMaps &zmap, int grid, cudaStream_t st) {
     int rc = ensure_dynamic_smem<rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC>>(SM_TOTAL, "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
     if (rc) return rc;
-    rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC><<<grid, TC_NTH, SM_TOTAL, st>>>(P);
+    rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC><<<grid, TC_NTH, SM_TOTAL, st>>>(P, zmap);
     return check_cuda(cudaGetLastError(), "rvq_encode_tc_kernel launch");
 }
 template <int D, bool ZQIS>
-static int launch_tc(const TcParams &P, int grid, cudaStream_t st) {
+static int launch_tc(const TcParams &P, const ZMaps &zmap, int grid, cudaStream_t st) {
     // the phase-counter build (VRVQ_DEBUG_PHASES=1) is a separate instantiation: the production kernel carries no counters
     const char *dbg = getenv("VRVQ_DEBUG_PHASES");
-    const bool full = P.e.phase_cycles != nullptr && !(dbg != nullptr && dbg[0] == '2');  // "2": production code + 3 timestamps per CTA
-    return full ? launch_tc_one<D, ZQIS, true>(P, grid, st) : launch_tc_one<D, ZQIS, false>(P, grid, st);
+    const bool full = P.e.phase_cycles != nullptr && !(dbg != nullptr && dbg[0] == '2');  // "2": production code + 3 timestamps per CTA; "3": per-chunk trace
+    return full ? launch_tc_one<D, ZQIS, true>(P, zmap, grid, st) : launch_tc_one<D, ZQIS, false>(P, zmap, grid, st);
 }
 
 int encode_tc_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem) {
@@ -1069,8 +1293,9 @@ int encode_tc_launch_info(const vrvq_encode_args *a, int *grid, int *block, int 
     int rc = fill_encode_params(a, e);
     if (rc) return rc;
     TcParams P{};
+    ZMaps zmap;
     int g = 0;
-    rc = make_params(a, e, P, &g);
+    rc = make_params(a, e, P, &g, &zmap);
     if (rc) return rc;
     if (grid) *grid = g;
     if (block) *block = TC_NTH;
@@ -1080,8 +1305,9 @@ int encode_tc_launch_info(const vrvq_encode_args *a, int *grid, int *block, int 
 
 int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
     TcParams P{};
+    ZMaps zmap;
     int grid = 0;
-    int rc = make_params(a, e, P, &grid);
+    int rc = make_params(a, e, P, &grid, &zmap);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool zqis = a->z_q_is != nullptr;
@@ -1089,10 +1315,11 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
     P.e.phase_cycles = nullptr;
     if (dbg && cudaMalloc(&P.e.phase_cycles, sizeof(long long) * 64 * (size_t)grid) != cudaSuccess) P.e.phase_cycles = nullptr;
     if (P.e.phase_cycles != nullptr) cudaMemsetAsync(P.e.phase_cycles, 0, sizeof(long long) * 64 * (size_t)grid, st);
+    P.trace = (dbg && getenv("VRVQ_DEBUG_PHASES")[0] == '3' && grid >= 32) ? 1 : 0;
     switch (a->input_dim) {
-        case 1024: rc = zqis ? launch_tc<1024, true>(P, grid, st) : launch_tc<1024, false>(P, grid, st); break;
-        case 512: rc = zqis ? launch_tc<512, true>(P, grid, st) : launch_tc<512, false>(P, grid, st); break;
-        case 256: rc = zqis ? launch_tc<256, true>(P, grid, st) : launch_tc<256, false>(P, grid, st); break;
+        case 1024: rc = zqis ? launch_tc<1024, true>(P, zmap, grid, st) : launch_tc<1024, false>(P, zmap, grid, st); break;
+        case 512: rc = zqis ? launch_tc<512, true>(P, zmap, grid, st) : launch_tc<512, false>(P, zmap, grid, st); break;
+        case 256: rc = zqis ? launch_tc<256, true>(P, zmap, grid, st) : launch_tc<256, false>(P, zmap, grid, st); break;
         default: rc = VRVQ_EUNSUPPORTED;
     }
     if (dbg && P.e.phase_cycles != nullptr) {
@@ -1106,6 +1333,23 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
         cudaStreamSynchronize(st);
         cudaMemcpy(h, P.e.phase_cycles, sizeof(long long) * 64 * (size_t)grid, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[vrvq tc phases] grid %d, tile %d frames, %d tiles; mean cycles per CTA\n", grid, P.adv, P.n_tiles);
+        if (P.trace) {
+            static const char *ev[8] = {"z_full", "split", "a_empty", "a_handed", "iss_saw", "iss_done", "w_empty", "drain"};
+            long long t0 = 0;
+            for (int e = 0; e < 7; ++e)
+                for (int c = 0; c < 32; ++c) { const long long v = h[1024 + 32 * e + c]; if (v != 0 && (t0 == 0 || v < t0)) t0 = v; }
+            fprintf(stderr, "[vrvq tc trace] block 0, first tile, cycles since the first event; chunk:");
+            for (int e = 0; e < 8; ++e) fprintf(stderr, " %s", ev[e]);
+            fprintf(stderr, "\n");
+            for (int c = 0; c < 32; ++c) {
+                fprintf(stderr, "  %2d:", c);
+                for (int e = 0; e < 8; ++e) { const long long v = h[1024 + 32 * e + c]; fprintf(stderr, " %7lld", v ? v - t0 : -1); }
+                fprintf(stderr, "\n");
+            }
+            free(h);
+            cudaFree(P.e.phase_cycles);
+            return rc;
+        }
         if (getenv("VRVQ_DEBUG_PHASES")[0] == '2') {
             double a0 = 0, a1 = 0;
             for (int g = 0; g < grid; ++g) { a0 += (double)h[g * 64 + 0] / grid; a1 += (double)h[g * 64 + 1] / grid; }
@@ -1155,19 +1399,22 @@ int from_codes_tc(const vrvq_from_codes_args *a, void *stream) {
     P.codes_in = reinterpret_cast<const long long *>(a->codes); P.cin_sb = a->codes_stride_b; P.cin_sq = a->codes_stride_q;
     P.mask_in = a->mask; P.min_sb = a->mask_stride_b; P.min_sq = a->mask_stride_q;
     P.error_flag = a->error_flag;
-    int dev = 0, sms = 0;
-    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
-    if (rc) return rc;
-    rc = check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
-    if (rc) return rc;
+    const int sms = current_sm_count();
+    if (sms <= 0) {
+        set_error("cannot query the SM count of the current device");
+        return VRVQ_ECUDA;
+    }
     pick_tiling(a->B, a->T, sms, &P.adv, &P.tiles_per_b);
     P.n_tiles = P.tiles_per_b * a->B;
+    P.zmode = ZMODE_LDG;  // no latent on this path
+    ZMaps zmap;
+    memset(&zmap, 0, sizeof(zmap));
     const int grid = P.n_tiles < sms ? P.n_tiles : sms;
     const bool zqis = a->z_q_is != nullptr;
     switch (a->input_dim) {
-        case 1024: return zqis ? launch_tc_one<1024, true, false, true>(P, grid, st) : launch_tc_one<1024, false, false, true>(P, grid, st);
-        case 512: return zqis ? launch_tc_one<512, true, false, true>(P, grid, st) : launch_tc_one<512, false, false, true>(P, grid, st);
-        case 256: return zqis ? launch_tc_one<256, true, false, true>(P, grid, st) : launch_tc_one<256, false, false, true>(P, grid, st);
+        case 1024: return zqis ? launch_tc_one<1024, true, false, true>(P, zmap, grid, st) : launch_tc_one<1024, false, false, true>(P, zmap, grid, st);
+        case 512: return zqis ? launch_tc_one<512, true, false, true>(P, zmap, grid, st) : launch_tc_one<512, false, false, true>(P, zmap, grid, st);
+        case 256: return zqis ? launch_tc_one<256, true, false, true>(P, zmap, grid, st) : launch_tc_one<256, false, false, true>(P, zmap, grid, st);
         default: return VRVQ_EUNSUPPORTED;
     }
 }
