@@ -400,7 +400,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(CFG["workload"]),
-                         "kernel": "rvq_encode_tc_kernel<1024,true> (tcgen05 kind::tf32)" if info["block"] == 480 else "rvq_encode_kernel<1024,1024> (CUDA cores)",
+                         "kernel": "rvq_encode_tc_kernel<1024,true> (tcgen05 kind::tf32, TMA-staged latent)" if info["kernel"] == "tc" else "rvq_encode_kernel<1024,1024> (CUDA cores)",
                          "algorithmic_bytes_per_frame": algorithmic_bytes_per_frame(D, Nq, True), "frames_per_launch": frames,
                          "launch_us": launch_ms * 1e3, "peak_source": peak_src, "grid": info["grid"], "block": info["block"],
                          "smem_bytes": info["smem_bytes"]},

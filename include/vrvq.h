@@ -122,6 +122,10 @@ int vrvq_rvq_encode_f32(const vrvq_encode_args *args, void *stream);
 /* Number of CTAs / dynamic shared memory bytes the encode launch would use (bench/roofline reporting). */
 int vrvq_rvq_encode_launch_info(const vrvq_encode_args *args, int *grid, int *block, int *smem_bytes);
 
+/* Which kernel vrvq_rvq_encode_f32 would launch for these arguments: "tc" = rvq_encode_tc_kernel (tcgen05 tensor cores),
+ * "cuda" = rvq_encode_kernel (CUDA cores); NULL (and an error message) for invalid arguments.  Static strings. */
+const char *vrvq_rvq_encode_kernel_name(const vrvq_encode_args *args);
+
 /* ---------------------------------------------------------------------------------------------
  * Decode side.  Replaces ResidualVectorQuantize.from_codes, models/quantize.py:217-249
  * (z_q = sum_i out_proj_i(codebook_i[codes_i]); z_p = the gathered raw rows).

@@ -54,7 +54,7 @@ def assert_kernel(impl, m_or_pw, B, T, n_run, z_q_is=False):
     info = ops.encode_launch_info(pw, B, T, n_run, "cuda")
     if impl == "tc" and not ops.tc_kernel_available(pw, n_run, z_q_is=z_q_is):
         pytest.skip("no tensor-core kernel for this shape (the call is served by the CUDA-core kernel, covered by the other parameter)")
-    assert (info["block"] != 512) == (impl == "tc"), (impl, info)
+    assert info["kernel"] == impl, (impl, info)
 
 
 def test_extension_is_loaded():

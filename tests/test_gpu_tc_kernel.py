@@ -43,12 +43,12 @@ def test_tc_kernel_is_the_default_path():
     pw = ops.PackedWeights.from_state_dict(sd, "cuda")
     tc = run_impl(None, lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda"))
     cc = run_impl("cuda", lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda"))
-    assert tc["block"] == 480 and cc["block"] == 512, (tc, cc)
+    assert tc["kernel"] == "tc" and tc["block"] == 512 and cc["kernel"] == "cuda", (tc, cc)
     assert tc["grid"] == 144  # 9 tiles of 96 frames per item: one wave on 148 SMs
     small = run_impl(None, lambda: ops.encode_launch_info(pw, 1, 87, 8, "cuda"))
-    assert small["block"] == 512, "calls that fit one wave of the CUDA-core kernel stay on it (lower latency)"
+    assert small["kernel"] == "cuda", "calls that fit one wave of the CUDA-core kernel stay on it (lower latency)"
     forced = run_impl("tc", lambda: ops.encode_launch_info(pw, 1, 87, 8, "cuda"))
-    assert forced["block"] == 480
+    assert forced["kernel"] == "tc"
 
 
 @pytest.mark.parametrize("D,Nq,B,T,n_run,vbr", [

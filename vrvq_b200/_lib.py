@@ -52,7 +52,7 @@ class FromCodesArgs(C.Structure):
 # every symbol include/vrvq.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "vrvq_abi_version", "vrvq_last_error", "vrvq_supported", "vrvq_blob_bytes", "vrvq_pack_weights",
-    "vrvq_blob_codebook", "vrvq_rvq_encode_f32", "vrvq_rvq_encode_launch_info", "vrvq_from_codes_f32",
+    "vrvq_blob_codebook", "vrvq_rvq_encode_f32", "vrvq_rvq_encode_launch_info", "vrvq_rvq_encode_kernel_name", "vrvq_from_codes_f32",
     "vrvq_search_latents_f32", "vrvq_generate_mask_hard_f32", "vrvq_mask_sum_f32", "vrvq_remask_f32",
     "vrvq_pack_codes_u16", "vrvq_unpack_codes_u16", "vrvq_conv3_packed_floats", "vrvq_pack_conv3_weights", "vrvq_snake_conv3_f32",
 ]
@@ -87,6 +87,8 @@ def lib():
     L.vrvq_blob_codebook.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
     L.vrvq_rvq_encode_f32.argtypes = [C.POINTER(EncodeArgs), C.c_void_p]
     L.vrvq_rvq_encode_launch_info.argtypes = [C.POINTER(EncodeArgs), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.vrvq_rvq_encode_kernel_name.restype = C.c_char_p
+    L.vrvq_rvq_encode_kernel_name.argtypes = [C.POINTER(EncodeArgs)]
     L.vrvq_from_codes_f32.argtypes = [C.POINTER(FromCodesArgs), C.c_void_p]
     L.vrvq_search_latents_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]

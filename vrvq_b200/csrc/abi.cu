@@ -47,6 +47,7 @@ int check_device() {
 int encode_supported(int D, int K, int cd);
 int encode(const vrvq_encode_args *a, void *stream);
 int encode_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem);
+const char *encode_kernel_name(const vrvq_encode_args *a);
 int launch_mask_hard(const float *x, long long x_sb, int B, int T, int nq, float *mask, long long m_sb, long long m_sq, cudaStream_t st);
 int launch_mask_sum(const float *mask, long long m_sb, long long m_sq, int B, int T, int nq, double *sums, cudaStream_t st);
 int launch_remask(const float *zis, long long s_b, long long s_q, long long s_d, const float *imp, long long imp_sb, float level_scaled,
@@ -265,6 +266,8 @@ int vrvq_rvq_encode_f32(const vrvq_encode_args *args, void *stream) { return enc
 int vrvq_rvq_encode_launch_info(const vrvq_encode_args *args, int *grid, int *block, int *smem_bytes) {
     return encode_launch_info(args, grid, block, smem_bytes);
 }
+
+const char *vrvq_rvq_encode_kernel_name(const vrvq_encode_args *args) { return encode_kernel_name(args); }
 
 int vrvq_from_codes_f32(const vrvq_from_codes_args *args, void *stream) {
     int rc = check_device();

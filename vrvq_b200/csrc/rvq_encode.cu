@@ -733,6 +733,12 @@ static bool use_tc(const vrvq_encode_args *a) {
     return encode_tc_usable(a) != 0 && prefer_tc_for_size(a->B, a->T);
 }
 
+const char *encode_kernel_name(const vrvq_encode_args *a) {
+    EncodeParams p{};
+    if (fill_encode_params(a, p)) return nullptr;
+    return use_tc(a) ? "tc" : "cuda";
+}
+
 int encode_launch_info(const vrvq_encode_args *a, int *grid, int *block, int *smem) {
     EncodeParams p{};
     int rc = fill_encode_params(a, p);

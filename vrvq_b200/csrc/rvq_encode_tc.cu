@@ -45,7 +45,7 @@
 namespace vrvq {
 
 constexpr int TCK = 1024;      // codebook size
-constexpr int TC_NTH = 480;    // 15 warps: 8 search/load, 4 epilogue, MMA issuer, copy producer, search-MMA issuer
+constexpr int TC_NTH = 512;    // 16 warps: 8 search/load, 4 epilogue, MMA issuer, copy producer, search-MMA issuer / latent producer, second phase-L MMA issuer
 constexpr int TC_NSEARCH = 256;
 
 // shared memory map (bytes).  Phase L uses [0, 49152); phase S re-uses that region.
@@ -83,7 +83,7 @@ static_assert(SM_ZR % 128 == 0 && Z_SLOT % 128 == 0, "TMA destinations are 128-b
 enum {
     B_L_FULL = 0, B_L_EMPTY = 4, B_SET_FULL = 24, B_SET_EMPTY = 26, B_W_FULL = 28, B_W_EMPTY = 32,
     B_D_FULL = 36, B_D_EMPTY = 38, B_CB_FULL = 40, B_A_READY = 42, B_ZQ_READY = 50, B_MMA_DONE = 51, B_F_FULL = 52, B_F_EMPTY = 56,
-    B_E_READY = 60, B_SB_FULL = 61, B_SB_EMPTY = 64, B_Z_FULL = 67, B_Z_EMPTY = 70, B_COUNT = 73
+    B_E_READY = 60, B_SB_FULL = 61, B_SB_EMPTY = 64, B_Z_FULL = 67, B_Z_EMPTY = 70, B_L_FULL2 = 73, B_COUNT = 76
 };
 enum { ZMODE_LDG = 0, ZMODE_BULK = 1, ZMODE_TMA = 2 };  // how phase L fetches the latent
 
@@ -147,6 +147,8 @@ struct TcParams {
     int zmode;        // ZMODE_*
     int znc_log2;     // ZMODE_TMA: log2 of the number of channel classes (1, 2 or 4 tensor maps; see pick_zmode)
     int zshift[4];    // ZMODE_TMA: x offset of frame 0 in the rows of class k
+    int single_issuer;  // debugging knob
+    int stagger;      // cycles of start delay per (blockIdx % 8): de-synchronises the CTAs' W_in chunk requests (L2 hot spot)
     int trace;        // VRVQ_DEBUG_PHASES=3 (profiling instantiation only): block 0 records per-chunk timestamps of its first tile's phase L
     // from_codes mode (FC): codes [B][n_run][T] are an input, mask_in an optional 0/1 mask [B][n_run][T], error_flag is set when
     // a code lies outside [0, K)
@@ -212,9 +214,10 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     // ---- one-time setup -------------------------------------------------------------------------------------
     if (tid == 0) {
         // phase-L slot: 8 loader warps + the producer's expect_tx arrive; released by one tcgen05.commit
-        for (int i = 0; i < L_SLOTS; ++i) { mbar_init(&bars[B_L_FULL + i], 9); mbar_init(&bars[B_L_EMPTY + i], 1); }
+        // (a slot has two full barriers, for its even and its odd uses: see l_full)
+        for (int i = 0; i < L_SLOTS; ++i) { mbar_init(&bars[B_L_FULL + i], 9); mbar_init(&bars[B_L_FULL2 + i], 9); mbar_init(&bars[B_L_EMPTY + i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars[B_SET_FULL + i], 1); mbar_init(&bars[B_SET_EMPTY + i], 4);
+            mbar_init(&bars[B_SET_FULL + i], 2); mbar_init(&bars[B_SET_EMPTY + i], 4);  // full: one commit per phase-L issuer
             mbar_init(&bars[B_D_FULL + i], 1); mbar_init(&bars[B_D_EMPTY + i], 4);
             mbar_init(&bars[B_CB_FULL + i], 1);
         }
@@ -243,6 +246,11 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     tmem_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t smem_base = smem_u32(smem);
+    if (P.stagger > 0) {
+        const long long until = clock64() + (long long)P.stagger * (long long)(blockIdx.x & 7);
+        while (clock64() < until) {
+        }
+    }
 
     // profiling only (VRVQ_DEBUG_PHASES=1): clock64 totals per phase for one thread of each role
     const int ph_role = tid == 0 ? 0 : tid == 256 ? 1 : tid == 384 ? 2 : tid == 416 ? 3 : -1;
@@ -266,6 +274,16 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     // 7 drains: [4g] accumulator set full, [4g+1] drained)
     auto trace = [&](int ev, int idx) {
         if (PROFILE && P.trace && blockIdx.x == 0 && p.phase_cycles != nullptr) p.phase_cycles[1024 + 32 * ev + idx] = clock64();
+    };
+
+    // Full barrier of phase-L chunk n (slot n % 3, use n / 3).  Consecutive uses of a slot belong to different issuing threads
+    // (3 is odd), and a parity wait can only tell the current phase from the previous one: an issuer that ran one use ahead of
+    // the other would see "complete" for a slot that is still being filled.  So even and odd uses get their own barrier, each
+    // waited on by one thread, in order.  Returns the barrier; *parity = the phase parity of use n / 3 on it.
+    auto l_full = [&](uint32_t n, uint32_t *parity) -> uint64_t * {
+        const uint32_t sl = n % L_SLOTS, use = n / L_SLOTS;
+        *parity = (use >> 1) & 1u;
+        return &bars[((use & 1u) ? B_L_FULL2 : B_L_FULL) + sl];
     };
 
     double loss_acc = 0.0;               // frame threads
@@ -316,6 +334,43 @@ auto drain = [&](int g, uint32_t tq) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[B_SET_EMPTY + set]);
             if (PROFILE && tid == 256 && it == 0) trace(7, 4 * g + 1);
+        };
+        // Phase-L MMA issue, split over two issuing threads (lane 0 of warps 12 and 15): issuer X takes the chunks c % 2 == X and
+        // accumulates all three 3xTF32 products of its chunks -- hi*W_hi + hi*W_lo + lo*W_hi, three N = 64 MMAs per k-step -- into its
+        // own 64 columns of the current accumulator set (columns [64 X, 64 X + 64) of TM_SET + 128 set; the drain adds the two
+        // halves).  A tcgen05.mma blocks its issuing thread while the tensor pipe is busy and a completed mbarrier wait costs
+        // ~170 cycles, so one thread alone alternates between the two (trace: 370 + 730 cycles per chunk); two threads overlap them.
+        auto issue_phase_l = [&](int X0) {
+            constexpr uint32_t ID_64 = umma_idesc_tf32(128, 64);
+            const bool solo = P.single_issuer != 0;  // debugging knob (VRVQ_DEBUG_SINGLE_ISSUER=1): issuer 0 takes every chunk
+            if (solo && X0 == 1) {
+                return;
+            }
+            for (int c = X0; c < NCH; c += solo ? 1 : 2) {
+                const int X = c & 1;
+                const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS;
+                {
+                    uint32_t par;
+                    uint64_t *fb = l_full(n, &par);
+                    TC_WAIT(fb, par);
+                }
+                if (PROFILE && it == 0 && X == 0) trace(4, c);
+                const uint32_t gg = gbase + (uint32_t)(c >> 2), set = gg & 1u;
+                if ((c & 3) == X && gg >= 2) TC_WAIT(&bars[B_SET_EMPTY + set], ((gg >> 1) - 1) & 1u);
+                tmem_fence_after_sync();
+                const uint32_t a_hi = tmem + TM_AL + 64u * sl, a_lo = a_hi + 32;  // A in tensor memory: 8 columns per k-step
+                const uint64_t bh = desc128(smem_base + SM_LR + sl * L_SLOT), bl = bh + (1024 >> 4);  // B rows 0-63 heads, 64-127 remainders
+                const uint32_t d = tmem + TM_SET + 128u * set + 64u * (uint32_t)X;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    umma_tf32_ts(d, a_lo + 8 * ks, bh + ks * (4096 >> 4), ID_64, (c & 3) != X || ks != 0);  // smallest terms first
+                    umma_tf32_ts(d, a_hi + 8 * ks, bl + ks * (4096 >> 4), ID_64, true);
+                    umma_tf32_ts(d, a_hi + 8 * ks, bh + ks * (4096 >> 4), ID_64, true);
+                }
+                umma_commit(&bars[B_L_EMPTY + sl]);
+                if ((c & 3) == 2 + X) umma_commit(&bars[B_SET_FULL + set]);
+                if (PROFILE && it == 0 && X == 0) trace(5, c);
+            }
         };
         if (w < 8) {
             // =====================================================================================================
@@ -405,7 +460,7 @@ auto drain = [&](int g, uint32_t tq) {
                         tmem_wait_st();
                         tmem_fence_before_sync();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars[B_L_FULL + sl]);
+                        if (lane == 0) { uint32_t par_; mbar_arrive(l_full(n, &par_)); }
                         if (PROFILE && tid == 0 && it == 0) trace(3, c);
                     }
                 };
@@ -457,7 +512,7 @@ auto drain = [&](int g, uint32_t tq) {
                         tmem_wait_st();
                         tmem_fence_before_sync();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars[B_L_FULL + sl]);
+                        if (lane == 0) { uint32_t par_; mbar_arrive(l_full(n, &par_)); }
                     }
                 }
             }
@@ -850,28 +905,7 @@ auto drain = [&](int g, uint32_t tq) {
             // MMA issuer: lane 0 of warp 12.
             // =====================================================================================================
             constexpr uint32_t ID_128 = umma_idesc_tf32(128, 128), ID_64 = umma_idesc_tf32(128, 64), ID_32 = umma_idesc_tf32(128, 32);
-            if (!FC && lane == 0) {
-                for (int c = 0; c < NCH; ++c) {
-                    const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS;
-                    TC_WAIT(&bars[B_L_FULL + sl], (n / L_SLOTS) & 1u);
-                    if (PROFILE && it == 0) trace(4, c);
-                    const uint32_t gg = gbase + (uint32_t)(c >> 2), set = gg & 1u;
-                    if ((c & 3) == 0 && gg >= 2) TC_WAIT(&bars[B_SET_EMPTY + set], ((gg >> 1) - 1) & 1u);
-                    tmem_fence_after_sync();
-                    const uint32_t a_hi = tmem + TM_AL + 64u * sl, a_lo = a_hi + 32;  // A in tensor memory: 8 columns per k-step
-                    const uint64_t bw = desc128(smem_base + SM_LR + sl * L_SLOT);
-                    const uint32_t d = tmem + TM_SET + 128u * set;
-                    // [hi*hi | hi*lo] in one N = 128 MMA (B rows 0-63 heads, 64-127 remainders), lo*hi added to the second half
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        umma_tf32_ts(d, a_hi + 8 * ks, bw + ks * (4096 >> 4), ID_128, (c & 3) != 0 || ks != 0);
-                        umma_tf32_ts(d + 64, a_lo + 8 * ks, bw + ks * (4096 >> 4), ID_64, true);
-                    }
-                    umma_commit(&bars[B_L_EMPTY + sl]);
-                    if ((c & 3) == 3) umma_commit(&bars[B_SET_FULL + set]);
-                    if (PROFILE && it == 0) trace(5, c);
-                }
-            }
+            if (!FC && lane == 0) issue_phase_l(0);
             ph_mark(0);
             __syncwarp();
             tmem_fence_before_sync();
@@ -971,6 +1005,15 @@ auto drain = [&](int g, uint32_t tq) {
                 }
             }
             __syncwarp();
+        } else if (w == 15) {
+            // =====================================================================================================
+            // Second phase-L MMA issuer: lane 0 of warp 15 (odd chunks); idle afterwards.
+            // =====================================================================================================
+            if (!FC && lane == 0) issue_phase_l(1);
+            __syncwarp();
+            tmem_fence_before_sync();
+            __syncthreads();  // L -> S
+            tmem_fence_after_sync();
         } else if (w == 14) {
             // =====================================================================================================
             // Search-MMA issuer: lane 0 of warp 14.  Per stage, NSC MMAs of M = 128 frames x N = SCW codes x K = 8 (plain TF32)
@@ -1051,8 +1094,10 @@ auto drain = [&](int g, uint32_t tq) {
                     const uint32_t m = lbase + (uint32_t)c, slot = m % L_SLOTS, use = m / L_SLOTS;
                     if (use >= 1) TC_WAIT(&bars[B_L_EMPTY + slot], (use - 1) & 1u);
                     if (PROFILE && it == 0) trace(6, c);
-                    mbar_arrive_expect_tx(&bars[B_L_FULL + slot], 16384);
-                    bulk_g2s(smem + SM_LR + slot * L_SLOT, win + (size_t)c * 4096, 16384, &bars[B_L_FULL + slot]);
+                    uint32_t par_;
+                    uint64_t *fb = l_full(m, &par_);
+                    mbar_arrive_expect_tx(fb, 16384);
+                    bulk_g2s(smem + SM_LR + slot * L_SLOT, win + (size_t)c * 4096, 16384, fb);
                 }
             }
             ph_mark(0);
@@ -1269,6 +1314,8 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
     }
     P.n_tiles = P.tiles_per_b * a->B;
     P.zmode = pick_zmode(a, zmap, P);
+    P.single_issuer = getenv("VRVQ_DEBUG_SINGLE_ISSUER") != nullptr;
+    P.stagger = getenv("VRVQ_DEBUG_STAGGER") ? atoi(getenv("VRVQ_DEBUG_STAGGER")) : 0;
     *grid = P.n_tiles < sms ? P.n_tiles : sms;
     return VRVQ_OK;
 }

@@ -184,7 +184,8 @@ def encode_launch_info(w: PackedWeights, B: int, T: int, n_run: int, device):
     g, b, s = C.c_int(), C.c_int(), C.c_int()
     with torch.cuda.device(device):
         check(_lib.lib().vrvq_rvq_encode_launch_info(C.byref(a), C.byref(g), C.byref(b), C.byref(s)), "vrvq_rvq_encode_launch_info")
-    return {"grid": g.value, "block": b.value, "smem_bytes": s.value}
+        name = _lib.lib().vrvq_rvq_encode_kernel_name(C.byref(a))
+    return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "kernel": name.decode() if name else None}
 
 
 def tc_kernel_available(w: PackedWeights, n_run: int, z_q_is: bool = False) -> bool:
