@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include <cstdint>
 
 #include "common.cuh"
@@ -102,18 +103,53 @@ static void pack_tc_section(int Nq, int D, int K, const float *w_in, const float
                             const float *codebook, float *tc) {
     const TcLayout T(D, Nq);
     memset(tc, 0, sizeof(float) * (size_t)T.total());
-    // WIN: chunk c = channels 32c..32c+31 (k = channel - 32c); rows 0..63 heads (row = 8*stage + out-channel), rows 64..127 remainders
-    for (int c = 0; c < T.nch(); ++c) {
-        float *tile = tc + T.off_win() + (size_t)c * 4096;
-        for (int s = 0; s < Nq; ++s)
-            for (int oc = 0; oc < CD; ++oc)
-                for (int k = 0; k < 32; ++k) {
-                    const float x = w_in[((size_t)s * CD + oc) * D + 32 * c + k];
-                    const float h = tf32_head(x);
-                    tile[umma_idx(128, 8 * s + oc, k)] = h;
-                    tile[umma_idx(128, 64 + 8 * s + oc, k)] = x - h;
+    // WIN: group g, chunk c = channels 32c..32c+31 (k = channel - 32c); rows 0..63 heads (row = 8*(stage - 8g) + out-channel), rows 64..127 remainders
+    for (int g = 0; g < T.ngrp(); ++g)
+        for (int c = 0; c < T.nch(); ++c) {
+            float *tile = tc + T.off_win() + ((size_t)g * T.nch() + c) * 4096;
+            for (int s = 8 * g; s < Nq && s < 8 * g + 8; ++s)
+                for (int oc = 0; oc < CD; ++oc)
+                    for (int k = 0; k < 32; ++k) {
+                        const float x = w_in[((size_t)s * CD + oc) * D + 32 * c + k];
+                        const float h = tf32_head(x);
+                        tile[umma_idx(128, 8 * (s - 8 * g) + oc, k)] = h;
+                        tile[umma_idx(128, 64 + 8 * (s - 8 * g) + oc, k)] = x - h;
+                    }
+        }
+    // G[s][j] = W_in[s] W_out[j] (8x8) and gv[s][j] = W_in[s] b_out[j] for all j < s, in binary64
+    std::vector<double> Gd((size_t)Nq * Nq * 72, 0.0);
+    for (int j = 0; j < Nq; ++j)
+        for (int s = j + 1; s < Nq; ++s) {
+            double *G = Gd.data() + ((size_t)s * Nq + j) * 72;
+            for (int c = 0; c < CD; ++c) {
+                const float *wi = w_in + ((size_t)s * CD + c) * D;
+                for (int k = 0; k < CD; ++k) {
+                    double acc = 0.0;
+                    for (int d = 0; d < D; ++d) acc += (double)wi[d] * (double)w_out[((size_t)j * D + d) * CD + k];
+                    G[c * 8 + k] = acc;
                 }
-    }
+                double acc = 0.0;
+                for (int d = 0; d < D; ++d) acc += (double)wi[d] * (double)b_out[(size_t)j * D + d];
+                G[64 + c] = acc;
+            }
+        }
+    // GX: virtual-channel chunks of group g >= 1 (cross-group corrections as extra K of the in_proj GEMM): B = -G[s][j]
+    for (int g = 1; g < T.ngrp(); ++g)
+        for (int v = 0; v < TcLayout::vp(g); ++v) {
+            float *tile = tc + T.off_gx() + (size_t)(TcLayout::gx_base(g) + v) * 4096;
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * v + jj;
+                if (j >= 8 * g) continue;  // padding chunk / stage of this or a later group: zero
+                for (int s = 8 * g; s < Nq && s < 8 * g + 8; ++s)
+                    for (int c = 0; c < CD; ++c)
+                        for (int kk = 0; kk < CD; ++kk) {
+                            const float x = (float)(-Gd[((size_t)s * Nq + j) * 72 + c * 8 + kk]);
+                            const float h = tf32_head(x);
+                            tile[umma_idx(128, 8 * (s - 8 * g) + c, 8 * jj + kk)] = h;
+                            tile[umma_idx(128, 64 + 8 * (s - 8 * g) + c, 8 * jj + kk)] = x - h;
+                        }
+            }
+        }
     // WOUT / BOUT: row i of chunk j <-> channel 128j + 4(i%32) + i/32
     for (int j = 0; j < T.nj(); ++j)
         for (int i = 0; i < 128; ++i) {
@@ -130,28 +166,25 @@ static void pack_tc_section(int Nq, int D, int K, const float *w_in, const float
                 const float bh = tf32_head(bv);
                 bt[umma_idx(128, i, 0)] = bh;
                 bt[umma_idx(128, i, 1)] = bv - bh;
-                float *bhi = tc + T.off_bout() + (size_t)j * 2048, *blo = bhi + 1024;
-                bhi[umma_idx(128, i, s)] = bh;
-                blo[umma_idx(128, i, s)] = bv - bh;
+                float *bhi = tc + T.off_bout() + ((size_t)(s / 8) * T.nj() + j) * 2048, *blo = bhi + 1024;
+                bhi[umma_idx(128, i, s % 8)] = bh;
+                blo[umma_idx(128, i, s % 8)] = bv - bh;
             }
         }
-    // GG: for j < s: G = W_in[s] W_out[j] (8x8) and g = W_in[s] b_out[j], accumulated in binary64, rounded once
+    // GG: for j < s: G and g rounded once
     for (int j = 0; j < Nq; ++j)
         for (int s = j + 1; s < Nq; ++s) {
             float *G = tc + T.off_gg() + (size_t)TcLayout::pair_index(Nq, j, s) * 72;
-            for (int c = 0; c < CD; ++c) {
-                const float *wi = w_in + ((size_t)s * CD + c) * D;
-                for (int k = 0; k < CD; ++k) {
-                    double acc = 0.0;
-                    for (int d = 0; d < D; ++d) acc += (double)wi[d] * (double)w_out[((size_t)j * D + d) * CD + k];
-                    G[c * 8 + k] = (float)acc;
-                }
-                double acc = 0.0;
-                for (int d = 0; d < D; ++d) acc += (double)wi[d] * (double)b_out[(size_t)j * D + d];
-                G[64 + c] = (float)acc;
-            }
+            for (int i = 0; i < 72; ++i) G[i] = (float)Gd[((size_t)s * Nq + j) * 72 + i];
         }
     memcpy(tc + T.off_bin(), b_in, sizeof(float) * (size_t)Nq * CD);
+    // b_in' = b_in[s] - sum over the stages j of EARLIER groups of g[s][j] (the in-group terms stay in GG)
+    for (int s = 0; s < Nq; ++s)
+        for (int c = 0; c < CD; ++c) {
+            double acc = (double)b_in[(size_t)s * CD + c];
+            for (int j = 0; j < 8 * (s / 8); ++j) acc -= Gd[((size_t)s * Nq + j) * 72 + 64 + c];
+            tc[T.off_bin() + (size_t)Nq * CD + (size_t)s * CD + c] = (float)acc;
+        }
     // CBK: F.normalize(codebook) (same arithmetic as the P1 section) as a [2 kg][K][4] tile, then c2[K]
     for (int s = 0; s < Nq; ++s) {
         float *cbk = tc + T.off_cbk() + (size_t)s * 9216;

@@ -126,13 +126,18 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 // The TC section is appended to the blob after the per-stage sections (header.pad[0] = offset in floats, 0 = absent).
 // All operand tiles are stored in the canonical K-major no-swizzle UMMA layout: element (row r, k) of a tile with R rows
 // lives at float index ((k / 4) * R + r) * 4 + (k % 4), i.e. 8 rows x 16 bytes core matrices, SBO = 128 B, LBO = R * 16 B.
-//   WIN  [D/32 chunks][8 kg][128 rows][4]   in_proj B operand of one 32-channel chunk: rows 0..63 = TF32 heads of W_in
-//        (row n = 8*stage + out-channel, zero rows above 8*Nq), rows 64..127 = the remainders (W - head)
+// The stages are processed in groups of 8 (group g = stages 8g .. 8g+7; one group for models with <= 8 codebooks,
+// up to four: conf/base_24kbps.yml has 28):
+//   WIN  [groups][D/32 chunks][8 kg][128 rows][4]   in_proj B operand of one 32-channel chunk: rows 0..63 = TF32 heads of W_in
+//        (row n = 8*(stage - 8g) + out-channel, zero rows for absent stages), rows 64..127 = the remainders (W - head)
+//   GX   [sum_g vp(g)][8 kg][128 rows][4]   "virtual channel" chunks of group g >= 1: the cross-group corrections
+//        z_e[s] -= G[s][j] q_j (j < 8g) as extra K of the in_proj GEMM: chunk v covers stages j = 4v .. 4v+3 (k = 8 (j - 4v) + kk),
+//        B = -G[s][j][c][kk] (heads / remainders as in WIN); vp(g) = 2g rounded up to a multiple of 4 (zero chunks pad)
 //   WOUT [Nq][D/128 chunks][3072]: [hi | lo | bias] tiles of [2 kg][128 rows][4]; row i of chunk j = channel 128j + 4(i%32) + i/32;
 //        bias tile: k = 0 -> head of b_out, k = 1 -> remainder, other k zero (multiplied by a constant tile of ones)
-//   BOUT [D/128 chunks][hi,lo][2 kg][128 rows][4]  bias as a B operand for the final GEMM: element (row, k = stage) = b_out[stage][channel(row)]
+//   BOUT [groups][D/128 chunks][hi,lo][2 kg][128 rows][4]  bias as a B operand for the final GEMM: element (row, k) = b_out[8g + k][channel(row)]
 //   GG   [Nq(Nq-1)/2][72]  for j < s: G = W_in[s] W_out[j] (8x8, row-major [c][k]) followed by g = W_in[s] b_out[j] (8)
-//   BIN  [Nq][8] b_in
+//   BIN  [Nq][8] b_in, then [Nq][8] b_in' = b_in[s] - sum_{j < 8 (s / 8)} g[s][j]  (the cross-group bias terms folded in)
 //   CBK  [Nq][9216]: normalised codebook as a K-major B operand [2 kg][1024 codes][4] (also read row-wise for the exact re-scoring),
 //        then c2[1024]
 struct TcLayout {
@@ -140,17 +145,23 @@ struct TcLayout {
     __host__ __device__ constexpr TcLayout(int d, int nq) : D(d), Nq(nq) {}
     __host__ __device__ constexpr int nch() const { return D / 32; }
     __host__ __device__ constexpr int nj() const { return D / 128; }
+    __host__ __device__ constexpr int ngrp() const { return (Nq + 7) / 8; }
+    __host__ __device__ static constexpr int vp(int g) { return (2 * g + 3) / 4 * 4; }         // virtual chunks of group g
+    __host__ __device__ static constexpr int gx_base(int g) { return g <= 1 ? 0 : g == 2 ? 4 : g == 3 ? 8 : 16; }  // sum_{h<g} vp(h)
+    __host__ __device__ constexpr int gx_chunks() const { return gx_base(ngrp()); }
     __host__ __device__ constexpr int off_win() const { return 0; }
-    __host__ __device__ constexpr int off_wout() const { return nch() * 4096; }
+    __host__ __device__ constexpr int off_gx() const { return ngrp() * nch() * 4096; }
+    __host__ __device__ constexpr int off_wout() const { return off_gx() + gx_chunks() * 4096; }
     __host__ __device__ constexpr int off_bout() const { return off_wout() + Nq * nj() * 3072; }
-    __host__ __device__ constexpr int off_gg() const { return off_bout() + nj() * 2048; }
+    __host__ __device__ constexpr int off_gg() const { return off_bout() + ngrp() * nj() * 2048; }
     __host__ __device__ constexpr int gg_floats() const { return (Nq * (Nq - 1) / 2 * 72 + 3) / 4 * 4; }
     __host__ __device__ constexpr int off_bin() const { return off_gg() + gg_floats(); }
-    __host__ __device__ constexpr int off_cbk() const { return off_bin() + Nq * 8; }
+    __host__ __device__ constexpr int off_cbk() const { return off_bin() + 2 * Nq * 8; }
     __host__ __device__ constexpr int total() const { return off_cbk() + Nq * 9216; }
     __host__ __device__ static constexpr int pair_index(int nq, int j, int s) { return j * nq - j * (j + 1) / 2 + (s - j - 1); }
 };
-constexpr int TC_MAX_NQ = 8;
+constexpr int TC_MAX_NQ = 32;       // stages per model on the tensor-core path (4 groups of 8)
+constexpr int TC_MAX_NQ_ZQIS = 8;   // with the per-stage outputs z_q_is: one group (the per-stage out_proj ring shares the TMEM)
 __host__ __device__ constexpr bool tc_shape_ok(int D, int K, int Nq) { return K == 1024 && (D == 1024 || D == 512 || D == 256) && Nq >= 1 && Nq <= TC_MAX_NQ; }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
