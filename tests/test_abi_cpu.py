@@ -122,6 +122,34 @@ def test_module_surface_matches_reference_signatures():
         m(torch.zeros(1, 512, 4))
 
 
+def _tc_layout(Nq, D):
+    """Mirror of csrc/common.cuh TcLayout (float offsets inside the TC section)."""
+    nch, nj, ngrp = D // 32, D // 128, (Nq + 7) // 8
+    vp = lambda g: (2 * g + 3) // 4 * 4
+    gx_base = lambda g: sum(vp(h) for h in range(g))
+    L = dict(nch=nch, nj=nj, ngrp=ngrp, vp=vp, gx_base=gx_base, off_win=0)
+    L["off_gx"] = ngrp * nch * 4096
+    L["off_wout"] = L["off_gx"] + gx_base(ngrp) * 4096
+    L["off_bout"] = L["off_wout"] + Nq * nj * 3072
+    L["off_gg"] = L["off_bout"] + ngrp * nj * 2048
+    L["off_bin"] = L["off_gg"] + (Nq * (Nq - 1) // 2 * 72 + 3) // 4 * 4
+    L["off_cbk"] = L["off_bin"] + 2 * Nq * 8
+    L["total"] = L["off_cbk"] + Nq * 9216
+    return L
+
+
+def _tile_get(tile, rows, r, k):  # canonical K-major, no swizzle: 8-row x 16-byte core matrices
+    return tile[((k // 4) * rows + r) * 4 + (k % 4)]
+
+
+def _folded(sd, Nq):
+    w_in = np.stack([ops.fold_weight_norm(sd[f"quantizers.{s}.in_proj.weight_v"], sd[f"quantizers.{s}.in_proj.weight_g"])[:, :, 0].numpy() for s in range(Nq)])
+    w_out = np.stack([ops.fold_weight_norm(sd[f"quantizers.{s}.out_proj.weight_v"], sd[f"quantizers.{s}.out_proj.weight_g"])[:, :, 0].numpy() for s in range(Nq)])
+    b_in = np.stack([sd[f"quantizers.{s}.in_proj.bias"].numpy() for s in range(Nq)])
+    b_out = np.stack([sd[f"quantizers.{s}.out_proj.bias"].numpy() for s in range(Nq)])
+    return w_in, b_in, w_out, b_out
+
+
 def test_tensor_core_blob_section_layout():
     """The tensor-core section of the packed blob (csrc/common.cuh TcLayout): TF32 head/remainder split is exact, tiles are in
     the canonical K-major UMMA layout, the 8x8 correction matrices equal W_in[s] @ W_out[j] in binary64."""
@@ -133,20 +161,12 @@ def test_tensor_core_blob_section_layout():
     tc_off, tc_floats = int(hdr[6]), int(hdr[7])
     assert tc_off > 0 and tc_off + tc_floats == blob.size, "TC section is appended after the per-stage sections"
     tc = blob[tc_off:]
-    w_in = np.stack([ops.fold_weight_norm(sd[f"quantizers.{s}.in_proj.weight_v"], sd[f"quantizers.{s}.in_proj.weight_g"])[:, :, 0].numpy() for s in range(Nq)])
-    w_out = np.stack([ops.fold_weight_norm(sd[f"quantizers.{s}.out_proj.weight_v"], sd[f"quantizers.{s}.out_proj.weight_g"])[:, :, 0].numpy() for s in range(Nq)])
-    b_out = np.stack([sd[f"quantizers.{s}.out_proj.bias"].numpy() for s in range(Nq)])
-    nch, nj = D // 32, D // 128
-    off_win, off_wout = 0, nch * 4096
-    off_bout = off_wout + Nq * nj * 3072
-    off_gg = off_bout + nj * 2048
-    gg_floats = (Nq * (Nq - 1) // 2 * 72 + 3) // 4 * 4
-    off_bin = off_gg + gg_floats
-    off_cbk = off_bin + Nq * 8
-    assert off_cbk + Nq * 9216 == tc_floats
-
-    def tile_get(tile, rows, r, k):  # canonical K-major, no swizzle: 8-row x 16-byte core matrices
-        return tile[((k // 4) * rows + r) * 4 + (k % 4)]
+    w_in, b_in, w_out, b_out = _folded(sd, Nq)
+    L = _tc_layout(Nq, D)
+    nj = L["nj"]
+    off_win, off_wout, off_gg, off_bin, off_cbk = L["off_win"], L["off_wout"], L["off_gg"], L["off_bin"], L["off_cbk"]
+    assert L["total"] == tc_floats and L["off_gx"] == L["off_wout"], "one stage group: no virtual chunks"
+    tile_get = _tile_get
 
     # WIN chunk 1: rows 0..63 heads, 64..127 remainders of W_in[s][oc][32 + k]
     tile = tc[off_win + 4096: off_win + 2 * 4096]
@@ -169,6 +189,9 @@ def test_tensor_core_blob_section_layout():
     ref = w_in[2].astype(np.float64) @ w_out[0].astype(np.float64)
     np.testing.assert_array_equal(G[:64].reshape(8, 8), ref.astype(np.float32))
     np.testing.assert_array_equal(G[64:], (w_in[2].astype(np.float64) @ b_out[0].astype(np.float64)).astype(np.float32))
+    # BIN: b_in, then b_in' (identical for a single stage group)
+    np.testing.assert_array_equal(tc[off_bin: off_bin + Nq * 8].reshape(Nq, 8), b_in)
+    np.testing.assert_array_equal(tc[off_bin + Nq * 8: off_bin + 2 * Nq * 8].reshape(Nq, 8), b_in)
     # CBK stage 2: the normalised codebook as a [2][K][4] tile + c2
     cb, c2 = pw.normalized_codebook(2)
     cbk = tc[off_cbk + 2 * 9216: off_cbk + 3 * 9216]
@@ -176,8 +199,52 @@ def test_tensor_core_blob_section_layout():
     assert np.array_equal(cbk[8192:], c2)
 
 
-def test_blob_without_tensor_core_section_for_large_nq():
-    sd = gi.torch_state_dict(gi.make_state_dict(12, 9, 256))
+def test_tensor_core_blob_section_stage_groups():
+    """Models with more than 8 codebooks (conf/base_24kbps.yml: 28) run in groups of 8 stages: per-group W_in rows, the
+    cross-group corrections as "virtual channel" chunks GX (B = -W_in[s] @ W_out[j] for the stages j of earlier groups, zero
+    elsewhere), their bias terms folded into b_in', one bias tile per group."""
+    Nq, D = 19, 256
+    sd = gi.torch_state_dict(gi.make_state_dict(13, Nq, D))
     pw = ops.PackedWeights.from_state_dict(sd, "cpu")
     hdr = pw.host_blob[:16].view(np.int32)
-    assert int(hdr[6]) == 0 and int(hdr[7]) == 0, "Nq > 8 keeps the CUDA-core kernel: no TC section"
+    tc = pw.host_blob[int(hdr[6]):]
+    L = _tc_layout(Nq, D)
+    assert L["total"] == int(hdr[7]) and L["ngrp"] == 3 and L["gx_base"](3) == 8
+    w_in, b_in, w_out, b_out = _folded(sd, Nq)
+    G = lambda s, j: w_in[s].astype(np.float64) @ w_out[j].astype(np.float64)  # [c][k]
+    # WIN group 2, chunk 3: local rows 8 (s - 16) + oc; rows of the absent stages 19..23 are zero
+    tile = tc[(2 * L["nch"] + 3) * 4096: (2 * L["nch"] + 4) * 4096]
+    x = w_in[18, 5, 3 * 32 + 9]
+    assert np.float32(_tile_get(tile, 128, 8 * 2 + 5, 9)) + np.float32(_tile_get(tile, 128, 64 + 8 * 2 + 5, 9)) == x
+    assert _tile_get(tile, 128, 8 * 3, 0) == 0.0 and _tile_get(tile, 128, 64 + 8 * 7 + 7, 31) == 0.0
+    # GX group 1 (stages 8..15): 4 chunks, chunk v covers the earlier stages j = 4v .. 4v+3 (< 8): chunks 2, 3 are padding
+    for v, jj, s, c, kk in [(0, 0, 8, 0, 0), (1, 3, 15, 7, 7), (0, 2, 12, 3, 5)]:
+        tile = tc[L["off_gx"] + (L["gx_base"](1) + v) * 4096:][:4096]
+        want = np.float32(-G(s, 4 * v + jj)[c, kk])
+        got = np.float32(_tile_get(tile, 128, 8 * (s - 8) + c, 8 * jj + kk)) + np.float32(_tile_get(tile, 128, 64 + 8 * (s - 8) + c, 8 * jj + kk))
+        assert got == want
+    assert not tc[L["off_gx"] + (L["gx_base"](1) + 2) * 4096:][:2 * 4096].any(), "padding chunks are zero"
+    # GX group 2 (stages 16..18): chunk 3 covers stages 12..15; rows of stages >= 19 zero
+    tile = tc[L["off_gx"] + (L["gx_base"](2) + 3) * 4096:][:4096]
+    want = np.float32(-G(17, 14)[2, 6])
+    assert np.float32(_tile_get(tile, 128, 8 * 1 + 2, 8 * 2 + 6)) + np.float32(_tile_get(tile, 128, 64 + 8 * 1 + 2, 8 * 2 + 6)) == want
+    assert _tile_get(tile, 128, 8 * 3 + 0, 0) == 0.0
+    # b_in'[s] = b_in[s] - sum_{j < 8 (s // 8)} W_in[s] @ b_out[j]
+    bp = tc[L["off_bin"] + Nq * 8: L["off_bin"] + 2 * Nq * 8].reshape(Nq, 8)
+    np.testing.assert_array_equal(bp[:8], b_in[:8])
+    for s in (8, 18):
+        want = b_in[s].astype(np.float64) - sum(w_in[s].astype(np.float64) @ b_out[j].astype(np.float64) for j in range(8 * (s // 8)))
+        np.testing.assert_array_equal(bp[s], want.astype(np.float32))
+    # BOUT group 2, chunk 1: element (row i, k) = b_out[16 + k][channel(i)] (head + remainder), k >= 3 zero
+    bt = tc[L["off_bout"] + (2 * L["nj"] + 1) * 2048:][:2048]
+    i, k = 37, 2
+    ch = 128 + 4 * (i % 32) + i // 32
+    assert np.float32(_tile_get(bt[:1024], 128, i, k)) + np.float32(_tile_get(bt[1024:], 128, i, k)) == b_out[16 + k, ch]
+    assert _tile_get(bt[:1024], 128, i, 3) == 0.0
+
+
+def test_blob_without_tensor_core_section_for_large_nq():
+    sd = gi.torch_state_dict(gi.make_state_dict(12, 33, 256))
+    pw = ops.PackedWeights.from_state_dict(sd, "cpu")
+    hdr = pw.host_blob[:16].view(np.int32)
+    assert int(hdr[6]) == 0 and int(hdr[7]) == 0, "Nq > 32 has no tensor-core kernel: no TC section"

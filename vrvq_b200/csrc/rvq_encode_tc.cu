@@ -72,6 +72,10 @@ constexpr int SM_ONES = SM_NK + 512;  // constant A tile [2 kg][128][4]: k = 0, 
 constexpr int SM_BAR = SM_ONES + 4096;  // mbarriers
 constexpr int SM_TMEM = SM_BAR + 1024;
 constexpr int SM_TOTAL = SM_TMEM + 16;
+// grouped instantiation: codes of all stages as u16 [32 stages][128 rows] -- stages 0-15 over the (unused) ones tile, 16-31 appended
+constexpr int SM_XC = (SM_TOTAL + 127) / 128 * 128, SM_TOTAL_G = SM_XC + 4096;
+constexpr int G_FI = 4, G_ASLOT = G_FI * 8192;  // grouped final GEMM: stages per ring step; A staging slot (2 slots at SM_AT)
+static_assert(SM_TOTAL_G <= 232448 && 2 * G_ASLOT <= SM_AM, "grouped shared memory map");
 constexpr int W_SLOT = 12288, W_SLOTS = 4;
 constexpr int F_SLOT = 40960, F_SLOTS = 3, F_ITEMS = 5;  // final-GEMM ring (<= 5 chunks of 8 KB per step) over the W_out ring and both codebook buffers
 static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
@@ -185,8 +189,15 @@ __device__ __forceinline__ uint32_t base_mod8(const float *ptr, long long off) {
 
 // FC = from_codes mode (models/quantize.py:217-249): no latent, no in_proj, no search -- the codes are an input; the gather, the
 // out_proj units, the masking and the final GEMM are the encode path's own.
-template <int D, bool ZQIS, bool PROFILE, bool FC>
+// GRP = models with more than 8 codebooks (conf/base_24kbps.yml: 28), without z_q_is: the stages run in groups of 8 on the same
+// tile, one pass of the tile loop per (tile, group).  Group g re-streams the latent through the in_proj GEMM with ITS W_in rows and
+// appends "virtual channel" chunks -- the raw codebook rows of the stages of the earlier groups, gathered by their codes, against
+// -G[s][j] = -W_in[s] W_out[j] -- so the cross-group corrections are extra K of the same GEMM (the straight-through vector q_j is
+// taken as the code's row there: it differs from it by <= 1 ulp, below the rounding of z_e itself); codes stay in shared memory,
+// and the final z_q GEMM over K = 8 n_run regenerates its A tiles from them, four stages per ring step.
+template <int D, bool ZQIS, bool PROFILE, bool FC, bool GRP = false>
 __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P, const __grid_constant__ ZMaps zmaps) {
+    static_assert(!GRP || (!ZQIS && !FC && !PROFILE), "the grouped instantiation has no z_q_is, from_codes or profiling variant");
     constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;  // 32-channel chunks, accumulator drained every 4 chunks
     // search-score chunks: 64 codes per MMA into 3 x 64 TMEM columns; without z_q_is the out_proj ring is idle during the
     // searches, so the scores take 3 x 128 columns from TM_SET on and half as many (170-cycle) barrier hand-overs
@@ -221,7 +232,8 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
             mbar_init(&bars[B_D_FULL + i], 1); mbar_init(&bars[B_D_EMPTY + i], 4);
             mbar_init(&bars[B_CB_FULL + i], 1);
         }
-        for (int i = 0; i < W_SLOTS; ++i) { mbar_init(&bars[B_W_FULL + i], 1); mbar_init(&bars[B_W_EMPTY + i], 1); }
+        // (grouped: slots 0-1 are the A staging ring of the final GEMM, filled by the 8 search warps)
+        for (int i = 0; i < W_SLOTS; ++i) { mbar_init(&bars[B_W_FULL + i], GRP ? 8 : 1); mbar_init(&bars[B_W_EMPTY + i], 1); }
         for (int i = 0; i < 8; ++i) mbar_init(&bars[B_A_READY + i], 4);
         mbar_init(&bars[B_ZQ_READY], 4);
         mbar_init(&bars[B_MMA_DONE], 1);
@@ -236,8 +248,10 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         tmem_alloc(tmem_slot, TM_COLS);
         tmem_relinquish();
     }
-    for (int i = tid; i < TL.gg_floats(); i += TC_NTH) ggs[i] = P.tc[TL.off_gg() + i];
-    for (int i = tid; i < Nq * 8; i += TC_NTH) bins[i] = P.tc[TL.off_bin() + i];
+    if constexpr (!GRP) {  // (grouped: the in-group correction matrices and biases are loaded per group)
+        for (int i = tid; i < TL.gg_floats(); i += TC_NTH) ggs[i] = P.tc[TL.off_gg() + i];
+        for (int i = tid; i < Nq * 8; i += TC_NTH) bins[i] = P.tc[TL.off_bin() + i];
+    }
     for (int i = tid; i < 256; i += TC_NTH)  // ones tile: k group 0 = (1, 1, 0, 0) for every row, k group 1 = 0
         reinterpret_cast<float4 *>(smem + SM_ONES)[i] = i < 128 ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
@@ -291,18 +305,48 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     uint32_t wn = 0, fn = 0, dn = 0;     // W_out ring / final ring step counters, out_proj unit counter
     uint32_t cbu0 = 0, cbu1 = 0;         // uses of the two codebook buffers
 
-    for (int it = 0; it < n_my_tiles; ++it) {
-        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    // One pass of this loop = one group of <= 8 stages of one tile (one pass per tile unless GRP).  Ring positions are running
+    // totals, since the passes of different groups have different chunk counts.
+    const int n_grp = GRP ? (n_run + 7) / 8 : 1;
+    const int n_my_passes = n_my_tiles * n_grp;
+    uint32_t lbase = 0, gbase = 0, zbase = 0;  // phase-L chunks / accumulator groups / latent slots consumed so far
+    uint32_t astep = 0;                        // grouped final GEMM: A staging steps so far
+    unsigned short *codes_lo = reinterpret_cast<unsigned short *>(smem + SM_ONES), *codes_hi = reinterpret_cast<unsigned short *>(smem + SM_XC);
+    auto code_slot = [&](int s) -> unsigned short * { return (s < 16 ? codes_lo : codes_hi) + (s & 15) * 128; };  // [128 rows] of stage s (GRP)
+
+    for (int it = 0; it < n_my_passes; ++it) {
+        const int tile_i = GRP ? it / n_grp : it, grp = GRP ? it - tile_i * n_grp : 0;
+        const int s0 = 8 * grp;                                   // first stage of this pass
+        const int nl = GRP ? min(8, n_run - s0) : n_run;          // stages of this pass
+        const bool first_grp = grp == 0, last_grp = grp == n_grp - 1;
+        const int NV = GRP ? TcLayout::vp(grp) : 0, NCT = NCH + NV;  // virtual chunks (cross-group corrections); chunks of this pass
+        const int tile = (int)blockIdx.x + tile_i * (int)gridDim.x;
         const int b = tile / P.tiles_per_b;
         const int t0 = (tile % P.tiles_per_b) * P.adv;
         const int fv = min(P.adv, p.T - t0);  // frames this tile owns: tile rows 8 .. 8+fv-1 (rows 0-7: halo = the previous 8 frames)
         const bool last_tile = (tile % P.tiles_per_b) == P.tiles_per_b - 1;
-        const uint32_t lbase = (uint32_t)it * NCH, gbase = (uint32_t)it * NG, zbase = (uint32_t)it * (NCH / 2);
         // latent staging geometry of this tile (ZMODE_BULK / ZMODE_TMA): smem column of frame fr in a staged row = fr - tstart + shift(row)
         const int tstart = P.zmode == ZMODE_TMA ? t0 - 8 : max(t0 - 8, 0);
-        const uint32_t tpar = (uint32_t)it & 1u;
+        const uint32_t tpar = (uint32_t)it & 1u;  // phase parity of the once-per-pass barriers
+        // A_READY[s] completes one phase per pass that HAS a stage s (the last group of a tile may be shorter): its phase index
+        auto apar = [&](int s) -> uint32_t {
+            return GRP ? (((uint32_t)tile_i * (uint32_t)((n_run - s + 7) / 8) + (uint32_t)grp) & 1u) : tpar;
+        };
         const int n_stage_steps = ZQIS ? n_run * NJ : 0;
-        const int n_final_steps = (p.z_q != nullptr) ? NJ * ((n_run + F_ITEMS) / F_ITEMS) : 0;  // ceil((n_run + 1) / F_ITEMS) per 128-channel chunk
+        const int G_NST = (n_run + G_FI - 1) / G_FI + 1;  // grouped final GEMM: ring steps per 128-channel chunk (stages in fours, then the bias)
+        const int n_final_steps = (p.z_q == nullptr || !last_grp) ? 0 : GRP ? NJ * G_NST : NJ * ((n_run + F_ITEMS) / F_ITEMS);  // !GRP: ceil((n_run + 1) / F_ITEMS) per chunk
+        if constexpr (GRP) {
+            // this group's correction matrices (pairs j < s inside the group, local pair order) and biases (cross-group terms folded in)
+            for (int i = tid; i < 28 * 72; i += TC_NTH) {
+                const int pr = i / 72, e = i - pr * 72;
+                int j = 0, rem = pr;  // local pair index -> (j, s2)
+                while (rem >= 7 - j) { rem -= 7 - j; ++j; }
+                const int s2 = j + 1 + rem;
+                ggs[i] = (s2 < nl) ? P.tc[TL.off_gg() + TcLayout::pair_index(Nq, s0 + j, s0 + s2) * 72 + e] : 0.0f;
+            }
+            for (int i = tid; i < 64; i += TC_NTH) bins[i] = (i < nl * 8) ? P.tc[TL.off_bin() + Nq * 8 + s0 * 8 + i] : 0.0f;
+            // (visible to the frame threads after the L -> S barrier)
+        }
 
 // Fold the phase-L accumulator set of channel group g into the running fp32 sums (also in TMEM); run by the epilogue warps,
 // which have nothing to store yet (tq = the warp's TMEM lane quarter)
@@ -346,7 +390,7 @@ auto drain = [&](int g, uint32_t tq) {
             if (solo && X0 == 1) {
                 return;
             }
-            for (int c = X0; c < NCH; c += solo ? 1 : 2) {
+            for (int c = X0; c < NCT; c += solo ? 1 : 2) {
                 const int X = c & 1;
                 const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS;
                 {
@@ -382,7 +426,7 @@ auto drain = [&](int g, uint32_t tq) {
             const bool inb = fr >= 0 && (f < 8 || f - 8 < fv);  // rows that hold a real frame (halo rows of the first tile do not)
             const uint32_t tq = tmem + ((uint32_t)(32 * (w & 3)) << 16);  // this warp's lane quarter
             if constexpr (!FC) {
-            if (w < 4) {
+            if (w < 4 && first_grp) {
                 // ---- keep counts, mask, kept-frame counts (quantize.py:389, utils.py:59-60) ----
                 int nk = 0;
                 if (own) {
@@ -516,6 +560,46 @@ auto drain = [&](int g, uint32_t tq) {
                     }
                 }
             }
+            if constexpr (GRP) {
+                // ---- virtual chunks: the code rows of the stages of the earlier groups as extra "channels" (B = -G, blob section GX) ----
+                const int q = tid >> 7;
+                for (int v = 0; v < NV; ++v) {
+                    float h[16], l[16];
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int j = 4 * v + 2 * q + jj;  // stage whose row fills this thread's columns 8 jj .. 8 jj + 7 of the chunk half
+                        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+                        if (j < s0) {
+                            const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)j * L.stage_floats() + L.off_raw() + (size_t)code_slot(j)[f] * 8);
+                            ra = __ldg(rawp);
+                            rb = __ldg(rawp + 1);
+                        }
+                        const float x[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            h[8 * jj + k] = __uint_as_float(__float_as_uint(x[k]) & 0xffffe000u);
+                            l[8 * jj + k] = __fsub_rn(x[k], h[8 * jj + k]);
+                        }
+                    }
+                    const uint32_t n = lbase + (uint32_t)(NCH + v), sl = n % L_SLOTS, use = n / L_SLOTS;
+                    if (use >= 1) {
+                        TC_WAIT(&bars[B_L_EMPTY + sl], (use - 1) & 1u);
+                        tmem_fence_after_sync();
+                    }
+                    {
+                        uint32_t hv[16], lv[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { hv[i] = __float_as_uint(h[i]); lv[i] = __float_as_uint(l[i]); }
+                        const uint32_t ta = tq + TM_AL + 64u * sl + 16u * (uint32_t)q;
+                        tmem_st16(ta, hv);
+                        tmem_st16(ta + 32, lv);
+                    }
+                    tmem_wait_st();
+                    tmem_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) { uint32_t par_; mbar_arrive(l_full(n, &par_)); }
+                }
+            }
             }  // !FC
             ph_mark(1);
             tmem_fence_before_sync();
@@ -583,7 +667,8 @@ auto drain = [&](int g, uint32_t tq) {
             } else {
             // ---- phase S ----
             float zev[8];  // frame threads: z_e of the current stage
-            for (int s = 0; s < n_run; ++s) {
+            for (int s = 0; s < nl; ++s) {  // s: stage within this pass, sg = s0 + s: stage of the model
+                const int sg = s0 + s;
                 if (w < 4) {
                     // bias, latents, normalise (quantize.py:66,92 in torch's op order)
                     uint32_t r8[8];
@@ -610,7 +695,7 @@ auto drain = [&](int g, uint32_t tq) {
                     if (lane == 0) mbar_arrive(&bars[B_E_READY]);  // the search-MMA issuer may start on this stage
                     if (p.latents != nullptr && own) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)(s * 8 + k) * p.lat_sc + fr] = zev[k];
+                        for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)(sg * 8 + k) * p.lat_sc + fr] = zev[k];
                     }
                 }
                 named_bar_sync(1, TC_NSEARCH);  // 2e / e2 of the stage visible to warps 4-7
@@ -756,7 +841,7 @@ auto drain = [&](int g, uint32_t tq) {
                         if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
                     }
                     if (bi >= TCK) bi = 0;  // no candidate at all (NaN latent): code 0, like an argmin over NaNs that never updates
-                    const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)s * L.stage_floats() + L.off_raw() + (size_t)bi * 8);
+                    const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)sg * L.stage_floats() + L.off_raw() + (size_t)bi * 8);
                     const float4 ra = __ldg(rawp), rb = __ldg(rawp + 1);
                     const float cr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                     float qv[8], ls = 0.0f;
@@ -769,12 +854,13 @@ auto drain = [&](int g, uint32_t tq) {
                     }
                     if (own) {
                         const float loss = __fdiv_rn(ls, 8.0f);
-                        p.codes[(long long)b * p.codes_sb + (long long)s * p.codes_sq + fr] = (long long)bi;
-                        if (p.loss_pf != nullptr) p.loss_pf[(long long)b * p.loss_sb + (long long)s * p.loss_sq + fr] = loss;
-                        if (nkeep[f] > s) loss_acc += (double)loss;
+                        p.codes[(long long)b * p.codes_sb + (long long)sg * p.codes_sq + fr] = (long long)bi;
+                        if (p.loss_pf != nullptr) p.loss_pf[(long long)b * p.loss_sb + (long long)sg * p.loss_sq + fr] = loss;
+                        if (nkeep[f] > sg) loss_acc += (double)loss;
                     }
+                    if constexpr (GRP) code_slot(sg)[f] = (unsigned short)bi;  // for the later groups' virtual chunks and the final GEMM
                     // A operand of this stage's out_proj: q split into TF32 head and remainder
-                    {
+                    if constexpr (!GRP) {
                         float h[8], l[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { h[k] = tf32_hi(qv[k]); l[k] = __fsub_rn(qv[k], h[k]); }
@@ -788,8 +874,8 @@ auto drain = [&](int g, uint32_t tq) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars[B_A_READY + s]);
                     // corrections of the later stages: z_e[s2] -= G[s2][s] q + g[s2][s]
-                    for (int s2 = s + 1; s2 < n_run; ++s2) {
-                        const float *G = ggs + TcLayout::pair_index(Nq, s, s2) * 72;
+                    for (int s2 = s + 1; s2 < nl; ++s2) {
+                        const float *G = ggs + TcLayout::pair_index(GRP ? 8 : Nq, s, s2) * 72;
                         uint32_t r8[8];
                         tmem_ld8(tq + TM_RUN + 8 * s2, r8);
                         float a[8];
@@ -812,7 +898,7 @@ auto drain = [&](int g, uint32_t tq) {
                 }
                 ph_mark(5);
             }
-            if (w < 4) {
+            if (!GRP && w < 4) {
                 // ---- mask the A tiles for the final z_q GEMM (quantize.py:194 / :421) once every per-stage MMA has read them ----
                 TC_WAIT(&bars[B_MMA_DONE], tpar);
                 const int nk = nkeep[f];
@@ -831,6 +917,54 @@ auto drain = [&](int g, uint32_t tq) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[B_ZQ_READY]);
             }
+            if constexpr (GRP) {
+                if (last_grp && p.z_q != nullptr) {
+                    // ---- A tiles of the final z_q GEMM (quantize.py:194 / :421), regenerated from the codes: per 128-channel chunk j the
+                    // stages go through a two-slot staging ring four at a time (rows of masked stages zero), then one step with the
+                    // mask tiles that multiply the bias rows.  Warps 0-3 build items 0-1 of a step, warps 4-7 items 2-3; row = f.
+                    const int hsel = w >> 2;
+                    uint32_t m = astep;
+                    for (int j = 0; j < NJ; ++j)
+                        for (int st = 0; st < G_NST; ++st, ++m) {
+                            const uint32_t sa = m & 1u, use = m >> 1;
+                            if (use >= 1) TC_WAIT(&bars[B_W_EMPTY + sa], (use - 1) & 1u);
+                            unsigned char *base = smem + SM_AT + sa * G_ASLOT;
+                            const int nk = nkeep[f];
+#pragma unroll
+                            for (int ii = 0; ii < 2; ++ii) {
+                                const int i = 2 * hsel + ii;
+                                if (st < G_NST - 1) {
+                                    const int s = G_FI * st + i;
+                                    if (s < n_run) {
+                                        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+                                        if (nk > s) {
+                                            const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)s * L.stage_floats() + L.off_raw() + (size_t)code_slot(s)[f] * 8);
+                                            ra = __ldg(rawp);
+                                            rb = __ldg(rawp + 1);
+                                        }
+                                        const float qv[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                                        float h[8], l[8];
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) { h[k] = tf32_hi(qv[k]); l[k] = __fsub_rn(qv[k], h[k]); }
+                                        unsigned char *at = base + i * 8192 + f * 16;
+                                        *reinterpret_cast<float4 *>(at) = make_float4(h[0], h[1], h[2], h[3]);
+                                        *reinterpret_cast<float4 *>(at + 2048) = make_float4(h[4], h[5], h[6], h[7]);
+                                        *reinterpret_cast<float4 *>(at + 4096) = make_float4(l[0], l[1], l[2], l[3]);
+                                        *reinterpret_cast<float4 *>(at + 4096 + 2048) = make_float4(l[4], l[5], l[6], l[7]);
+                                    }
+                                } else if (i < n_grp) {  // mask tile of stage group i: k = stage - 8 i
+                                    const int r = nk - 8 * i;
+                                    unsigned char *am = base + i * 4096 + f * 16;
+                                    *reinterpret_cast<float4 *>(am) = make_float4(r > 0 ? 1.f : 0.f, r > 1 ? 1.f : 0.f, r > 2 ? 1.f : 0.f, r > 3 ? 1.f : 0.f);
+                                    *reinterpret_cast<float4 *>(am + 2048) = make_float4(r > 4 ? 1.f : 0.f, r > 5 ? 1.f : 0.f, r > 6 ? 1.f : 0.f, r > 7 ? 1.f : 0.f);
+                                }
+                            }
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bars[B_W_FULL + sa]);
+                        }
+                }
+            }
             }  // !FC
             ph_mark(6);
         } else if (w < 12) {
@@ -838,7 +972,7 @@ auto drain = [&](int g, uint32_t tq) {
             // Epilogue warps: TMEM -> global.  Lane quarter q4 = w - 8, frame f = 32*q4 + lane.
             // =====================================================================================================
             if constexpr (!FC)
-                for (int g = 0; g < NG; ++g) drain(g, tmem + ((uint32_t)(32 * (w - 8)) << 16));
+                for (int g = 0; g < NCT / 4; ++g) drain(g, tmem + ((uint32_t)(32 * (w - 8)) << 16));
             tmem_fence_before_sync();
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
@@ -896,7 +1030,7 @@ auto drain = [&](int g, uint32_t tq) {
                     for (int j = 0; j < NJ; ++j) unit(p.z_q_is + off + (long long)(128 * j) * p.zqis_sd, p.zqis_sd, shifts);
                 }
             }
-            if (p.z_q != nullptr) {  // the final GEMM uses delta = 8 for every class: lane r <-> frame t0 + r
+            if (p.z_q != nullptr && last_grp) {  // the final GEMM uses delta = 8 for every class: lane r <-> frame t0 + r
                 float *outp = p.z_q + (long long)b * p.zq_sb;
                 for (int j = 0; j < NJ; ++j) unit(outp + (long long)(128 * j) * p.zq_sd, p.zq_sd, 0x08080808u);
             }
@@ -929,8 +1063,8 @@ auto drain = [&](int g, uint32_t tq) {
                     if (use >= 1) TC_WAIT(&bars[B_D_EMPTY + buf], (use - 1) & 1u);
                     return buf;
                 };
-                for (int s = 0; s < n_run; ++s) {
-                    TC_WAIT(&bars[B_A_READY + s], tpar);
+                for (int s = 0; s < nl; ++s) {
+                    TC_WAIT(&bars[B_A_READY + s], apar(s));
                     fence_proxy_async();
                     tmem_fence_after_sync();
                     ph_mark(2);
@@ -968,7 +1102,42 @@ auto drain = [&](int g, uint32_t tq) {
                     }
                 }
                 umma_commit(&bars[B_MMA_DONE]);
-                if (p.z_q != nullptr) {
+                if (GRP && p.z_q != nullptr && last_grp) {
+                    // grouped final GEMM: A tiles from the staging ring (search warps), W_out / bias tiles from the final ring
+                    uint32_t fstep = fn, am_ = astep;
+                    for (int j = 0; j < NJ; ++j) {
+                        const uint32_t buf = wait_dbuf();
+                        const uint32_t d = tmem + TM_SET + 128u * buf;
+                        for (int st = 0; st < G_NST; ++st, ++am_, ++fstep) {
+                            const uint32_t sa = am_ & 1u, slot = fstep % F_SLOTS;
+                            TC_WAIT(&bars[B_W_FULL + sa], (am_ >> 1) & 1u);
+                            TC_WAIT(&bars[B_F_FULL + slot], (fstep / F_SLOTS) & 1u);
+                            fence_proxy_async();
+                            tmem_fence_after_sync();
+                            const uint32_t abase = smem_base + SM_AT + sa * G_ASLOT, wbase = smem_base + SM_WO + slot * F_SLOT;
+                            if (st < G_NST - 1) {
+                                for (int i = 0; i < G_FI && G_FI * st + i < n_run; ++i) {
+                                    const uint64_t ah = desc128(abase + i * 8192) + 8, al = ah + (4096 >> 4);  // + 8 rows: skip the halo
+                                    const uint64_t wb = desc128(wbase + i * 8192);
+                                    umma_tf32(d, al, wb, ID_128, st > 0 || i > 0);
+                                    umma_tf32(d, ah, wb + (4096 >> 4), ID_128, true);
+                                    umma_tf32(d, ah, wb, ID_128, true);
+                                }
+                            } else {
+                                for (int i = 0; i < n_grp; ++i) {  // + sum_s mask_s b_out[s], eight stages per mask tile
+                                    const uint64_t am = desc128(abase + i * 4096) + 8, wb = desc128(wbase + i * 8192);
+                                    umma_tf32(d, am, wb + (4096 >> 4), ID_128, true);
+                                    umma_tf32(d, am, wb, ID_128, true);
+                                }
+                            }
+                            umma_commit(&bars[B_W_EMPTY + sa]);
+                            umma_commit(&bars[B_F_EMPTY + slot]);
+                        }
+                        umma_commit(&bars[B_D_FULL + buf]);
+                        ++dn;
+                    }
+                }
+                if (!GRP && p.z_q != nullptr) {
                     TC_WAIT(&bars[B_ZQ_READY], tpar);
                     fence_proxy_async();
                     tmem_fence_after_sync();
@@ -1064,7 +1233,7 @@ auto drain = [&](int g, uint32_t tq) {
                 // codebook tile: 1024 rows -> LBO = 16384 B, SBO = 128 B
                 constexpr uint64_t DESC_CB = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)(16384 >> 4) << 16);
                 const uint64_t ae = desc128(smem_base + SM_ES);
-                for (int s = 0; s < n_run; ++s) {
+                for (int s = 0; s < nl; ++s) {
                     const uint32_t gs = gstage + (uint32_t)s;
                     TC_WAIT(&bars[B_E_READY], gs & 1u);
                     const uint32_t cbuse = (s & 1) ? (cbu1 + (uint32_t)(s >> 1)) : (cbu0 + (uint32_t)(s >> 1));
@@ -1086,18 +1255,19 @@ auto drain = [&](int g, uint32_t tq) {
             // Copy producer: lane 0 of warp 13 issues every cp.async.bulk (W_in ring, W_out ring, search codebooks).
             // =====================================================================================================
             if (!FC && lane == 0) {
-                const float *win = P.tc + TL.off_win();
-                // codebook of stage 0 (its buffer is outside the phase-L region)
+                const float *win = P.tc + TL.off_win() + (size_t)grp * NCH * 4096;  // this group's W_in rows
+                const float *gx = P.tc + TL.off_gx() + (size_t)TcLayout::gx_base(grp) * 4096 - (size_t)NCH * 4096;  // virtual chunks follow (c >= NCH)
+                // codebook of the pass's first stage (its buffer is outside the phase-L region)
                 mbar_arrive_expect_tx(&bars[B_CB_FULL + 0], 36864);
-                bulk_g2s(smem + SM_CB0, P.tc + TL.off_cbk(), 36864, &bars[B_CB_FULL + 0]);
-                for (int c = 0; c < NCH; ++c) {
+                bulk_g2s(smem + SM_CB0, P.tc + TL.off_cbk() + (size_t)s0 * 9216, 36864, &bars[B_CB_FULL + 0]);
+                for (int c = 0; c < NCT; ++c) {
                     const uint32_t m = lbase + (uint32_t)c, slot = m % L_SLOTS, use = m / L_SLOTS;
                     if (use >= 1) TC_WAIT(&bars[B_L_EMPTY + slot], (use - 1) & 1u);
                     if (PROFILE && it == 0) trace(6, c);
                     uint32_t par_;
                     uint64_t *fb = l_full(m, &par_);
                     mbar_arrive_expect_tx(fb, 16384);
-                    bulk_g2s(smem + SM_LR + slot * L_SLOT, win + (size_t)c * 4096, 16384, fb);
+                    bulk_g2s(smem + SM_LR + slot * L_SLOT, (c < NCH ? win : gx) + (size_t)c * 4096, 16384, fb);
                 }
             }
             ph_mark(0);
@@ -1106,17 +1276,17 @@ auto drain = [&](int g, uint32_t tq) {
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
             if (lane == 0) {
-                if (!FC && n_run > 1) {  // codebook of stage 1 (its buffer is inside the phase-L region)
+                if (!FC && nl > 1) {  // codebook of the pass's second stage (its buffer is inside the phase-L region)
                     mbar_arrive_expect_tx(&bars[B_CB_FULL + 1], 36864);
-                    bulk_g2s(smem + SM_CB1, P.tc + TL.off_cbk() + 9216, 36864, &bars[B_CB_FULL + 1]);
+                    bulk_g2s(smem + SM_CB1, P.tc + TL.off_cbk() + (size_t)(s0 + 1) * 9216, 36864, &bars[B_CB_FULL + 1]);
                 }
                 // W_out ring of the per-stage out_proj: chunk (s, j), row-major; refills of the search codebooks interleaved
                 const float *wout = P.tc + TL.off_wout();
                 const float *bout = P.tc + TL.off_bout();
-                int wi = 0, cs = FC ? n_run : 0;  // (from_codes: no search codebooks to refill)
+                int wi = 0, cs = FC ? nl : 0;  // (from_codes: no search codebooks to refill)
                 uint32_t spins = 0;
                 unsigned long long spin_t0 = 0;
-                while (wi < n_stage_steps || cs < n_run) {
+                while (wi < n_stage_steps || cs < nl) {
                     bool progressed = false;
                     if (wi < n_stage_steps) {
                         const uint32_t m = wn + (uint32_t)wi, slot = m % W_SLOTS, use = m / W_SLOTS;
@@ -1127,11 +1297,11 @@ auto drain = [&](int g, uint32_t tq) {
                             progressed = true;
                         }
                     }
-                    if (cs < n_run && mbar_try_wait(&bars[B_A_READY + cs], tpar)) {
+                    if (cs < nl && mbar_try_wait(&bars[B_A_READY + cs], apar(cs))) {
                         // the search group is done with the codebook of stage cs: refill its buffer
-                        if (cs + 2 < n_run) {
+                        if (cs + 2 < nl) {
                             mbar_arrive_expect_tx(&bars[B_CB_FULL + (cs & 1)], 36864);
-                            bulk_g2s(smem + ((cs & 1) ? SM_CB1 : SM_CB0), P.tc + TL.off_cbk() + (size_t)(cs + 2) * 9216, 36864,
+                            bulk_g2s(smem + ((cs & 1) ? SM_CB1 : SM_CB0), P.tc + TL.off_cbk() + (size_t)(s0 + cs + 2) * 9216, 36864,
                                      &bars[B_CB_FULL + (cs & 1)]);
                         }
                         ++cs;
@@ -1142,7 +1312,22 @@ auto drain = [&](int g, uint32_t tq) {
                 }
                 // final GEMM ring: for j: W_out (0..n_run-1, j) then the bias chunk j.  Its slots overlay the W_out ring and the
                 // codebook buffers, so it starts once every per-stage MMA has completed (and the last search is over).
-                if (n_final_steps > 0) {
+                if (GRP && n_final_steps > 0) {  // grouped: four stages per step (W_out hi | lo tiles), last step = the groups' bias tiles
+                    TC_WAIT(&bars[B_MMA_DONE], tpar);
+                    uint32_t m = fn;
+                    for (int j = 0; j < NJ; ++j)
+                        for (int st = 0; st < G_NST; ++st, ++m) {
+                            const uint32_t slot = m % F_SLOTS, use = m / F_SLOTS;
+                            if (use >= 1) TC_WAIT(&bars[B_F_EMPTY + slot], (use - 1) & 1u);
+                            const int cnt = st < G_NST - 1 ? min(G_FI, n_run - G_FI * st) : n_grp;
+                            mbar_arrive_expect_tx(&bars[B_F_FULL + slot], (uint32_t)cnt * 8192u);
+                            for (int i = 0; i < cnt; ++i) {
+                                const float *src = st < G_NST - 1 ? wout + ((size_t)(G_FI * st + i) * NJ + j) * 3072 : bout + ((size_t)i * NJ + j) * 2048;
+                                bulk_g2s(smem + SM_WO + slot * F_SLOT + i * 8192, src, 8192, &bars[B_F_FULL + slot]);
+                            }
+                        }
+                }
+                if (!GRP && n_final_steps > 0) {
                     TC_WAIT(&bars[B_MMA_DONE], tpar);
                     uint32_t m = fn;
                     for (int j = 0; j < NJ; ++j)
@@ -1163,9 +1348,13 @@ auto drain = [&](int g, uint32_t tq) {
         }
         wn += (uint32_t)n_stage_steps;
         fn += (uint32_t)n_final_steps;
-        gstage += (uint32_t)n_run;
-        cbu0 += (uint32_t)((n_run + 1) >> 1);  // buffer 0 serves the even stages, buffer 1 the odd ones
-        cbu1 += (uint32_t)(n_run >> 1);
+        if (GRP) astep += (uint32_t)n_final_steps;
+        gstage += (uint32_t)nl;
+        cbu0 += (uint32_t)((nl + 1) >> 1);  // buffer 0 serves the even stages, buffer 1 the odd ones
+        cbu1 += (uint32_t)(nl >> 1);
+        lbase += (uint32_t)NCT;
+        gbase += (uint32_t)(NCT / 4);
+        zbase += (uint32_t)(NCH / 2);
         tmem_fence_before_sync();
         __syncthreads();  // end of tile: every MMA of the tile has completed (the epilogue waited for the last one)
         tmem_fence_after_sync();
@@ -1215,6 +1404,7 @@ static int pick_tiling(int B, int T, int sms, int *adv, int *tiles_per_b) {
 
 int encode_tc_usable(const vrvq_encode_args *a) {
     if (!tc_shape_ok(a->input_dim, a->codebook_size, a->n_codebooks)) return 0;
+    if (a->n_codebooks > TC_MAX_NQ_ZQIS && a->z_q_is != nullptr) return 0;  // more than one stage group: no per-stage outputs on this path
     // the epilogue forms store addresses as base + i * (16 * row pitch) with a 32-bit step
     const long long lim = 1ll << 27;
     if (a->z_q_is != nullptr && (a->z_q_is_stride_d < 0 || a->z_q_is_stride_d >= lim)) return 0;
@@ -1320,11 +1510,12 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
     return VRVQ_OK;
 }
 
-template <int D, bool ZQIS, bool PROFILE, bool FC = false>
+template <int D, bool ZQIS, bool PROFILE, bool FC = false, bool GRP = false>
 static int launch_tc_one(const TcParams &P, const ZMaps &zmap, int grid, cudaStream_t st) {
-    int rc = ensure_dynamic_smem<rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC>>(SM_TOTAL, "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
+    constexpr int SMEM = GRP ? SM_TOTAL_G : SM_TOTAL;
+    int rc = ensure_dynamic_smem<rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC, GRP>>(SMEM, "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
     if (rc) return rc;
-    rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC><<<grid, TC_NTH, SM_TOTAL, st>>>(P, zmap);
+    rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC, GRP><<<grid, TC_NTH, SMEM, st>>>(P, zmap);
     return check_cuda(cudaGetLastError(), "rvq_encode_tc_kernel launch");
 }
 template <int D, bool ZQIS>
@@ -1346,7 +1537,7 @@ int encode_tc_launch_info(const vrvq_encode_args *a, int *grid, int *block, int 
     if (rc) return rc;
     if (grid) *grid = g;
     if (block) *block = TC_NTH;
-    if (smem) *smem = SM_TOTAL;
+    if (smem) *smem = a->n_codebooks > TC_MAX_NQ_ZQIS ? SM_TOTAL_G : SM_TOTAL;
     return VRVQ_OK;
 }
 
@@ -1363,6 +1554,14 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
     if (dbg && cudaMalloc(&P.e.phase_cycles, sizeof(long long) * 64 * (size_t)grid) != cudaSuccess) P.e.phase_cycles = nullptr;
     if (P.e.phase_cycles != nullptr) cudaMemsetAsync(P.e.phase_cycles, 0, sizeof(long long) * 64 * (size_t)grid, st);
     P.trace = (dbg && getenv("VRVQ_DEBUG_PHASES")[0] == '3' && grid >= 32) ? 1 : 0;
+    if (a->n_codebooks > TC_MAX_NQ_ZQIS) {  // stage groups (no profiling instantiation)
+        switch (a->input_dim) {
+            case 1024: return launch_tc_one<1024, false, false, false, true>(P, zmap, grid, st);
+            case 512: return launch_tc_one<512, false, false, false, true>(P, zmap, grid, st);
+            case 256: return launch_tc_one<256, false, false, false, true>(P, zmap, grid, st);
+            default: return VRVQ_EUNSUPPORTED;
+        }
+    }
     switch (a->input_dim) {
         case 1024: rc = zqis ? launch_tc<1024, true>(P, zmap, grid, st) : launch_tc<1024, false>(P, zmap, grid, st); break;
         case 512: rc = zqis ? launch_tc<512, true>(P, zmap, grid, st) : launch_tc<512, false>(P, zmap, grid, st); break;
@@ -1424,7 +1623,7 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
 // ---- from_codes on the tensor-core path (vrvq_from_codes_f32 for models with <= 8 codebooks) ------------------------
 int from_codes_tc_usable(const vrvq_from_codes_args *a) {
     const long long lim = 1ll << 27;
-    if (!tc_shape_ok(a->input_dim, a->codebook_size, a->n_codebooks)) return 0;
+    if (!tc_shape_ok(a->input_dim, a->codebook_size, a->n_codebooks) || a->n_codebooks > TC_MAX_NQ_ZQIS) return 0;
     if (a->z_q_stride_d < 0 || a->z_q_stride_d >= lim) return 0;
     if (a->z_q_is != nullptr && (a->z_q_is_stride_d < 0 || a->z_q_is_stride_d >= lim)) return 0;
     const char *impl = getenv("VRVQ_ENCODE_IMPL");

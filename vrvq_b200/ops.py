@@ -190,8 +190,9 @@ def encode_launch_info(w: PackedWeights, B: int, T: int, n_run: int, device):
 
 def tc_kernel_available(w: PackedWeights, n_run: int, z_q_is: bool = False) -> bool:
     """Whether a tensor-core (tcgen05) instantiation of the fused encode exists for this model / call shape: D in
-    {256, 512, 1024}, K = 1024 and at most 8 codebooks (csrc/common.cuh: tc_shape_ok)."""
-    return w.codebook_size == 1024 and w.input_dim in (256, 512, 1024) and 1 <= w.n_codebooks <= 8
+    {256, 512, 1024}, K = 1024, at most 32 codebooks -- and at most 8 when the per-stage outputs z_q_is are requested
+    (csrc/common.cuh: tc_shape_ok, TC_MAX_NQ_ZQIS)."""
+    return w.codebook_size == 1024 and w.input_dim in (256, 512, 1024) and 1 <= w.n_codebooks <= (8 if z_q_is else 32)
 
 
 def rvq_encode(w: PackedWeights, z, n_run=None, imp_map=None, level=None, want_z_q_is=False, want_loss_pf=False):
