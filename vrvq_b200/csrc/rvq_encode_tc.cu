@@ -42,6 +42,13 @@
 #include "common.cuh"
 #include "encode_params.cuh"
 
+#ifndef VRVQ_THIRD_SCAN_GROUP
+#define VRVQ_THIRD_SCAN_GROUP 0
+#endif
+#ifndef VRVQ_ROW_PREFETCH
+#define VRVQ_ROW_PREFETCH 0
+#endif
+
 namespace vrvq {
 
 constexpr int TCK = 1024;      // codebook size
@@ -416,6 +423,151 @@ auto drain = [&](int g, uint32_t tq) {
                 if (PROFILE && it == 0 && X == 0) trace(5, c);
             }
         };
+        // ---- search of one stage by one scan group (quantize.py:96-101): the tensor core scores all 1024 codes per frame (TF32,
+        // |error| <= 2^-8); scan group h (warps 4h .. 4h+3, thread = frame f) takes the score chunks ck = h, h + NSG, ..., keeps the
+        // 8-code groups within SEARCH_MARGIN of its running maximum and re-scores those with the reference's exact fp32 arithmetic
+        // (first index wins ties).  Groups: warps 0-3, 4-7 and -- when there is no z_q_is to store -- the epilogue warps 8-11.
+        constexpr int NSG = (ZQIS || !VRVQ_THIRD_SCAN_GROUP) ? 2 : 3, NSCAN = 128 * NSG;
+        unsigned char *list_base = smem + (ZQIS ? SM_SB : SM_WO);  // candidate lists [16][NSCAN] u32 (without z_q_is the W_out ring is idle)
+        auto scan_stage = [&](int s, int h, int f, uint32_t tq, float &bd_out, int &bi_out) {
+                    const uint32_t cbuse = (s & 1) ? (cbu1 + (uint32_t)(s >> 1)) : (cbu0 + (uint32_t)(s >> 1));
+                    const float *CB = reinterpret_cast<const float *>(smem + ((s & 1) ? SM_CB1 : SM_CB0));
+                    uint32_t *list = reinterpret_cast<uint32_t *>(list_base) + tid;  // (group maximum, group id) entries, [entry][thread]: no bank conflicts
+                    float bd = __int_as_float(0x7f800000);
+                    int bidx = 0x7fffffff;
+                    float runmax = __int_as_float(0xff800000);
+                    int cnt = 0;
+                    constexpr int NPIECE = (NSC + NSG - 1) / NSG * (SCW / 64);  // this group's score chunks (SCW codes each), in 64-code pieces
+                    for (int pc = 0; pc < NPIECE; ++pc) {
+                        const int ck = NSG * (pc / (SCW / 64)) + h, sub = pc % (SCW / 64);
+                        if (NSC % NSG != 0 && ck >= NSC) break;
+                        const uint32_t gc = (gstage + (uint32_t)s) * (uint32_t)NSC + (uint32_t)ck, sbuf = gc % 3u;
+                        const uint32_t tsc = tq + TM_SC + (uint32_t)SCW * sbuf + 64u * (uint32_t)sub;
+                        if (sub == 0) {
+                            TC_WAIT(&bars[B_SB_FULL + sbuf], (gc / 3u) & 1u);
+                            tmem_fence_after_sync();
+                        }
+                        ph_mark(8);
+                        uint32_t va[32], vb[32];
+                        tmem_ld32(tsc, va);
+                        tmem_ld32(tsc + 32, vb);
+                        tmem_wait_ld32(va);
+                        tmem_wait_ld32(vb);
+                        if (sub == SCW / 64 - 1) {
+                            tmem_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bars[B_SB_EMPTY + sbuf]);
+                        }
+                        ph_mark(9);
+                        // maxima of the eight 8-code groups of this chunk (FMNMX3)
+                        float g[8];
+#define VRVQ_GROUP_MAX(dst, v, o)                                                                                                       \
+    {                                                                                                                                   \
+        float m_;                                                                                                                       \
+        asm("max.f32 %0, %1, %2, %3;" : "=f"(m_) : "f"(__uint_as_float(v[o])), "f"(__uint_as_float(v[o + 1])), "f"(__uint_as_float(v[o + 2]))); \
+        asm("max.f32 %0, %1, %2, %3;" : "=f"(m_) : "f"(m_), "f"(__uint_as_float(v[o + 3])), "f"(__uint_as_float(v[o + 4])));               \
+        asm("max.f32 %0, %1, %2, %3;" : "=f"(m_) : "f"(m_), "f"(__uint_as_float(v[o + 5])), "f"(__uint_as_float(v[o + 6])));               \
+        dst = fmaxf(m_, __uint_as_float(v[o + 7]));                                                                                     \
+    }
+                        VRVQ_GROUP_MAX(g[0], va, 0) VRVQ_GROUP_MAX(g[1], va, 8) VRVQ_GROUP_MAX(g[2], va, 16) VRVQ_GROUP_MAX(g[3], va, 24)
+                        VRVQ_GROUP_MAX(g[4], vb, 0) VRVQ_GROUP_MAX(g[5], vb, 8) VRVQ_GROUP_MAX(g[6], vb, 16) VRVQ_GROUP_MAX(g[7], vb, 24)
+#undef VRVQ_GROUP_MAX
+                        float cm;
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(g[0]), "f"(g[1]), "f"(g[2]));
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(cm), "f"(g[3]), "f"(g[4]));
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(cm), "f"(g[5]), "f"(g[6]));
+                        runmax = fmaxf(runmax, fmaxf(cm, g[7]));
+                        const float thr = runmax - SEARCH_MARGIN;
+                        const uint32_t gid0 = (uint32_t)(ck * (SCW / 8) + sub * 8);  // group id = code / 8
+                        // branch-free append of every group whose maximum is within the margin: entry = (max & ~0xff) | group id
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t entry = (__float_as_uint(g[i]) & 0xffffff00u) | (gid0 + (uint32_t)i);
+                            const uint32_t addr = smem_u32(list) + (4u * NSCAN) * (uint32_t)min(cnt, 15);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p st.shared.u32 [%3], %4;\n\t@p add.s32 %0, %0, 1;\n\t}"
+                                : "+r"(cnt)
+                                : "f"(g[i]), "f"(thr), "r"(addr), "r"(entry)
+                                : "memory");
+                        }
+                        ph_mark(10);
+                    }
+                    TC_WAIT(&bars[B_CB_FULL + (s & 1)], cbuse & 1u);  // (long complete: the score MMAs read the same buffer)
+                    // 2e / e2 of the frame (written by its frame thread before it released the stage to the search-MMA issuer: the
+                    // scores waited for above are causally after those writes)
+                    const float4 ea = *reinterpret_cast<const float4 *>(&es[f * 4]), eb = *reinterpret_cast<const float4 *>(&es[512 + f * 4]);
+                    const float e2 = e2s[f];
+                    {
+                        // Work list of 8-code groups to re-score exactly.  Normal case: the (<= 3) groups still within the margin of
+                        // the final maximum (the stored maximum lost its low 8 bits: 1e-4 of slack), compacted first so that a warp
+                        // runs the expensive body only max-over-lanes times.  Fallbacks: every listed group (more than 3 hits), or
+                        // every group of this thread's share of the codebook (list overflow: degenerate frames, e.g. an all-zero latent).
+                        const float thr = runmax - SEARCH_MARGIN - 1e-4f;
+                        int c0 = -1, c1 = -1, c2 = -1, nc = 0;
+                        const int nlist = cnt <= 16 ? cnt : 0;
+                        for (int i = 0; i < nlist; ++i) {
+                            const uint32_t entry = list[i * NSCAN];
+                            const bool hit = __uint_as_float(entry & 0xffffff00u) >= thr;
+                            const int gidx = (int)(entry & 0xffu);
+                            c2 = (hit && nc == 2) ? gidx : c2;
+                            c1 = (hit && nc == 1) ? gidx : c1;
+                            c0 = (hit && nc == 0) ? gidx : c0;
+                            nc += hit ? 1 : 0;
+                        }
+                        const int mode = cnt > 16 ? 2 : nc > 3 ? 1 : 0;
+                        const int total = mode == 2 ? ((NSC - h + NSG - 1) / NSG) * (SCW / 8) : mode == 1 ? cnt : nc;
+                        for (int wi = 0; wi < total; ++wi) {
+                            int gid;
+                            if (mode == 0) {
+                                gid = wi == 0 ? c0 : wi == 1 ? c1 : c2;
+                            } else if (mode == 1) {
+                                const uint32_t entry = list[wi * NSCAN];
+                                gid = (__uint_as_float(entry & 0xffffff00u) >= thr) ? (int)(entry & 0xffu) : -1;
+                            } else {
+                                gid = (NSG * (wi / (SCW / 8)) + h) * (SCW / 8) + wi % (SCW / 8);  // wi-th group of this thread's share
+                            }
+                            if (gid >= 0) {
+                                const float4 *r0 = reinterpret_cast<const float4 *>(CB + gid * 32), *r1 = reinterpret_cast<const float4 *>(CB + 4096 + gid * 32);
+                                const float *c2p = CB + 8192 + gid * 8;
+#pragma unroll
+                                for (int j8 = 0; j8 < 8; ++j8) {  // exact distance of code 8*gid + jj; lexicographic (distance, index) minimum
+                                    const int jj = (j8 + lane) & 7;  // lane-staggered: the rows of different groups share their banks
+                                    const float4 ca = r0[jj], cb4 = r1[jj];
+                                    float d = __fmul_rn(ea.x, ca.x);
+                                    d = __fmaf_rn(ea.y, ca.y, d); d = __fmaf_rn(ea.z, ca.z, d); d = __fmaf_rn(ea.w, ca.w, d);
+                                    d = __fmaf_rn(eb.x, cb4.x, d); d = __fmaf_rn(eb.y, cb4.y, d); d = __fmaf_rn(eb.z, cb4.z, d); d = __fmaf_rn(eb.w, cb4.w, d);
+                                    const float t = __fadd_rn(__fadd_rn(e2, -d), c2p[jj]);  // dist = fl(fl(e2 - dot) + c2)
+                                    const int jx = gid * 8 + jj;
+                                    if (t < bd || (t == bd && jx < bidx)) { bd = t; bidx = jx; }
+                                }
+                            }
+                        }
+                    }
+                    ph_mark(11);
+                    bd_out = bd;
+                    bi_out = bidx;
+        };
+        // A scan group's result for the merge by the frame threads: best (distance, index) per frame, and -- without z_q_is, where the
+        // candidate lists live in the idle W_out ring and this area is free -- the un-normalised codebook row of that index, fetched
+        // here so that its L2 latency passes during the hand-over instead of on the frame thread's critical path.
+        auto publish_best = [&](int s, int h, int f, float bd, int bidx) {
+            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+            if constexpr (!ZQIS && VRVQ_ROW_PREFETCH) {
+                if (bidx < TCK) {
+                    const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)(s0 + s) * L.stage_floats() + L.off_raw() + (size_t)bidx * 8);
+                    ra = __ldg(rawp);
+                    rb = __ldg(rawp + 1);
+                }
+            }
+            if constexpr (ZQIS) named_bar_sync(1, NSCAN);  // (with z_q_is the lists share this area: every group must be done with them)
+            reinterpret_cast<float *>(smem + SM_SB)[h * 128 + f] = bd;
+            reinterpret_cast<int *>(smem + SM_SB + 2048)[h * 128 + f] = bidx;
+            if constexpr (!ZQIS && VRVQ_ROW_PREFETCH) {
+                float4 *rowp = reinterpret_cast<float4 *>(smem + SM_SB + 4096) + (h * 128 + f) * 2;
+                rowp[0] = ra;
+                rowp[1] = rb;
+            }
+        };
         if (w < 8) {
             // =====================================================================================================
             // Search group.  Frame threads (warps 0-3): f = tid = TMEM lane.
@@ -667,182 +819,103 @@ auto drain = [&](int g, uint32_t tq) {
             } else {
             // ---- phase S ----
             float zev[8];  // frame threads: z_e of the current stage
+            // bias, latents, normalise (quantize.py:66,92 in torch's op order) of stage s: frame threads.  Runs one stage ahead of the
+            // searches: right after stage s - 1 has corrected the running sum of stage s (below), so the score MMAs of stage s
+            // start while the corrections of the later stages are still being applied.
+            auto prep = [&](int s) {
+                uint32_t r8[8];
+                tmem_ld8(tq + TM_RUN + 8 * s, r8);
+                tmem_wait_ld(r8);
+                float ss = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    zev[k] = __fadd_rn(__uint_as_float(r8[k]), bins[s * 8 + k]);
+                    const float sq = __fmul_rn(zev[k], zev[k]);
+                    ss = (k == 0) ? sq : __fadd_rn(ss, sq);
+                }
+                const float den = fmaxf(__fsqrt_rn(ss), 1e-12f);
+                float e2 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float ec = __fdiv_rn(zev[k], den);
+                    const float sqe = __fmul_rn(ec, ec);
+                    e2 = (k == 0) ? sqe : __fadd_rn(e2, sqe);
+                    es[(k >> 2) * 512 + f * 4 + (k & 3)] = __fmul_rn(2.0f, ec);
+                }
+                e2s[f] = e2;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[B_E_READY]);  // the search-MMA issuer may start on this stage
+                if (p.latents != nullptr && own) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)((s0 + s) * 8 + k) * p.lat_sc + fr] = zev[k];
+                }
+            };
+            // correction of a later stage of the pass by the straight-through vector of stage s: z_e[s2] -= G[s2][s] q + g[s2][s]
+            auto correct = [&](int s, int s2, const float (&qv)[8]) {
+                const float *G = ggs + TcLayout::pair_index(GRP ? 8 : Nq, s, s2) * 72;
+                uint32_t r8[8];
+                tmem_ld8(tq + TM_RUN + 8 * s2, r8);
+                float a[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 g0 = *reinterpret_cast<const float4 *>(G + c * 8), g1 = *reinterpret_cast<const float4 *>(G + c * 8 + 4);
+                    float acc = G[64 + c];
+                    acc = __fmaf_rn(g0.x, qv[0], acc); acc = __fmaf_rn(g0.y, qv[1], acc);
+                    acc = __fmaf_rn(g0.z, qv[2], acc); acc = __fmaf_rn(g0.w, qv[3], acc);
+                    acc = __fmaf_rn(g1.x, qv[4], acc); acc = __fmaf_rn(g1.y, qv[5], acc);
+                    acc = __fmaf_rn(g1.z, qv[6], acc); acc = __fmaf_rn(g1.w, qv[7], acc);
+                    a[c] = acc;
+                }
+                tmem_wait_ld(r8);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) r8[c] = __float_as_uint(__fsub_rn(__uint_as_float(r8[c]), a[c]));
+                tmem_st8(tq + TM_RUN + 8 * s2, r8);
+            };
+            // (the pipelined order pays where the stores are the critical path: config 2 with z_q_is 148.0 -> 145.8 us; without z_q_is
+            // the frame threads are the critical path and it costs 2 %: 934 -> 955 us on the config-4 shape, so that variant keeps the
+            // classic order: prep, barrier, scan, merge, all corrections)
+            constexpr bool PIPE = ZQIS;
+            if (PIPE && w < 4) prep(0);
             for (int s = 0; s < nl; ++s) {  // s: stage within this pass, sg = s0 + s: stage of the model
                 const int sg = s0 + s;
-                if (w < 4) {
-                    // bias, latents, normalise (quantize.py:66,92 in torch's op order)
-                    uint32_t r8[8];
-                    tmem_ld8(tq + TM_RUN + 8 * s, r8);
-                    tmem_wait_ld(r8);
-                    float ss = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        zev[k] = __fadd_rn(__uint_as_float(r8[k]), bins[s * 8 + k]);
-                        const float sq = __fmul_rn(zev[k], zev[k]);
-                        ss = (k == 0) ? sq : __fadd_rn(ss, sq);
-                    }
-                    const float den = fmaxf(__fsqrt_rn(ss), 1e-12f);
-                    float e2 = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float ec = __fdiv_rn(zev[k], den);
-                        const float sqe = __fmul_rn(ec, ec);
-                        e2 = (k == 0) ? sqe : __fadd_rn(e2, sqe);
-                        es[(k >> 2) * 512 + f * 4 + (k & 3)] = __fmul_rn(2.0f, ec);
-                    }
-                    e2s[f] = e2;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars[B_E_READY]);  // the search-MMA issuer may start on this stage
-                    if (p.latents != nullptr && own) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)(sg * 8 + k) * p.lat_sc + fr] = zev[k];
-                    }
+                if constexpr (!PIPE) {
+                    if (w < 4) prep(s);
+                    named_bar_sync(1, NSCAN);  // 2e / e2 of the stage visible to every scan group
                 }
-                named_bar_sync(1, TC_NSEARCH);  // 2e / e2 of the stage visible to warps 4-7
                 ph_mark(3);
                 float bd_pub;
                 int bi_pub;
-                {
-                    // ---- search (quantize.py:96-101): the tensor core scores all 1024 codes per frame (TF32, |error| <= 2^-8),
-                    // each thread scans half of the codes of its frame for scores within SEARCH_MARGIN of the running maximum and
-                    // re-scores those candidates with the reference's exact fp32 arithmetic (first index wins ties) ----
-                    const int h = w >> 2;  // warps 0-3 take the even 64-code chunks (score buffer 0), warps 4-7 the odd ones
-                    const uint32_t cbuse = (s & 1) ? (cbu1 + (uint32_t)(s >> 1)) : (cbu0 + (uint32_t)(s >> 1));
-                    const float *CB = reinterpret_cast<const float *>(smem + ((s & 1) ? SM_CB1 : SM_CB0));
-                    uint32_t *list = reinterpret_cast<uint32_t *>(smem + SM_SB) + tid;  // (group maximum, group id) entries, [entry][thread]: no bank conflicts
-                    const float4 ea = *reinterpret_cast<const float4 *>(&es[f * 4]), eb = *reinterpret_cast<const float4 *>(&es[512 + f * 4]);
-                    const float e2 = e2s[f];
-                    float bd = __int_as_float(0x7f800000);
-                    int bidx = 0x7fffffff;
-                    float runmax = __int_as_float(0xff800000);
-                    int cnt = 0;
-                    for (int c64 = 0; c64 < 8; ++c64) {  // this thread's eight 64-code pieces: code chunks 2*ci + h of width SCW
-                        const int ci = c64 / (SCW / 64), sub = c64 % (SCW / 64);
-                        const uint32_t gc = (gstage + (uint32_t)s) * (uint32_t)NSC + (uint32_t)(2 * ci + h), sbuf = gc % 3u;
-                        const uint32_t tsc = tq + TM_SC + (uint32_t)SCW * sbuf + 64u * (uint32_t)sub;
-                        if (sub == 0) {
-                            TC_WAIT(&bars[B_SB_FULL + sbuf], (gc / 3u) & 1u);
-                            tmem_fence_after_sync();
-                        }
-                        ph_mark(8);
-                        uint32_t va[32], vb[32];
-                        tmem_ld32(tsc, va);
-                        tmem_ld32(tsc + 32, vb);
-                        tmem_wait_ld32(va);
-                        tmem_wait_ld32(vb);
-                        if (sub == SCW / 64 - 1) {
-                            tmem_fence_before_sync();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&bars[B_SB_EMPTY + sbuf]);
-                        }
-                        ph_mark(9);
-                        // maxima of the eight 8-code groups of this chunk (FMNMX3)
-                        float g[8];
-#define VRVQ_GROUP_MAX(dst, v, o)                                                                                                       \
-    {                                                                                                                                   \
-        float m_;                                                                                                                       \
-        asm("max.f32 %0, %1, %2, %3;" : "=f"(m_) : "f"(__uint_as_float(v[o])), "f"(__uint_as_float(v[o + 1])), "f"(__uint_as_float(v[o + 2]))); \
-        asm("max.f32 %0, %1, %2, %3;" : "=f"(m_) : "f"(m_), "f"(__uint_as_float(v[o + 3])), "f"(__uint_as_float(v[o + 4])));               \
-        asm("max.f32 %0, %1, %2, %3;" : "=f"(m_) : "f"(m_), "f"(__uint_as_float(v[o + 5])), "f"(__uint_as_float(v[o + 6])));               \
-        dst = fmaxf(m_, __uint_as_float(v[o + 7]));                                                                                     \
-    }
-                        VRVQ_GROUP_MAX(g[0], va, 0) VRVQ_GROUP_MAX(g[1], va, 8) VRVQ_GROUP_MAX(g[2], va, 16) VRVQ_GROUP_MAX(g[3], va, 24)
-                        VRVQ_GROUP_MAX(g[4], vb, 0) VRVQ_GROUP_MAX(g[5], vb, 8) VRVQ_GROUP_MAX(g[6], vb, 16) VRVQ_GROUP_MAX(g[7], vb, 24)
-#undef VRVQ_GROUP_MAX
-                        float cm;
-                        asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(g[0]), "f"(g[1]), "f"(g[2]));
-                        asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(cm), "f"(g[3]), "f"(g[4]));
-                        asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(cm), "f"(g[5]), "f"(g[6]));
-                        runmax = fmaxf(runmax, fmaxf(cm, g[7]));
-                        const float thr = runmax - SEARCH_MARGIN;
-                        const uint32_t gid0 = (uint32_t)((2 * ci + h) * (SCW / 8) + sub * 8);  // group id = code / 8
-                        // branch-free append of every group whose maximum is within the margin: entry = (max & ~0xff) | group id
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const uint32_t entry = (__float_as_uint(g[i]) & 0xffffff00u) | (gid0 + (uint32_t)i);
-                            const uint32_t addr = smem_u32(list) + 1024u * (uint32_t)min(cnt, 15);
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p st.shared.u32 [%3], %4;\n\t@p add.s32 %0, %0, 1;\n\t}"
-                                : "+r"(cnt)
-                                : "f"(g[i]), "f"(thr), "r"(addr), "r"(entry)
-                                : "memory");
-                        }
-                        ph_mark(10);
-                    }
-                    TC_WAIT(&bars[B_CB_FULL + (s & 1)], cbuse & 1u);  // (long complete: the score MMAs read the same buffer)
-                    {
-                        // Work list of 8-code groups to re-score exactly.  Normal case: the (<= 3) groups still within the margin of
-                        // the final maximum (the stored maximum lost its low 8 bits: 1e-4 of slack), compacted first so that a warp
-                        // runs the expensive body only max-over-lanes times.  Fallbacks: every listed group (more than 3 hits), or
-                        // every group of this thread's half of the codebook (list overflow: degenerate frames, e.g. an all-zero latent).
-                        const float thr = runmax - SEARCH_MARGIN - 1e-4f;
-                        int c0 = -1, c1 = -1, c2 = -1, nc = 0;
-                        const int nlist = cnt <= 16 ? cnt : 0;
-                        for (int i = 0; i < nlist; ++i) {
-                            const uint32_t entry = list[i * 256];
-                            const bool hit = __uint_as_float(entry & 0xffffff00u) >= thr;
-                            const int gidx = (int)(entry & 0xffu);
-                            c2 = (hit && nc == 2) ? gidx : c2;
-                            c1 = (hit && nc == 1) ? gidx : c1;
-                            c0 = (hit && nc == 0) ? gidx : c0;
-                            nc += hit ? 1 : 0;
-                        }
-                        const int mode = cnt > 16 ? 2 : nc > 3 ? 1 : 0;
-                        const int total = mode == 2 ? 64 : mode == 1 ? cnt : nc;
-                        for (int wi = 0; wi < total; ++wi) {
-                            int gid;
-                            if (mode == 0) {
-                                gid = wi == 0 ? c0 : wi == 1 ? c1 : c2;
-                            } else if (mode == 1) {
-                                const uint32_t entry = list[wi * 256];
-                                gid = (__uint_as_float(entry & 0xffffff00u) >= thr) ? (int)(entry & 0xffu) : -1;
-                            } else {
-                                gid = (2 * (wi / (SCW / 8)) + h) * (SCW / 8) + wi % (SCW / 8);  // wi-th group of this thread's half
-                            }
-                            if (gid >= 0) {
-                                const float4 *r0 = reinterpret_cast<const float4 *>(CB + gid * 32), *r1 = reinterpret_cast<const float4 *>(CB + 4096 + gid * 32);
-                                const float *c2p = CB + 8192 + gid * 8;
-#pragma unroll
-                                for (int j8 = 0; j8 < 8; ++j8) {  // exact distance of code 8*gid + jj; lexicographic (distance, index) minimum
-                                    const int jj = (j8 + lane) & 7;  // lane-staggered: the rows of different groups share their banks
-                                    const float4 ca = r0[jj], cb4 = r1[jj];
-                                    float d = __fmul_rn(ea.x, ca.x);
-                                    d = __fmaf_rn(ea.y, ca.y, d); d = __fmaf_rn(ea.z, ca.z, d); d = __fmaf_rn(ea.w, ca.w, d);
-                                    d = __fmaf_rn(eb.x, cb4.x, d); d = __fmaf_rn(eb.y, cb4.y, d); d = __fmaf_rn(eb.z, cb4.z, d); d = __fmaf_rn(eb.w, cb4.w, d);
-                                    const float t = __fadd_rn(__fadd_rn(e2, -d), c2p[jj]);  // dist = fl(fl(e2 - dot) + c2)
-                                    const int jx = gid * 8 + jj;
-                                    if (t < bd || (t == bd && jx < bidx)) { bd = t; bidx = jx; }
-                                }
-                            }
-                        }
-                    }
-                    ph_mark(11);
-                    bd_pub = bd;
-                    bi_pub = bidx;
-                }
-                named_bar_sync(1, TC_NSEARCH);
-                {
-                    float *sbd = reinterpret_cast<float *>(smem + SM_SB);  // [2][128] best distance, [2][128] best index
-                    int *sbi = reinterpret_cast<int *>(smem + SM_SB + 1024);
-                    sbd[(w >> 2) * 128 + f] = bd_pub;
-                    sbi[(w >> 2) * 128 + f] = bi_pub;
-                }
-                named_bar_sync(1, TC_NSEARCH);
+                scan_stage(s, w >> 2, f, tq, bd_pub, bi_pub);
+                publish_best(s, w >> 2, f, bd_pub, bi_pub);
+                named_bar_sync(1, NSCAN);
                 ph_mark(4);
                 if (w < 4) {
-                    // ---- merge of the two halves (first index on ties), gather, loss, straight-through (quantize.py:69-75,81-85,102) ----
+                    // ---- merge of the groups' results (first index on ties), gather, loss, straight-through (quantize.py:69-75,81-85,102) ----
                     const float *sbd = reinterpret_cast<const float *>(smem + SM_SB);
-                    const int *sbi = reinterpret_cast<const int *>(smem + SM_SB + 1024);
+                    const int *sbi = reinterpret_cast<const int *>(smem + SM_SB + 2048);
                     float best = sbd[f];
-                    int bi = sbi[f];
-                    {
-                        const float ob = sbd[128 + f];
-                        const int oi = sbi[128 + f];
-                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    int bi = sbi[f], bh = 0;
+#pragma unroll
+                    for (int h2 = 1; h2 < NSG; ++h2) {
+                        const float ob = sbd[h2 * 128 + f];
+                        const int oi = sbi[h2 * 128 + f];
+                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; bh = h2; }
                     }
-                    if (bi >= TCK) bi = 0;  // no candidate at all (NaN latent): code 0, like an argmin over NaNs that never updates
-                    const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)sg * L.stage_floats() + L.off_raw() + (size_t)bi * 8);
-                    const float4 ra = __ldg(rawp), rb = __ldg(rawp + 1);
+                    float4 ra, rb;
+                    if (bi >= TCK) {  // no candidate at all (NaN latent): code 0, like an argmin over NaNs that never updates
+                        bi = 0;
+                        const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)sg * L.stage_floats() + L.off_raw());
+                        ra = __ldg(rawp);
+                        rb = __ldg(rawp + 1);
+                    } else if constexpr (!ZQIS && VRVQ_ROW_PREFETCH) {  // the winning group already fetched the un-normalised row (publish_best)
+                        const float4 *rowp = reinterpret_cast<const float4 *>(smem + SM_SB + 4096) + (bh * 128 + f) * 2;
+                        ra = rowp[0];
+                        rb = rowp[1];
+                    } else {
+                        const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)sg * L.stage_floats() + L.off_raw() + (size_t)bi * 8);
+                        ra = __ldg(rawp);
+                        rb = __ldg(rawp + 1);
+                    }
                     const float cr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                     float qv[8], ls = 0.0f;
 #pragma unroll
@@ -851,6 +924,12 @@ auto drain = [&](int g, uint32_t tq) {
                         const float sq = __fmul_rn(diff, diff);
                         ls = (k == 0) ? sq : __fadd_rn(ls, sq);
                         qv[k] = __fadd_rn(zev[k], __fsub_rn(cr[k], zev[k]));
+                    }
+                    // the next stage first: correct its running sum, normalise, hand 2e to the search-MMA issuer
+                    if (PIPE && s + 1 < nl) {
+                        correct(s, s + 1, qv);
+                        tmem_wait_st();
+                        prep(s + 1);  // (overwrites zev: everything of stage s that needs z_e is done)
                     }
                     if (own) {
                         const float loss = __fdiv_rn(ls, 8.0f);
@@ -873,27 +952,8 @@ auto drain = [&](int g, uint32_t tq) {
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars[B_A_READY + s]);
-                    // corrections of the later stages: z_e[s2] -= G[s2][s] q + g[s2][s]
-                    for (int s2 = s + 1; s2 < nl; ++s2) {
-                        const float *G = ggs + TcLayout::pair_index(GRP ? 8 : Nq, s, s2) * 72;
-                        uint32_t r8[8];
-                        tmem_ld8(tq + TM_RUN + 8 * s2, r8);
-                        float a[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float4 g0 = *reinterpret_cast<const float4 *>(G + c * 8), g1 = *reinterpret_cast<const float4 *>(G + c * 8 + 4);
-                            float acc = G[64 + c];
-                            acc = __fmaf_rn(g0.x, qv[0], acc); acc = __fmaf_rn(g0.y, qv[1], acc);
-                            acc = __fmaf_rn(g0.z, qv[2], acc); acc = __fmaf_rn(g0.w, qv[3], acc);
-                            acc = __fmaf_rn(g1.x, qv[4], acc); acc = __fmaf_rn(g1.y, qv[5], acc);
-                            acc = __fmaf_rn(g1.z, qv[6], acc); acc = __fmaf_rn(g1.w, qv[7], acc);
-                            a[c] = acc;
-                        }
-                        tmem_wait_ld(r8);
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) r8[c] = __float_as_uint(__fsub_rn(__uint_as_float(r8[c]), a[c]));
-                        tmem_st8(tq + TM_RUN + 8 * s2, r8);
-                    }
+                    // corrections of the stages after the next one (in the shadow of the next stage's score MMAs)
+                    for (int s2 = s + (PIPE ? 2 : 1); s2 < nl; ++s2) correct(s, s2, qv);
                     tmem_wait_st();
                 }
                 ph_mark(5);
@@ -979,6 +1039,16 @@ auto drain = [&](int g, uint32_t tq) {
             ph_mark(0);
             const int q4 = w - 8, r = 32 * q4 + lane;  // TMEM lane
             const uint32_t tq = tmem + ((uint32_t)(32 * q4) << 16);
+            if constexpr (!ZQIS && !FC && VRVQ_THIRD_SCAN_GROUP) {
+                // no per-stage outputs to store: these warps are the third scan group of every stage (lane r = frame row r)
+                for (int s = 0; s < nl; ++s) {
+                    float bd;
+                    int bidx;
+                    scan_stage(s, 2, r, tq, bd, bidx);
+                    publish_best(s, 2, r, bd, bidx);
+                    named_bar_sync(1, NSCAN);
+                }
+            }
             // One unit = 128 channels x 128 lanes: column 32p + i of the TMEM buffer <-> channel 128j + 4i + p, lane r <-> frame
             // t0 - 8 + delta_p + r.  The tile owns, per class, the frames [t0 - 8 + delta_p, t0 + adv - 8 + delta_p) (the last tile of
             // an item up to T), so consecutive tiles cover every row exactly once and every 32-lane store starts on a sector.
