@@ -393,7 +393,7 @@ def run_ours(args):
         launch_ms = ms / args.steps  # the timed region is K back-to-back launches of the one fused kernel
         achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
         peak, peak_src = measured_peak()
-        info = ops.encode_launch_info(pw, B, T, Nq, dev)
+        info = ops.encode_launch_info(pw, B, T, Nq, dev, z_q_is=True)
         line = {
             "metric": "rvq_latent_frames_per_sec", "value": world * frames * args.steps / (ms_max * 1e-3), "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,

@@ -51,7 +51,7 @@ def assert_kernel(impl, m_or_pw, B, T, n_run, z_q_is=False):
     from vrvq_b200 import ops
 
     pw = m_or_pw if isinstance(m_or_pw, ops.PackedWeights) else m_or_pw.packed_weights(torch.device("cuda", torch.cuda.current_device()))
-    info = ops.encode_launch_info(pw, B, T, n_run, "cuda")
+    info = ops.encode_launch_info(pw, B, T, n_run, "cuda", z_q_is=z_q_is)
     if impl == "tc" and not ops.tc_kernel_available(pw, n_run, z_q_is=z_q_is):
         pytest.skip("no tensor-core kernel for this shape (the call is served by the CUDA-core kernel, covered by the other parameter)")
     assert info["kernel"] == impl, (impl, info)

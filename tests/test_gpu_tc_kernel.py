@@ -41,10 +41,13 @@ def test_tc_kernel_is_the_default_path():
 
     sd = gi.torch_state_dict(gi.make_state_dict(5, 8, 1024))
     pw = ops.PackedWeights.from_state_dict(sd, "cuda")
-    tc = run_impl(None, lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda"))
-    cc = run_impl("cuda", lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda"))
+    tc = run_impl(None, lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda", z_q_is=True))
+    cc = run_impl("cuda", lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda", z_q_is=True))
     assert tc["kernel"] == "tc" and tc["block"] == 512 and cc["kernel"] == "cuda", (tc, cc)
-    assert tc["grid"] == 144  # 9 tiles of 96 frames per item: one wave on 148 SMs
+    assert tc["grid"] == 144  # with z_q_is a tile's time is its stores: 9 tiles of 96 frames per item, one wave on 148 SMs
+    # without z_q_is a tile costs the same whatever its length: the fewest waves win (config-4 shard: 10 waves of 120-frame tiles)
+    nz = run_impl(None, lambda: ops.encode_launch_info(pw, 32, 5168, 8, "cuda"))
+    assert nz["kernel"] == "tc" and nz["grid"] == 148
     small = run_impl(None, lambda: ops.encode_launch_info(pw, 1, 87, 8, "cuda"))
     assert small["kernel"] == "cuda", "calls that fit one wave of the CUDA-core kernel stay on it (lower latency)"
     forced = run_impl("tc", lambda: ops.encode_launch_info(pw, 1, 87, 8, "cuda"))

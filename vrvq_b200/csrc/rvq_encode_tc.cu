@@ -1452,9 +1452,13 @@ auto drain = [&](int g, uint32_t tq) {
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static int pick_tiling(int B, int T, int sms, int *adv, int *tiles_per_b) {
-    // tiles of `adv` frames (multiple of 8, <= 120: 8 of the 128 rows are the halo) per batch item; minimise waves x adv
+static int pick_tiling(int B, int T, int sms, bool zqis, int *adv, int *tiles_per_b) {
+    // tiles of `adv` frames (multiple of 8, <= 120: 8 of the 128 rows are the halo) per batch item; minimise waves x time per tile.
+    // With z_q_is a tile's time is its stores, proportional to its frames (+ a fixed part: pipeline fill, first search); without,
+    // it is the in_proj stream and the serial stage chain, the same for any number of frames (measured: 85.9 us per wave at 104,
+    // 112 and 120 frames on the config-4 shape), so the fewest waves win and the frame count only breaks ties.
     const int nt_min = (T + 119) / 120;
+    const long fixed = zqis ? 24 : 1000;
     long best_cost = -1;
     int best_nt = nt_min, best_adv = 120;
     for (int nt = nt_min; nt <= nt_min * 4 + 4; ++nt) {
@@ -1464,7 +1468,7 @@ static int pick_tiling(int B, int T, int sms, int *adv, int *tiles_per_b) {
         const int nt_eff = (T + a - 1) / a;
         const long tiles = (long)B * nt_eff;
         const long waves = (tiles + sms - 1) / sms;
-        const long cost = waves * (a + 24);  // + a fixed per-tile cost (pipeline fill, first search)
+        const long cost = waves * (a + fixed);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nt = nt_eff; best_adv = a; }
     }
     *adv = best_adv;
@@ -1567,7 +1571,7 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
         set_error("cannot query the SM count of the current device");
         return VRVQ_ECUDA;
     }
-    pick_tiling(a->B, a->T, sms, &P.adv, &P.tiles_per_b);
+    pick_tiling(a->B, a->T, sms, a->z_q_is != nullptr, &P.adv, &P.tiles_per_b);
     if (const char *dbg = getenv("VRVQ_DEBUG_TILE_FRAMES")) {  // profiling knob
         const int v = atoi(dbg);
         if (v >= 8 && v <= 120 && v % 8 == 0) { P.adv = v; P.tiles_per_b = (a->T + v - 1) / v; }
@@ -1720,7 +1724,7 @@ int from_codes_tc(const vrvq_from_codes_args *a, void *stream) {
         set_error("cannot query the SM count of the current device");
         return VRVQ_ECUDA;
     }
-    pick_tiling(a->B, a->T, sms, &P.adv, &P.tiles_per_b);
+    pick_tiling(a->B, a->T, sms, a->z_q_is != nullptr, &P.adv, &P.tiles_per_b);
     P.n_tiles = P.tiles_per_b * a->B;
     P.zmode = ZMODE_LDG;  // no latent on this path
     ZMaps zmap;

@@ -174,13 +174,16 @@ def rvq_encode_into(w: PackedWeights, z: torch.Tensor, out: EncodeOutputs, n_run
     return out
 
 
-def encode_launch_info(w: PackedWeights, B: int, T: int, n_run: int, device):
+def encode_launch_info(w: PackedWeights, B: int, T: int, n_run: int, device, z_q_is: bool = False):
     a = EncodeArgs()
     a.struct_size = C.sizeof(EncodeArgs)
     a.B, a.T, a.input_dim, a.n_codebooks, a.codebook_size, a.n_run = B, T, w.input_dim, w.n_codebooks, w.codebook_size, n_run
     dummy = w.blob.data_ptr()
     a.blob, a.z, a.codes = dummy, dummy, dummy
     a.z_stride_b, a.z_stride_d = w.input_dim * T, T
+    if z_q_is:  # the per-stage outputs change the kernel choice and the tiling
+        a.z_q_is = dummy
+        a.z_q_is_stride_b, a.z_q_is_stride_q, a.z_q_is_stride_d = n_run * w.input_dim * T, w.input_dim * T, T
     g, b, s = C.c_int(), C.c_int(), C.c_int()
     with torch.cuda.device(device):
         check(_lib.lib().vrvq_rvq_encode_launch_info(C.byref(a), C.byref(g), C.byref(b), C.byref(s)), "vrvq_rvq_encode_launch_info")
