@@ -56,14 +56,15 @@ constexpr int TC_NTH = 512;    // 16 warps: 8 search/load, 4 epilogue, MMA issue
 constexpr int TC_NSEARCH = 256;
 
 // shared memory map (bytes).  Phase L uses [0, 49152); phase S re-uses that region.
-constexpr int SM_LR = 0;           // phase L ring, 3 slots x 16 KB: W_in [8 kg][128 rows][4] (rows 0-63 heads, 64-127 remainders);
-constexpr int L_SLOT = 16384, L_SLOTS = 3;  // the matching A operand (the split latent chunk) lives in tensor memory
+constexpr int SM_LR = 0;           // phase L W_in ring, 4 slots x 16 KB: [8 kg][128 rows][4] (rows 0-63 heads, 64-127 remainders)
+constexpr int L_SLOT = 16384, WL_SLOTS = 4;  // (4 chunks of prefetch: a chunk lands ~1.8k cycles after its request while z streams in)
+constexpr int L_SLOTS = 3;         // the matching A operand (the split latent chunk) lives in tensor memory: 3 slots
 // phase L latent staging ring (free in phase L: the per-stage A tiles, the W_out ring and codebook buffer 1 live there later):
-// 3 slots x [64 channels][132 floats].  A slot is filled by the TMA unit -- one cp.async.bulk.tensor box per slot when the row
-// pitch allows a tensor map (16-byte multiples), else one cp.async.bulk per channel row from the 16-byte aligned address at or
-// below the row's first frame (the row then sits `shift` = 0..3 floats into its 528-byte smem row) -- so the 256 loader threads
-// read the latent with conflict-free LDS (lane = frame) instead of issuing 128 misaligned LDGs per chunk and waiting on HBM.
-constexpr int SM_ZR = 49152, Z_CH = 64, Z_PITCH = 132, Z_SLOT = Z_CH * Z_PITCH * 4, Z_SLOTS = 3;
+// 5 slots x [32 channels][132 floats], one slot per 32-channel chunk.  A slot is filled by the TMA unit -- cp.async.bulk.tensor
+// boxes through the channel-class tensor maps (pick_zmode); or, for A/B runs, one cp.async.bulk per channel row from the 16-byte
+// aligned address at or below the row's first frame -- so the 256 loader threads read the latent with conflict-free LDS
+// (lane = frame) instead of issuing 128 misaligned LDGs per chunk and waiting on HBM.
+constexpr int SM_ZR = WL_SLOTS * L_SLOT, Z_CH = 32, Z_PITCH = 132, Z_SLOT = Z_CH * Z_PITCH * 4, Z_SLOTS = 5;
 constexpr int SM_AT = 0;           // phase S: per-stage A tiles, 8 x (hi 4 KB | lo 4 KB): [2 kg][128 frames][4]
 constexpr int SM_AM = 65536;       // phase S: mask tile (A operand of the bias rows of the final GEMM) [2 kg][128][4]
 constexpr int SM_WO = 69632;       // phase S: W_out ring, 4 slots x 12 KB (hi | lo | bias tile)
@@ -88,13 +89,13 @@ constexpr int F_SLOT = 40960, F_SLOTS = 3, F_ITEMS = 5;  // final-GEMM ring (<= 
 static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 static_assert(SM_WO + W_SLOTS * W_SLOT == SM_CB1 && SM_CB1 + 36864 == SM_CB0 && SM_CB0 + 36864 == SM_ES, "shared memory map");
 static_assert(SM_WO + F_SLOTS * F_SLOT == SM_ES, "final ring covers [SM_WO, SM_ES)");
-static_assert(L_SLOTS * L_SLOT <= SM_ZR && SM_ZR + Z_SLOTS * Z_SLOT <= SM_CB0, "phase-L rings must not reach codebook buffer 0");
+static_assert(SM_ZR + Z_SLOTS * Z_SLOT <= SM_CB0, "phase-L rings must not reach codebook buffer 0");
 static_assert(SM_ZR % 128 == 0 && Z_SLOT % 128 == 0, "TMA destinations are 128-byte aligned");
 
 enum {
     B_L_FULL = 0, B_L_EMPTY = 4, B_SET_FULL = 24, B_SET_EMPTY = 26, B_W_FULL = 28, B_W_EMPTY = 32,
     B_D_FULL = 36, B_D_EMPTY = 38, B_CB_FULL = 40, B_A_READY = 42, B_ZQ_READY = 50, B_MMA_DONE = 51, B_F_FULL = 52, B_F_EMPTY = 56,
-    B_E_READY = 60, B_SB_FULL = 61, B_SB_EMPTY = 64, B_Z_FULL = 67, B_Z_EMPTY = 70, B_L_FULL2 = 73, B_COUNT = 76
+    B_E_READY = 60, B_SB_FULL = 61, B_SB_EMPTY = 64, B_L_FULL2 = 73, B_WL_FULL = 76, B_WL_EMPTY = 80, B_Z_FULL = 84, B_Z_EMPTY = 89, B_COUNT = 94
 };
 enum { ZMODE_LDG = 0, ZMODE_BULK = 1, ZMODE_TMA = 2 };  // how phase L fetches the latent
 
@@ -231,9 +232,12 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
 
     // ---- one-time setup -------------------------------------------------------------------------------------
     if (tid == 0) {
-        // phase-L slot: 8 loader warps + the producer's expect_tx arrive; released by one tcgen05.commit
+        // phase-L A slot (tensor memory): the 8 loader warps arrive; released by one tcgen05.commit
         // (a slot has two full barriers, for its even and its odd uses: see l_full)
-        for (int i = 0; i < L_SLOTS; ++i) { mbar_init(&bars[B_L_FULL + i], 9); mbar_init(&bars[B_L_FULL2 + i], 9); mbar_init(&bars[B_L_EMPTY + i], 1); }
+        for (int i = 0; i < L_SLOTS; ++i) { mbar_init(&bars[B_L_FULL + i], 8); mbar_init(&bars[B_L_FULL2 + i], 8); mbar_init(&bars[B_L_EMPTY + i], 1); }
+        // W_in ring slot: the producer's expect_tx + bytes; released by the commit of the chunk's MMAs (uses of a slot are 4 chunks
+        // apart: always the same issuing thread, so one barrier per slot is enough here)
+        for (int i = 0; i < WL_SLOTS; ++i) { mbar_init(&bars[B_WL_FULL + i], 1); mbar_init(&bars[B_WL_EMPTY + i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars[B_SET_FULL + i], 2); mbar_init(&bars[B_SET_EMPTY + i], 4);  // full: one commit per phase-L issuer
             mbar_init(&bars[B_D_FULL + i], 1); mbar_init(&bars[B_D_EMPTY + i], 4);
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     // totals, since the passes of different groups have different chunk counts.
     const int n_grp = GRP ? (n_run + 7) / 8 : 1;
     const int n_my_passes = n_my_tiles * n_grp;
-    uint32_t lbase = 0, gbase = 0, zbase = 0;  // phase-L chunks / accumulator groups / latent slots consumed so far
+    uint32_t lbase = 0, gbase = 0, zbase = 0;  // phase-L chunks / accumulator groups / latent chunks consumed so far
     uint32_t astep = 0;                        // grouped final GEMM: A staging steps so far
     unsigned short *codes_lo = reinterpret_cast<unsigned short *>(smem + SM_ONES), *codes_hi = reinterpret_cast<unsigned short *>(smem + SM_XC);
     auto code_slot = [&](int s) -> unsigned short * { return (s < 16 ? codes_lo : codes_hi) + (s & 15) * 128; };  // [128 rows] of stage s (GRP)
@@ -400,17 +404,19 @@ auto drain = [&](int g, uint32_t tq) {
             for (int c = X0; c < NCT; c += solo ? 1 : 2) {
                 const int X = c & 1;
                 const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS;
+                const uint32_t wsl = n % WL_SLOTS;
                 {
                     uint32_t par;
                     uint64_t *fb = l_full(n, &par);
-                    TC_WAIT(fb, par);
+                    TC_WAIT(fb, par);                                           // A operand (loaders)
+                    TC_WAIT(&bars[B_WL_FULL + wsl], (n / WL_SLOTS) & 1u);      // B operand (W_in chunk)
                 }
                 if (PROFILE && it == 0 && X == 0) trace(4, c);
                 const uint32_t gg = gbase + (uint32_t)(c >> 2), set = gg & 1u;
                 if ((c & 3) == X && gg >= 2) TC_WAIT(&bars[B_SET_EMPTY + set], ((gg >> 1) - 1) & 1u);
                 tmem_fence_after_sync();
                 const uint32_t a_hi = tmem + TM_AL + 64u * sl, a_lo = a_hi + 32;  // A in tensor memory: 8 columns per k-step
-                const uint64_t bh = desc128(smem_base + SM_LR + sl * L_SLOT), bl = bh + (1024 >> 4);  // B rows 0-63 heads, 64-127 remainders
+                const uint64_t bh = desc128(smem_base + SM_LR + wsl * L_SLOT), bl = bh + (1024 >> 4);  // B rows 0-63 heads, 64-127 remainders
                 const uint32_t d = tmem + TM_SET + 128u * set + 64u * (uint32_t)X;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
@@ -419,6 +425,7 @@ auto drain = [&](int g, uint32_t tq) {
                     umma_tf32_ts(d, a_hi + 8 * ks, bh + ks * (4096 >> 4), ID_64, true);
                 }
                 umma_commit(&bars[B_L_EMPTY + sl]);
+                umma_commit(&bars[B_WL_EMPTY + wsl]);
                 if ((c & 3) == 2 + X) umma_commit(&bars[B_SET_FULL + set]);
                 if (PROFILE && it == 0 && X == 0) trace(5, c);
             }
@@ -623,10 +630,10 @@ auto drain = [&](int g, uint32_t tq) {
                 auto stage = [&](auto nc_tag) {
                     constexpr int NC = decltype(nc_tag)::value;
                     for (int c = 0; c < NCH; ++c) {
-                        const uint32_t zn = zbase + (uint32_t)(c >> 1), zsl = zn % Z_SLOTS;
-                        if ((c & 1) == 0) TC_WAIT(&bars[B_Z_FULL + zsl], (zn / Z_SLOTS) & 1u);
+                        const uint32_t zn = zbase + (uint32_t)c, zsl = zn % Z_SLOTS;
+                        TC_WAIT(&bars[B_Z_FULL + zsl], (zn / Z_SLOTS) & 1u);
                         if (PROFILE && tid == 0 && it == 0) trace(0, c);
-                        const float *zr = reinterpret_cast<const float *>(smem + SM_ZR + zsl * Z_SLOT) + ((32 * (c & 1) + 16 * q) / NC) * Z_PITCH + col;
+                        const float *zr = reinterpret_cast<const float *>(smem + SM_ZR + zsl * Z_SLOT) + ((16 * q) / NC) * Z_PITCH + col;
                         float h[16], l[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -634,10 +641,8 @@ auto drain = [&](int g, uint32_t tq) {
                             h[i] = __uint_as_float(__float_as_uint(x) & 0xffffe000u);  // TF32 head by truncation; x - head is exact
                             l[i] = __fsub_rn(x, h[i]);
                         }
-                        if (c & 1) {  // both halves of the slot are in registers: hand it back to the producer
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&bars[B_Z_EMPTY + zsl]);
-                        }
+                        __syncwarp();  // the slot is in registers: hand it back to the producer
+                        if (lane == 0) mbar_arrive(&bars[B_Z_EMPTY + zsl]);
                         if (PROFILE && tid == 0 && it == 0) trace(1, c);
                         const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS, use = n / L_SLOTS;
                         if (use >= 1) {
@@ -1261,7 +1266,7 @@ auto drain = [&](int g, uint32_t tq) {
             if (!FC && P.zmode != ZMODE_LDG) {
                 // ---- phase L: producer of the latent staging ring (this warp has nothing else to do before the searches) ----
                 const int fvz = t0 + fv - tstart;  // frames to stage per row (<= 128)
-                for (int zc = 0; zc < NCH / 2; ++zc) {
+                for (int zc = 0; zc < NCH; ++zc) {
                     const uint32_t m = zbase + (uint32_t)zc, slot = m % Z_SLOTS, use = m / Z_SLOTS;
                     if (use >= 1) TC_WAIT(&bars[B_Z_EMPTY + slot], (use - 1) & 1u);
                     unsigned char *dst = smem + SM_ZR + slot * Z_SLOT;
@@ -1275,22 +1280,15 @@ auto drain = [&](int g, uint32_t tq) {
                     } else {
                         // one bulk copy per channel row, from the 16-byte aligned address at or below its first frame to the
                         // 16-byte boundary at or above its last one (<= 12 bytes of over-read on either side, inside the same
-                        // 16-byte granule as a valid element); lane r copies rows r and r + 32 of the slot
+                        // 16-byte granule as a valid element); lane r copies row r of the slot
                         const float *row0 = p.z + (long long)b * p.z_sb + (long long)(Z_CH * zc) * p.z_sd + tstart;
-                        unsigned long long a0[2];
-                        uint32_t nb[2];
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const unsigned long long a = reinterpret_cast<unsigned long long>(row0 + (long long)(lane + 32 * k) * p.z_sd);
-                            a0[k] = a & ~15ull;
-                            nb[k] = (uint32_t)(((a + 4ull * (unsigned long long)fvz + 15ull) & ~15ull) - a0[k]);
-                        }
-                        const uint32_t total = __reduce_add_sync(0xffffffffu, nb[0] + nb[1]);
+                        const unsigned long long a = reinterpret_cast<unsigned long long>(row0 + (long long)lane * p.z_sd);
+                        const unsigned long long a0 = a & ~15ull;
+                        const uint32_t nb = (uint32_t)(((a + 4ull * (unsigned long long)fvz + 15ull) & ~15ull) - a0);
+                        const uint32_t total = __reduce_add_sync(0xffffffffu, nb);
                         if (lane == 0) mbar_arrive_expect_tx(&bars[B_Z_FULL + slot], total);
                         __syncwarp();
-#pragma unroll
-                        for (int k = 0; k < 2; ++k)
-                            bulk_g2s(dst + (lane + 32 * k) * (Z_PITCH * 4), reinterpret_cast<const void *>(a0[k]), nb[k], &bars[B_Z_FULL + slot]);
+                        bulk_g2s(dst + lane * (Z_PITCH * 4), reinterpret_cast<const void *>(a0), nb, &bars[B_Z_FULL + slot]);
                     }
                 }
             }
@@ -1331,13 +1329,11 @@ auto drain = [&](int g, uint32_t tq) {
                 mbar_arrive_expect_tx(&bars[B_CB_FULL + 0], 36864);
                 bulk_g2s(smem + SM_CB0, P.tc + TL.off_cbk() + (size_t)s0 * 9216, 36864, &bars[B_CB_FULL + 0]);
                 for (int c = 0; c < NCT; ++c) {
-                    const uint32_t m = lbase + (uint32_t)c, slot = m % L_SLOTS, use = m / L_SLOTS;
-                    if (use >= 1) TC_WAIT(&bars[B_L_EMPTY + slot], (use - 1) & 1u);
+                    const uint32_t m = lbase + (uint32_t)c, slot = m % WL_SLOTS, use = m / WL_SLOTS;
+                    if (use >= 1) TC_WAIT(&bars[B_WL_EMPTY + slot], (use - 1) & 1u);
                     if (PROFILE && it == 0) trace(6, c);
-                    uint32_t par_;
-                    uint64_t *fb = l_full(m, &par_);
-                    mbar_arrive_expect_tx(fb, 16384);
-                    bulk_g2s(smem + SM_LR + slot * L_SLOT, (c < NCH ? win : gx) + (size_t)c * 4096, 16384, fb);
+                    mbar_arrive_expect_tx(&bars[B_WL_FULL + slot], 16384);
+                    bulk_g2s(smem + SM_LR + slot * L_SLOT, (c < NCH ? win : gx) + (size_t)c * 4096, 16384, &bars[B_WL_FULL + slot]);
                 }
             }
             ph_mark(0);
@@ -1424,7 +1420,7 @@ auto drain = [&](int g, uint32_t tq) {
         cbu1 += (uint32_t)(nl >> 1);
         lbase += (uint32_t)NCT;
         gbase += (uint32_t)(NCT / 4);
-        zbase += (uint32_t)(NCH / 2);
+        zbase += (uint32_t)NCH;
         tmem_fence_before_sync();
         __syncthreads();  // end of tile: every MMA of the tile has completed (the epilogue waited for the last one)
         tmem_fence_after_sync();
