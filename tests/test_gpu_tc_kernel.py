@@ -203,3 +203,69 @@ def test_random_shapes_tensor_core_vs_cuda_core():
     spec.loader.exec_module(mod)
     worst = mod.run_cases(11, 14, verbose=False)
     assert worst <= 1e-5
+
+
+@pytest.mark.parametrize("D,Nq,B,T,n_run,vbr", [
+    (1024, 28, 2, 200, 28, True),    # conf/base_24kbps.yml: four stage groups, masks over 28 stages, several tiles per item
+    (1024, 28, 3, 131, 12, False),   # CBR early exit inside the second group (quantize.py:183-184)
+    (1024, 28, 2, 64, 3, False),     # early exit inside the first group: one pass of the grouped kernel
+    (512, 9, 2, 130, 9, True),       # class defaults of ResidualVectorQuantize: one stage in the second group
+    (256, 17, 4, 33, 17, True),      # three groups, ragged single tiles
+    (1024, 32, 1, 87, 32, True),     # the largest supported model, odd T (four channel classes of the latent tensor maps)
+    (1024, 16, 2, 1, 16, False),     # T = 1
+])
+def test_grouped_tensor_core_kernel_matches_cuda_core_kernel_and_oracle(D, Nq, B, T, n_run, vbr):
+    """Models with more than 8 codebooks run the tensor-core kernel in groups of 8 stages (no z_q_is): per-group in_proj,
+    cross-group corrections as virtual-channel chunks, final z_q from codes.  Against the oracle (audited codes, exact masks and
+    kept counts, z_q / latents within 1e-5) and the CUDA-core kernel."""
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(300 + Nq + D, Nq, D))
+    w = c_oracle.OracleWeights.from_state_dict(sd)
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    assert run_impl("tc", lambda: ops.encode_launch_info(pw, B, T, n_run, "cuda"))["kernel"] == "tc"
+    assert run_impl("tc", lambda: ops.encode_launch_info(pw, B, T, n_run, "cuda", z_q_is=True))["kernel"] == "cuda", "z_q_is needs the CUDA-core kernel here"
+    z_np = gi.make_latents(400 + T, B, D, T, 1.0)
+    imp_np = gi.make_imp_map(500 + T, B, T) if vbr else None
+    z = torch.from_numpy(z_np).cuda()
+    imp = torch.from_numpy(imp_np).cuda() if vbr else None
+    level = 0.45 if vbr else None
+
+    def call():
+        return ops.rvq_encode(pw, z, n_run, imp, level, want_z_q_is=False, want_loss_pf=True)
+
+    a = run_impl("tc", call)
+    c = run_impl("cuda", call)
+    o = c_oracle.encode(w, z_np, n_run if not vbr else None, imp_np, level, want_z_q_is=False)
+    excused, skip = H.assert_codes_match(w, o, npy(a.codes))
+    assert np.array_equal(npy(a.mask), o["mask"]) and np.array_equal(npy(a.mask), npy(c.mask))
+    assert np.array_equal(npy(a.kept), o["kept"])
+    H.assert_close_frames(npy(a.z_q), o["z_q"], skip=skip, what="z_q vs oracle")
+    H.assert_close_frames(npy(a.latents), o["latents"], skip=skip, what="latents vs oracle")
+    same = (npy(a.codes) == npy(c.codes)).all(axis=1)
+    assert (~same).sum() <= max(1, int(1e-3 * same.size))
+    H.assert_close_frames(npy(a.z_q), npy(c.z_q), skip=~same, what="z_q: grouped tensor-core vs CUDA-core kernel")
+    if excused == 0:
+        np.testing.assert_allclose(npy(a.loss_pf), o["loss_pf"], rtol=2e-4, atol=1e-7)
+        assert a.loss_sum.item() == pytest.approx(o["loss_masked_sum"], rel=1e-5)
+
+
+def test_grouped_kernel_views_and_many_tiles_per_cta():
+    """Config-3 shape at reduced batch: several tiles x 4 groups per CTA (ring positions are running totals across passes of
+    different length), and a frame-range view reproduces the full call bit for bit."""
+    from vrvq_b200 import ops
+
+    sd = gi.torch_state_dict(gi.make_state_dict(71, 28, 1024))
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    B, T = 48, 431
+    z = torch.randn(B, 1024, T, generator=torch.Generator().manual_seed(5)).cuda()
+    full = ops.rvq_encode(pw, z, None, None, None)
+    info = ops.encode_launch_info(pw, B, T, 28, "cuda")
+    assert info["kernel"] == "tc" and B * -(-T // 120) > info["grid"], "more tiles than CTAs"
+    part = ops.rvq_encode(pw, z[:, :, 64:300], None, None, None)
+    assert torch.equal(part.codes, full.codes[:, :, 64:300]) and torch.equal(part.z_q, full.z_q[:, :, 64:300])
+    w = c_oracle.OracleWeights.from_state_dict(sd)
+    idx = [0, 23, 47]
+    o = c_oracle.encode(w, npy(z[idx]), None, want_z_q_is=False)
+    excused, skip = H.assert_codes_match(w, o, npy(full.codes[idx]))
+    H.assert_close_frames(npy(full.z_q[idx]), o["z_q"], skip=skip, what="z_q")

@@ -988,6 +988,7 @@ auto drain = [&](int g, uint32_t tq) {
                     // stages go through a two-slot staging ring four at a time (rows of masked stages zero), then one step with the
                     // mask tiles that multiply the bias rows.  Warps 0-3 build items 0-1 of a step, warps 4-7 items 2-3; row = f.
                     const int hsel = w >> 2;
+                    named_bar_sync(1, NSCAN);  // the code of the last stage (written by the frame threads in its merge) is visible to warps 4-7
                     uint32_t m = astep;
                     for (int j = 0; j < NJ; ++j)
                         for (int st = 0; st < G_NST; ++st, ++m) {
