@@ -133,7 +133,8 @@ def _tc_layout(Nq, D):
     L["off_bout"] = L["off_wout"] + Nq * nj * 3072
     L["off_gg"] = L["off_bout"] + ngrp * nj * 2048
     L["off_bin"] = L["off_gg"] + (Nq * (Nq - 1) // 2 * 72 + 3) // 4 * 4
-    L["off_cbk"] = L["off_bin"] + 2 * Nq * 8
+    L["off_spc"] = L["off_bin"] + 2 * Nq * 8
+    L["off_cbk"] = L["off_spc"] + Nq * 16
     L["total"] = L["off_cbk"] + Nq * 9216
     return L
 

@@ -269,3 +269,40 @@ def test_grouped_kernel_views_and_many_tiles_per_cta():
     o = c_oracle.encode(w, npy(z[idx]), None, want_z_q_is=False)
     excused, skip = H.assert_codes_match(w, o, npy(full.codes[idx]))
     H.assert_close_frames(npy(full.z_q[idx]), o["z_q"], skip=skip, what="z_q")
+
+
+def test_codebook_rows_that_do_not_normalise_to_unit_vectors():
+    """F.normalize leaves a row with norm < 1e-12 at ~0, so its distance e2 - 0 + c2 ~ 1 beats every unit row whenever the
+    best cosine is below 0.5 -- but its TF32 score is 0, which the margin filter would drop.  Such rows are listed in the blob
+    (section SPC) and always re-scored exactly: the tensor-core kernel must pick them exactly where the oracle does."""
+    from vrvq_b200 import ops
+
+    D, Nq, B, T = 256, 3, 2, 150
+    raw = gi.make_state_dict(21, Nq, D)
+    rng = np.random.Generator(np.random.PCG64(5))
+    for s in (0, 2):  # codebooks crowded into a cone, so that most latents see a best cosine < 0.5 ...
+        cb = np.zeros((1024, 8), np.float32)
+        cb[:, 0] = 1.0
+        cb += 0.15 * rng.normal(size=cb.shape).astype(np.float32)
+        cb[7] = 0.0          # ... and prefer the all-zero row
+        cb[900] = 1e-20      # ... or the one whose norm is below F.normalize's eps
+        raw[f"quantizers.{s}.codebook.weight"] = cb
+    sd = gi.torch_state_dict(raw)
+    w = c_oracle.OracleWeights.from_state_dict(sd)
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    hdr = pw.host_blob[:16].view(np.int32)
+    from tests.test_abi_cpu import _tc_layout
+    spc = pw.host_blob[int(hdr[6]) + _tc_layout(Nq, D)["off_spc"]:][:16 * Nq].view(np.int32).reshape(Nq, 16)
+    assert spc[0, 0] == 2 and set(spc[0, 1:3]) == {7, 900} and spc[1, 0] == 0 and spc[2, 0] == 2
+    z_np = gi.make_latents(22, B, D, T, 1.0)
+    o = c_oracle.encode(w, z_np, None, None, None, want_z_q_is=True)
+    assert np.isin(o["codes"][:, 0], (7, 900)).mean() > 0.2, "the case must exercise the degenerate rows"
+    for impl in ("tc", "cuda"):
+        out = run_impl(impl, lambda: ops.rvq_encode(pw, torch.from_numpy(z_np).cuda(), None, None, None, want_z_q_is=True))
+        # (the two degenerate rows sit at distance 1 +- 1e-7 from EVERY frame: which of the two wins is decided by the last bit of
+        # e2, so audited near-ties between codes 7 and 900 are expected here -- what must not happen is a frame that prefers a
+        # unit row although a degenerate one is closer)
+        excused, skip = H.assert_codes_match(w, o, npy(out.codes), max_excused_frac=0.1, what=f"codes ({impl})")
+        differ = (npy(out.codes) != o["codes"])
+        assert np.isin(npy(out.codes)[differ], (7, 900)).all() or excused == 0
+        H.assert_close_frames(npy(out.z_q), o["z_q"], skip=skip, what=f"z_q ({impl})")

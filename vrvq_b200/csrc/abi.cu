@@ -185,14 +185,22 @@ static void pack_tc_section(int Nq, int D, int K, const float *w_in, const float
             for (int j = 0; j < 8 * (s / 8); ++j) acc -= Gd[((size_t)s * Nq + j) * 72 + 64 + c];
             tc[T.off_bin() + (size_t)Nq * CD + (size_t)s * CD + c] = (float)acc;
         }
-    // CBK: F.normalize(codebook) (same arithmetic as the P1 section) as a [2 kg][K][4] tile, then c2[K]
+    // CBK: F.normalize(codebook) (same arithmetic as the P1 section) as a [2 kg][K][4] tile, then c2[K]; SPC: the non-unit rows
     for (int s = 0; s < Nq; ++s) {
         float *cbk = tc + T.off_cbk() + (size_t)s * 9216;
+        int32_t *spc = reinterpret_cast<int32_t *>(tc + T.off_spc() + (size_t)s * 16);
+        int nsp = 0;
         for (int j = 0; j < K; ++j) {
             float e[CD];
             normalize_row(codebook + ((size_t)s * K + j) * CD, e, cbk + 8192 + j);
             for (int k = 0; k < CD; ++k) cbk[(size_t)(k / 4) * 4096 + (size_t)j * 4 + (k % 4)] = e[k];
+            const float c2 = cbk[8192 + j];
+            if (!(fabsf(c2 - 1.0f) <= 1e-3f)) {  // (also catches NaN rows)
+                if (nsp < 15) spc[1 + nsp] = j;
+                ++nsp;
+            }
         }
+        spc[0] = nsp > 15 ? 255 : nsp;
     }
 }
 

@@ -138,6 +138,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 //   BOUT [groups][D/128 chunks][hi,lo][2 kg][128 rows][4]  bias as a B operand for the final GEMM: element (row, k) = b_out[8g + k][channel(row)]
 //   GG   [Nq(Nq-1)/2][72]  for j < s: G = W_in[s] W_out[j] (8x8, row-major [c][k]) followed by g = W_in[s] b_out[j] (8)
 //   BIN  [Nq][8] b_in, then [Nq][8] b_in' = b_in[s] - sum_{j < 8 (s / 8)} g[s][j]  (the cross-group bias terms folded in)
+//   SPC  [Nq][16] (int32 bits): codes whose normalised row is not a unit vector (|c2 - 1| > 1e-3: rows with norm < 1e-12, which
+//        F.normalize leaves at ~0).  The TF32 score filter ranks codes by 2 e.c only, which equals -distance up to a constant
+//        only for unit rows; these codes are always re-scored exactly.  [0] = count (255: more than 15, the stage falls back to
+//        the exact scan), [1..15] = indices
 //   CBK  [Nq][9216]: normalised codebook as a K-major B operand [2 kg][1024 codes][4] (also read row-wise for the exact re-scoring),
 //        then c2[1024]
 struct TcLayout {
@@ -156,7 +160,8 @@ struct TcLayout {
     __host__ __device__ constexpr int off_gg() const { return off_bout() + ngrp() * nj() * 2048; }
     __host__ __device__ constexpr int gg_floats() const { return (Nq * (Nq - 1) / 2 * 72 + 3) / 4 * 4; }
     __host__ __device__ constexpr int off_bin() const { return off_gg() + gg_floats(); }
-    __host__ __device__ constexpr int off_cbk() const { return off_bin() + 2 * Nq * 8; }
+    __host__ __device__ constexpr int off_spc() const { return off_bin() + 2 * Nq * 8; }
+    __host__ __device__ constexpr int off_cbk() const { return off_spc() + Nq * 16; }
     __host__ __device__ constexpr int total() const { return off_cbk() + Nq * 9216; }
     __host__ __device__ static constexpr int pair_index(int nq, int j, int s) { return j * nq - j * (j + 1) / 2 + (s - j - 1); }
 };

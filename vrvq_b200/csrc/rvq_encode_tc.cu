@@ -521,7 +521,11 @@ auto drain = [&](int g, uint32_t tq) {
                             c0 = (hit && nc == 0) ? gidx : c0;
                             nc += hit ? 1 : 0;
                         }
-                        const int mode = cnt > 16 ? 2 : nc > 3 ? 1 : 0;
+                        // codes whose normalised row is not a unit vector (blob section SPC; none in a trained or random model): the
+                        // score filter cannot rank them, so they are always re-scored exactly -- or, if there are many, everything is
+                        const int *spc = reinterpret_cast<const int *>(P.tc + TL.off_spc()) + (s0 + s) * 16;
+                        const int nsp = __ldg(spc);
+                        const int mode = (cnt > 16 || nsp > 15) ? 2 : nc > 3 ? 1 : 0;
                         const int total = mode == 2 ? ((NSC - h + NSG - 1) / NSG) * (SCW / 8) : mode == 1 ? cnt : nc;
                         for (int wi = 0; wi < total; ++wi) {
                             int gid;
@@ -548,6 +552,15 @@ auto drain = [&](int g, uint32_t tq) {
                                     if (t < bd || (t == bd && jx < bidx)) { bd = t; bidx = jx; }
                                 }
                             }
+                        }
+                        for (int i = 0; i < nsp && nsp <= 15; ++i) {  // (every scan group re-scores them: the merge is idempotent)
+                            const int jx = __ldg(spc + 1 + i);
+                            const float4 ca = *reinterpret_cast<const float4 *>(CB + jx * 4), cb4 = *reinterpret_cast<const float4 *>(CB + 4096 + jx * 4);
+                            float d = __fmul_rn(ea.x, ca.x);
+                            d = __fmaf_rn(ea.y, ca.y, d); d = __fmaf_rn(ea.z, ca.z, d); d = __fmaf_rn(ea.w, ca.w, d);
+                            d = __fmaf_rn(eb.x, cb4.x, d); d = __fmaf_rn(eb.y, cb4.y, d); d = __fmaf_rn(eb.z, cb4.z, d); d = __fmaf_rn(eb.w, cb4.w, d);
+                            const float t = __fadd_rn(__fadd_rn(e2, -d), CB[8192 + jx]);
+                            if (t < bd || (t == bd && jx < bidx)) { bd = t; bidx = jx; }
                         }
                     }
                     ph_mark(11);
