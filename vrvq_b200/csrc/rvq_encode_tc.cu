@@ -42,6 +42,9 @@
 #include "common.cuh"
 #include "encode_params.cuh"
 
+// Experiment kept compiled out: the epilogue warps as a third scan group when there is no z_q_is to store --
+// slower in both forms tried (three groups on three 128-code buffers: +4-8 %; 64-code chunks in six buffers: +20 %), because the
+// stage chain is bound by the frame threads' serial part and by hand-over latency, not by scan throughput; not maintained for GRP.
 #ifndef VRVQ_THIRD_SCAN_GROUP
 #define VRVQ_THIRD_SCAN_GROUP 0
 #endif
@@ -95,7 +98,7 @@ static_assert(SM_ZR % 128 == 0 && Z_SLOT % 128 == 0, "TMA destinations are 128-b
 enum {
     B_L_FULL = 0, B_L_EMPTY = 4, B_SET_FULL = 24, B_SET_EMPTY = 26, B_W_FULL = 28, B_W_EMPTY = 32,
     B_D_FULL = 36, B_D_EMPTY = 38, B_CB_FULL = 40, B_A_READY = 42, B_ZQ_READY = 50, B_MMA_DONE = 51, B_F_FULL = 52, B_F_EMPTY = 56,
-    B_E_READY = 60, B_SB_FULL = 61, B_SB_EMPTY = 64, B_L_FULL2 = 73, B_WL_FULL = 76, B_WL_EMPTY = 80, B_Z_FULL = 84, B_Z_EMPTY = 89, B_COUNT = 94
+    B_E_READY = 60, B_L_FULL2 = 73, B_WL_FULL = 76, B_WL_EMPTY = 80, B_Z_FULL = 84, B_Z_EMPTY = 89, B_SB_FULL = 94, B_SB_EMPTY = 100, B_COUNT = 106
 };
 enum { ZMODE_LDG = 0, ZMODE_BULK = 1, ZMODE_TMA = 2 };  // how phase L fetches the latent
 
@@ -209,7 +212,9 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;  // 32-channel chunks, accumulator drained every 4 chunks
     // search-score chunks: 64 codes per MMA into 3 x 64 TMEM columns; without z_q_is the out_proj ring is idle during the
     // searches, so the scores take 3 x 128 columns from TM_SET on and half as many (170-cycle) barrier hand-overs
-    constexpr int SCW = ZQIS ? 64 : 128, NSC = TCK / SCW;
+    // (third scan group: 64-code chunks in six buffers, so that each of the three groups has two of its own in flight)
+    constexpr int SCW = (ZQIS || VRVQ_THIRD_SCAN_GROUP) ? 64 : 128, NSC = TCK / SCW;
+    constexpr uint32_t NSB = (!ZQIS && VRVQ_THIRD_SCAN_GROUP) ? 6u : 3u;  // score buffers
     constexpr uint32_t TM_SC = ZQIS ? TM_SCORE : TM_SET;
     static_assert(NCH % 4 == 0, "D must be a multiple of 128");
     const EncodeParams &p = P.e;
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         mbar_init(&bars[B_MMA_DONE], 1);
         for (int i = 0; i < F_SLOTS; ++i) { mbar_init(&bars[B_F_FULL + i], 1); mbar_init(&bars[B_F_EMPTY + i], 1); }
         mbar_init(&bars[B_E_READY], 4);
-        for (int i = 0; i < 3; ++i) { mbar_init(&bars[B_SB_FULL + i], 1); mbar_init(&bars[B_SB_EMPTY + i], 4); }
+        for (int i = 0; i < 6; ++i) { mbar_init(&bars[B_SB_FULL + i], 1); mbar_init(&bars[B_SB_EMPTY + i], 4); }
         // latent staging slot: filled by the producer's expect_tx + the TMA bytes, released by the 8 loader warps
         for (int i = 0; i < Z_SLOTS; ++i) { mbar_init(&bars[B_Z_FULL + i], 1); mbar_init(&bars[B_Z_EMPTY + i], 8); }
         fence_mbar_init();
@@ -435,6 +440,7 @@ auto drain = [&](int g, uint32_t tq) {
         // 8-code groups within SEARCH_MARGIN of its running maximum and re-scores those with the reference's exact fp32 arithmetic
         // (first index wins ties).  Groups: warps 0-3, 4-7 and -- when there is no z_q_is to store -- the epilogue warps 8-11.
         constexpr int NSG = (ZQIS || !VRVQ_THIRD_SCAN_GROUP) ? 2 : 3, NSCAN = 128 * NSG;
+        constexpr bool PIPE = ZQIS;  // stage-ahead normalise (phase S below)
         unsigned char *list_base = smem + (ZQIS ? SM_SB : SM_WO);  // candidate lists [16][NSCAN] u32 (without z_q_is the W_out ring is idle)
         auto scan_stage = [&](int s, int h, int f, uint32_t tq, float &bd_out, int &bi_out) {
                     const uint32_t cbuse = (s & 1) ? (cbu1 + (uint32_t)(s >> 1)) : (cbu0 + (uint32_t)(s >> 1));
@@ -448,10 +454,10 @@ auto drain = [&](int g, uint32_t tq) {
                     for (int pc = 0; pc < NPIECE; ++pc) {
                         const int ck = NSG * (pc / (SCW / 64)) + h, sub = pc % (SCW / 64);
                         if (NSC % NSG != 0 && ck >= NSC) break;
-                        const uint32_t gc = (gstage + (uint32_t)s) * (uint32_t)NSC + (uint32_t)ck, sbuf = gc % 3u;
+                        const uint32_t gc = (gstage + (uint32_t)s) * (uint32_t)NSC + (uint32_t)ck, sbuf = gc % NSB;
                         const uint32_t tsc = tq + TM_SC + (uint32_t)SCW * sbuf + 64u * (uint32_t)sub;
                         if (sub == 0) {
-                            TC_WAIT(&bars[B_SB_FULL + sbuf], (gc / 3u) & 1u);
+                            TC_WAIT(&bars[B_SB_FULL + sbuf], (gc / NSB) & 1u);
                             tmem_fence_after_sync();
                         }
                         ph_mark(8);
@@ -892,7 +898,6 @@ auto drain = [&](int g, uint32_t tq) {
             // (the pipelined order pays where the stores are the critical path: config 2 with z_q_is 148.0 -> 145.8 us; without z_q_is
             // the frame threads are the critical path and it costs 2 %: 934 -> 955 us on the config-4 shape, so that variant keeps the
             // classic order: prep, barrier, scan, merge, all corrections)
-            constexpr bool PIPE = ZQIS;
             if (PIPE && w < 4) prep(0);
             for (int s = 0; s < nl; ++s) {  // s: stage within this pass, sg = s0 + s: stage of the model
                 const int sg = s0 + s;
@@ -1061,6 +1066,7 @@ auto drain = [&](int g, uint32_t tq) {
             if constexpr (!ZQIS && !FC && VRVQ_THIRD_SCAN_GROUP) {
                 // no per-stage outputs to store: these warps are the third scan group of every stage (lane r = frame row r)
                 for (int s = 0; s < nl; ++s) {
+                    if constexpr (!PIPE) named_bar_sync(1, NSCAN);  // 2e / e2 of the stage are visible
                     float bd;
                     int bidx;
                     scan_stage(s, 2, r, tq, bd, bidx);
@@ -1323,7 +1329,7 @@ auto drain = [&](int g, uint32_t tq) {
                     fence_proxy_async();
                     const uint64_t cb = DESC_CB | (uint64_t)((smem_base + ((s & 1) ? SM_CB1 : SM_CB0)) >> 4);
                     for (int c = 0; c < NSC; ++c) {
-                        const uint32_t gc = gs * (uint32_t)NSC + (uint32_t)c, sbuf = gc % 3u, use = gc / 3u;
+                        const uint32_t gc = gs * (uint32_t)NSC + (uint32_t)c, sbuf = gc % NSB, use = gc / NSB;
                         if (use >= 1) TC_WAIT(&bars[B_SB_EMPTY + sbuf], (use - 1) & 1u);
                         tmem_fence_after_sync();
                         umma_tf32(tmem + TM_SC + (uint32_t)SCW * sbuf, ae, cb + (uint64_t)(c * (SCW * 16 >> 4)), ID_S, false);
