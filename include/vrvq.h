@@ -215,6 +215,23 @@ int vrvq_snake_conv3_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c,
                          const float *bias, int B, int Cin, int Cout, int T, int apply_sigmoid, float *y, int64_t y_stride_b,
                          int64_t y_stride_c, void *stream);
 
+/* The same block on the tensor cores (csrc/subnet_tc.cu: tcgen05 3xTF32 implicit GEMM, activations through TMA) for the wide
+ * layers of the subnet: Cin a multiple of 64 and Cout a multiple of 128 (models/importance_subnet.py: 1024 -> 1024 and
+ * 1024 -> 512, 95 % of its FLOPs); no sigmoid variant (only the 1-channel last block has one).  Weights are packed once on the
+ * host by vrvq_pack_conv3_tc_weights into vrvq_conv3_tc_packed_floats(Cout, Cin) floats (0 = shape not served: use
+ * vrvq_snake_conv3_f32).  x needs unit stride along T and an item pitch that is a multiple of 4 elements (or B = 1). */
+size_t vrvq_conv3_tc_packed_floats(int Cout, int Cin);
+int vrvq_pack_conv3_tc_weights(int Cout, int Cin, const float *w, float *packed, size_t packed_floats);
+/* alpha == NULL: x is already Snake-activated (by vrvq_snake_f32 or by the previous block's post_alpha); post_alpha != NULL: the
+ * output is stored as snake(y[co], post_alpha[co]), i.e. already activated for the NEXT block -- so a chain of tensor-core blocks
+ * evaluates every Snake once instead of once per 128-channel output tile of its consumer. */
+int vrvq_snake_conv3_tc_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, const float *alpha, const float *packed_tc,
+                            const float *bias, const float *post_alpha, int B, int Cin, int Cout, int T, float *y, int64_t y_stride_b,
+                            int64_t y_stride_c, void *stream);
+/* y = snake(x, alpha[c]) elementwise (models/layers.py:25-31): the activation of the first tensor-core block's input. */
+int vrvq_snake_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, const float *alpha, int B, int C, int T, float *y,
+                   int64_t y_stride_b, int64_t y_stride_c, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,7 +106,7 @@ def test_vbr_forward_uses_the_subnet_kernels():
     z = torch.from_numpy(gi.make_latents(8, B, D, T, 1.0)).cuda()
     n0 = _lib.launch_count
     r = m(z, n_quantizers=None, feat_enc=torch.from_numpy(feat).cuda(), level=0.5)
-    assert _lib.launch_count - n0 == 7, "six subnet launches + one fused encode launch"
+    assert _lib.launch_count - n0 == 8, "Snake pre-pass of the tensor-core blocks + six subnet launches + one fused encode launch"
     imp = r["imp_map"]
     assert imp.shape == (B, 1, T)
     assert np.abs(imp.cpu().numpy() - H.load_golden("subnet_d1024")["imp_map"]).max() <= IMP_ATOL
@@ -133,3 +133,70 @@ def test_every_tile_width_gives_identical_results(monkeypatch):
     o = sp.conv3(sp.snake(x.cpu().numpy().astype(np.float64), pw.alpha.cpu().numpy(), np.float64), w.astype(np.float64),
                  pw.bias.cpu().numpy().astype(np.float64))
     assert np.abs(ref.cpu().numpy() - o).max() <= 1e-5 * np.abs(o).max()
+
+
+# ---- the wide blocks on the tensor cores (csrc/subnet_tc.cu through vrvq_snake_conv3_tc_f32) ---------------------------------
+def _tc_case(seed, B, cin, cout, T):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    w = (rng.normal(size=(cout, cin, 3)) / np.sqrt(3 * cin)).astype(np.float32)
+    alpha = rng.uniform(0.5, 1.5, cin).astype(np.float32)
+    bias = rng.normal(size=cout).astype(np.float32)
+    x = rng.normal(0, 1.5, (B, cin, T)).astype(np.float32)
+    return w, alpha, bias, x
+
+
+@pytest.mark.parametrize("B,cin,cout,T", [(2, 64, 128, 130), (1, 96, 256, 257), (3, 64, 128, 100), (2, 128, 384, 87), (1, 64, 128, 1),
+                                           (2, 64, 128, 3), (1, 160, 128, 129), (5, 64, 256, 127)])
+def test_tensor_core_block_shapes(B, cin, cout, T, monkeypatch):
+    """One tensor-core block (frame tiles with ragged ends, odd row pitches -> 1, 2 or 4 channel classes of tensor maps, several
+    output-channel tiles) against the binary64 value and against the CUDA-core kernel of the same block."""
+    from vrvq_b200 import ops
+
+    w, alpha, bias, x = _tc_case(500 + B + cin + cout + T, B, cin, cout, T)
+    pw = ops.PackedConv3(torch.from_numpy(alpha), torch.from_numpy(w), torch.from_numpy(bias), "cuda")
+    assert pw.packed_tc is not None
+    xd = torch.from_numpy(x).cuda()
+    y = ops.snake_conv3(pw, xd).cpu().numpy()
+    monkeypatch.setenv("VRVQ_SUBNET_IMPL", "cuda")
+    y_cuda = ops.snake_conv3(pw, xd).cpu().numpy()
+    monkeypatch.delenv("VRVQ_SUBNET_IMPL")
+    o = sp.conv3(sp.snake(x.astype(np.float64), alpha, np.float64), w.astype(np.float64), bias.astype(np.float64))
+    scale = max(1.0, np.abs(o).max())
+    assert y.shape == (B, cout, T)
+    assert np.abs(y - o).max() <= 4e-6 * scale, "3xTF32 with drained accumulators is fp32-grade"
+    assert np.abs(y - y_cuda).max() <= 6e-6 * scale
+    assert not np.array_equal(y, y_cuda) or T <= 3, "the two kernels sum in different orders: identical outputs mean the tensor-core path did not run"
+
+
+def test_tensor_core_block_pre_and_post_activation():
+    """alpha == NULL (input already activated by vrvq_snake_f32) and post_alpha (output stored through the next block's Snake)
+    compose to the same chain as two plain blocks."""
+    from vrvq_b200 import ops
+
+    w0, a0, b0, x = _tc_case(901, 2, 64, 128, 301)
+    w1, a1, b1, _ = _tc_case(902, 1, 128, 128, 1)
+    p0 = ops.PackedConv3(torch.from_numpy(a0), torch.from_numpy(w0), torch.from_numpy(b0), "cuda")
+    p1 = ops.PackedConv3(torch.from_numpy(a1), torch.from_numpy(w1), torch.from_numpy(b1), "cuda")
+    xd = torch.from_numpy(x).cuda()
+    plain = ops.snake_conv3(p1, ops.snake_conv3(p0, xd))
+    xs = ops.snake(xd, p0.alpha)
+    o64 = sp.snake(x.astype(np.float64), a0, np.float64)
+    assert np.abs(xs.cpu().numpy() - o64).max() <= 2e-6 * np.abs(o64).max()
+    h = ops.snake_conv3(p0, xs, pre_activated=True, post_alpha=p1.alpha)
+    fused = ops.snake_conv3(p1, h, pre_activated=True)
+    assert torch.equal(fused, plain), "same operations in the same order, only moved between launches"
+    o = sp.conv3(sp.snake(sp.conv3(o64, w0.astype(np.float64), b0.astype(np.float64)), a1, np.float64), w1.astype(np.float64), b1.astype(np.float64))
+    assert np.abs(fused.cpu().numpy() - o).max() <= 5e-6 * np.abs(o).max()
+
+
+def test_tensor_core_block_on_views():
+    """Channel-range and frame-range views (unit stride along T, any row pitch): the tensor maps are built per call from the strides."""
+    from vrvq_b200 import ops
+
+    w, alpha, bias, x = _tc_case(903, 2, 64, 128, 400)
+    pw = ops.PackedConv3(torch.from_numpy(alpha), torch.from_numpy(w), torch.from_numpy(bias), "cuda")
+    big = torch.from_numpy(np.random.Generator(np.random.PCG64(9)).normal(size=(2, 96, 517)).astype(np.float32)).cuda()
+    big[:, 16:80, 57:457] = torch.from_numpy(x).cuda()
+    view = big[:, 16:80, 57:457]
+    assert not view.is_contiguous()
+    assert torch.equal(ops.snake_conv3(pw, view), ops.snake_conv3(pw, torch.from_numpy(x).cuda()))

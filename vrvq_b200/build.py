@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvrvq.so")
-SOURCES = ["abi.cu", "rvq_encode.cu", "rvq_encode_tc.cu", "rvq_aux.cu", "wire.cu", "subnet.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "encode_params.cuh"), os.path.join(os.path.dirname(HERE), "include", "vrvq.h")]
+SOURCES = ["abi.cu", "rvq_encode.cu", "rvq_encode_tc.cu", "rvq_aux.cu", "wire.cu", "subnet.cu", "subnet_tc.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "encode_params.cuh"), os.path.join(CSRC, "tmaps.cuh"), os.path.join(os.path.dirname(HERE), "include", "vrvq.h")]
 OBJ_DIR = os.path.join(CSRC, "_obj")  # per-source objects (git-ignored): only changed sources are recompiled
 
 NVCC_FLAGS = [

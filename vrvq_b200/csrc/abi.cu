@@ -61,6 +61,13 @@ int launch_unpack_codes(const unsigned short *in, const unsigned char *counts, i
                         long long c_sq, float *mask, long long m_sb, long long m_sq, int *error_flag, cudaStream_t st);
 int launch_snake_conv3(const float *x, long long x_sb, long long x_sc, const float *alpha, const float *wp, int cout_pad, const float *bias,
                        int B, int Cin, int Cout, int T, int sigmoid, float *y, long long y_sb, long long y_sc, cudaStream_t st);
+int snake_conv3_tc_usable(int Cin, int Cout);
+size_t conv3_tc_packed_floats(int Cout, int Cin);
+int pack_conv3_tc_weights(int Cout, int Cin, const float *w, float *out);
+int launch_snake_conv3_tc(const float *x, long long x_sb, long long x_sc, const float *alpha, const float *wtc, const float *bias,
+                          const float *post_alpha, int B, int Cin, int Cout, int T, float *y, long long y_sb, long long y_sc, cudaStream_t st);
+int launch_snake(const float *x, long long x_sb, long long x_sc, const float *alpha, int B, int C, int T, float *y, long long y_sb, long long y_sc,
+                 cudaStream_t st);
 int launch_search_latents(const float *blob, int D, int K, const float *lat, long long l_sb, long long l_sc, int B, int T, int n_run,
                           long long *codes, long long c_sb, long long c_sq, cudaStream_t st);
 
@@ -426,6 +433,42 @@ int vrvq_snake_conv3_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c,
     const int cp = (int)(vrvq_conv3_packed_floats(Cout, Cin) / ((size_t)Cin * 3));
     return launch_snake_conv3(x, x_stride_b, x_stride_c, alpha, packed, cp, bias, B, Cin, Cout, T, apply_sigmoid, y, y_stride_b, y_stride_c,
                               static_cast<cudaStream_t>(stream));
+}
+
+size_t vrvq_conv3_tc_packed_floats(int Cout, int Cin) { return conv3_tc_packed_floats(Cout, Cin); }
+
+int vrvq_pack_conv3_tc_weights(int Cout, int Cin, const float *w, float *packed, size_t packed_floats) {
+    const size_t need = conv3_tc_packed_floats(Cout, Cin);
+    if (need == 0 || !w || !packed || packed_floats < need) {
+        set_error("vrvq_pack_conv3_tc_weights: bad arguments (Cout=%d Cin=%d, %zu floats given, %zu needed; 0 = shape not served)", Cout, Cin,
+                  packed_floats, need);
+        return need == 0 ? VRVQ_EUNSUPPORTED : VRVQ_EINVAL;
+    }
+    return pack_conv3_tc_weights(Cout, Cin, w, packed);
+}
+
+int vrvq_snake_conv3_tc_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, const float *alpha, const float *packed_tc, const float *bias,
+                            const float *post_alpha, int B, int Cin, int Cout, int T, float *y, int64_t y_stride_b, int64_t y_stride_c,
+                            void *stream) {
+    if (!x || !packed_tc || !bias || !y || B < 0 || T < 0 || Cin <= 0 || Cout <= 0) {
+        set_error("vrvq_snake_conv3_tc_f32: bad arguments");
+        return VRVQ_EINVAL;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_snake_conv3_tc(x, x_stride_b, x_stride_c, alpha, packed_tc, bias, post_alpha, B, Cin, Cout, T, y, y_stride_b, y_stride_c,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int vrvq_snake_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, const float *alpha, int B, int C, int T, float *y, int64_t y_stride_b,
+                   int64_t y_stride_c, void *stream) {
+    if (!x || !alpha || !y || B < 0 || C < 0 || T < 0) {
+        set_error("vrvq_snake_f32: bad arguments");
+        return VRVQ_EINVAL;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_snake(x, x_stride_b, x_stride_c, alpha, B, C, T, y, y_stride_b, y_stride_c, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -32,8 +32,6 @@
 //
 // Exactness: only z_e differs from the reference's conv1d by rounding (as any two conv implementations do), so codes can
 // differ only at fp32 near-ties (audited in tests); z_q / z_q_is carry the tensor core's accumulation rounding (<= 2e-6).
-#include <cuda.h>  // CUtensorMap (types only: the driver entry point is fetched through the runtime, no -lcuda)
-
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,6 +39,7 @@
 
 #include "common.cuh"
 #include "encode_params.cuh"
+#include "tmaps.cuh"
 
 // Experiment kept compiled out: the epilogue warps as a third scan group when there is no z_q_is to store --
 // slower in both forms tried (three groups on three 128-code buffers: +4-8 %; 64-code chunks in six buffers: +20 %), because the
@@ -140,19 +139,6 @@ __device__ __noinline__ unsigned long long tc_wait_check(unsigned long long t0, 
             if ((++spins__ & 0x3fffu) == 0) t0__ = tc_wait_check(t0__, b__, bars, p__); \
         }                                                                        \
     } while (0)
-
-// one TMA box of a rank-3 tensor map into shared memory, completion on an mbarrier (SASS: UTMALDG)
-__device__ __forceinline__ void tma_load_3d(void *dst_smem, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// Tensor maps of the latent, one per channel class (channel % nc, nc = 1, 2 or 4): see pick_zmode
-struct ZMaps {
-    CUtensorMap m[4];
-};
 
 struct TcParams {
     EncodeParams e;
@@ -1502,33 +1488,9 @@ int encode_tc_usable(const vrvq_encode_args *a) {
     return 1;
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (libvrvq.so does not link libcuda)
-typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static encode_tiled_fn get_encode_tiled() {
-    static encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<encode_tiled_fn>(ptr);
-        else
-            cudaGetLastError();
-        tried = true;
-    }
-    return fn;
-}
-
-// How phase L fetches the latent.  Default: TMA tensor maps for EVERY layout.  A tensor map needs a 16-byte aligned base and
-// 16-byte multiples for its pitches, which a [B, D, T] tensor with T = 862 does not offer (rows are 8-byte aligned).  But the
-// channels of one class k = channel % nc (nc = 1, 2 or 4) do: their rows are nc * pitch apart (a 16-byte multiple as soon as
-// nc * pitch % 4 == 0), and the 16-byte aligned address at or below the first row of the class is a legal base -- the row then
-// starts s_k = 0..3 elements into the map's row; boxes start at 16-byte multiples of x and the loader threads add s_k to their column.  So the latent is seen
-// through nc rank-3 maps (x = frame + s_k, row = channel / nc, item), class k staged class-major in the slot; frames outside
-// [0, T) come back as zeros (or as the neighbouring row's elements for the <= 3 positions before frame 0: those rows are never
-// valid frames).  VRVQ_LATENT_LOAD=ldg|bulk|tma overrides (ldg = per-thread loads, the round-1 path; bulk = one cp.async.bulk per
-// channel row; both kept for A/B runs).
+// How phase L fetches the latent.  Default: TMA tensor maps for EVERY layout (channel-class maps, tmaps.cuh).
+// VRVQ_LATENT_LOAD=ldg|bulk|tma overrides (ldg = per-thread loads, the round-1 path; bulk = one cp.async.bulk per channel row; both
+// kept for A/B runs).
 static int pick_zmode(const vrvq_encode_args *a, ZMaps *maps, TcParams &P) {
     memset(maps, 0, sizeof(*maps));
     P.znc_log2 = 0;
@@ -1539,41 +1501,8 @@ static int pick_zmode(const vrvq_encode_args *a, ZMaps *maps, TcParams &P) {
         if (env[0] == 'b') want = ZMODE_BULK;
     }
     if (a->z_stride_d <= 0 || a->z_stride_b < 0) return ZMODE_LDG;
-    const uintptr_t zaddr = reinterpret_cast<uintptr_t>(a->z);
-    const int al = (int)((zaddr >> 2) & 3);  // base misalignment in floats
-    const bool item_ok = a->z_stride_b % 4 == 0 || a->B == 1;
-    if (want == ZMODE_TMA && item_ok) {
-        if (encode_tiled_fn enc = get_encode_tiled()) {
-            int lg = (a->z_stride_d % 4 == 0 && al == 0) ? 0 : (a->z_stride_d % 2 == 0) ? 1 : 2;
-            if (const char *env = getenv("VRVQ_DEBUG_ZNC_LOG2")) lg = atoi(env) > lg && atoi(env) <= 2 ? atoi(env) : lg;  // more classes than needed is always legal
-            const int nc = 1 << lg;
-            bool ok = true;
-            for (int k = 0; k < nc && ok; ++k) {
-                const int sk = (int)((al + (long long)k * a->z_stride_d) & 3);
-                const float *base = a->z + (long long)k * a->z_stride_d - sk;
-                // x extent rounded up to a 16-byte multiple: an extent of e.g. 86 floats makes the TMA unit fault at run time (found on
-                // B200, not rejected by cuTensorMapEncodeTiled).  The <= 3 extra elements are the next row's first ones (or lie in the
-                // 16-byte granule of the tensor's last element): frames >= T, which the kernel never uses.
-                const cuuint64_t dims[3] = {((cuuint64_t)a->T + (cuuint64_t)sk + 3ull) & ~3ull, (cuuint64_t)(a->input_dim / nc), (cuuint64_t)a->B};
-                const cuuint64_t strides[2] = {(cuuint64_t)nc * (cuuint64_t)a->z_stride_d * 4ull,
-                                               a->B == 1 ? (cuuint64_t)nc * (cuuint64_t)a->z_stride_d * 4ull * (cuuint64_t)(a->input_dim / nc) : (cuuint64_t)a->z_stride_b * 4ull};
-                const cuuint32_t box[3] = {(cuuint32_t)Z_PITCH, (cuuint32_t)(Z_CH / nc), 1u};
-                const cuuint32_t estr[3] = {1u, 1u, 1u};
-                ok = enc(&maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-                P.zshift[k] = sk;
-                if (getenv("VRVQ_DEBUG_ZMAP"))
-                    fprintf(stderr, "[vrvq zmap] class %d/%d: ok=%d shift=%d base%%16=%d dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)\n", k, nc, (int)ok, sk,
-                            (int)(reinterpret_cast<uintptr_t>(base) % 16), (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
-                            (unsigned long long)strides[0], (unsigned long long)strides[1], box[0], box[1], box[2]);
-            }
-            if (ok) {
-                P.znc_log2 = lg;
-                return ZMODE_TMA;
-            }
-        }
-    }
-    for (int k = 0; k < 4; ++k) P.zshift[k] = 0;
+    if (want == ZMODE_TMA && build_class_maps(a->z, a->B, a->input_dim, a->T, a->z_stride_d, a->z_stride_b, Z_PITCH, Z_CH, maps, &P.znc_log2, P.zshift))
+        return ZMODE_TMA;
     return ZMODE_BULK;
 }
 

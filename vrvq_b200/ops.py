@@ -353,14 +353,31 @@ class PackedConv3:
         check(L.vrvq_pack_conv3_weights(self.cout, self.cin, weight.data_ptr(), packed.data_ptr(), n), "vrvq_pack_conv3_weights")
         self.packed = packed.to(torch.device(device))
         self.device = self.packed.device  # resolved ("cuda" -> "cuda:0")
+        # the wide blocks (Cin % 64 == 0, Cout % 128 == 0) also get the tensor-core operand tiles (csrc/subnet_tc.cu)
+        self.packed_tc = None
+        n_tc = L.vrvq_conv3_tc_packed_floats(self.cout, self.cin)
+        if n_tc:
+            ptc = torch.empty(n_tc, dtype=torch.float32)
+            check(L.vrvq_pack_conv3_tc_weights(self.cout, self.cin, weight.data_ptr(), ptc.data_ptr(), n_tc), "vrvq_pack_conv3_tc_weights")
+            self.packed_tc = ptc.to(self.device)
         self.alpha = alpha.detach().to("cpu", torch.float32).reshape(-1).contiguous().to(self.device)
         self.bias = bias.detach().to("cpu", torch.float32).reshape(-1).contiguous().to(self.device)
         if self.alpha.numel() != self.cin or self.bias.numel() != self.cout:
             raise VrvqError("alpha must have Cin entries and bias Cout entries")
 
 
-def snake_conv3(w: PackedConv3, x: torch.Tensor, sigmoid: bool = False) -> torch.Tensor:
-    """vrvq_snake_conv3_f32 -- one block of the importance subnet: x [B,Cin,T] -> [B,Cout,T]."""
+def _tc_block_ok(w: PackedConv3, x: torch.Tensor) -> bool:
+    import os
+
+    return w.packed_tc is not None and os.environ.get("VRVQ_SUBNET_IMPL", "") != "cuda" and (x.stride(0) % 4 == 0 or x.shape[0] == 1)
+
+
+def snake_conv3(w: PackedConv3, x: torch.Tensor, sigmoid: bool = False, pre_activated: bool = False,
+                post_alpha: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One block of the importance subnet, x [B,Cin,T] -> [B,Cout,T]: vrvq_snake_conv3_tc_f32 (tcgen05 3xTF32 implicit GEMM) for
+    the wide blocks, vrvq_snake_conv3_f32 (CUDA cores) otherwise; VRVQ_SUBNET_IMPL=cuda forces the latter.
+    `pre_activated` / `post_alpha` (tensor-core block only): the input already went through Snake / store the output through the
+    next block's Snake (see importance_subnet)."""
     require_cuda_f32(x, "x")
     if x.dim() != 3 or x.shape[1] != w.cin:
         raise VrvqError(f"x must be [B, {w.cin}, T], got {tuple(x.shape)}")
@@ -371,6 +388,15 @@ def snake_conv3(w: PackedConv3, x: torch.Tensor, sigmoid: bool = False) -> torch
     if B * T == 0:
         return y
     _check_view(x, "x")
+    if not sigmoid and _tc_block_ok(w, x):
+        with torch.cuda.device(x.device):
+            check(_lib.lib().vrvq_snake_conv3_tc_f32(x.data_ptr(), x.stride(0), x.stride(1), None if pre_activated else w.alpha.data_ptr(),
+                                                     w.packed_tc.data_ptr(), w.bias.data_ptr(), ptr(post_alpha), B, w.cin, w.cout, T, y.data_ptr(),
+                                                     y.stride(0), y.stride(1), current_stream_ptr(x.device)), "vrvq_snake_conv3_tc_f32")
+        _lib.count_launch()
+        return y
+    if pre_activated or post_alpha is not None:
+        raise VrvqError("pre_activated / post_alpha are options of the tensor-core block")
     with torch.cuda.device(x.device):
         check(_lib.lib().vrvq_snake_conv3_f32(x.data_ptr(), x.stride(0), x.stride(1), w.alpha.data_ptr(), w.packed.data_ptr(),
                                               w.bias.data_ptr(), B, w.cin, w.cout, T, int(bool(sigmoid)), y.data_ptr(), y.stride(0),
@@ -379,8 +405,42 @@ def snake_conv3(w: PackedConv3, x: torch.Tensor, sigmoid: bool = False) -> torch
     return y
 
 
+def snake(x: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
+    """vrvq_snake_f32: x + sin(alpha x)^2 / (alpha + 1e-9) per channel (models/layers.py:25-31)."""
+    require_cuda_f32(x, "x")
+    _check_view(x, "x")
+    B, Cc, T = x.shape
+    y = torch.empty_like(x, memory_format=torch.contiguous_format)
+    if y.numel():
+        with torch.cuda.device(x.device):
+            check(_lib.lib().vrvq_snake_f32(x.data_ptr(), x.stride(0), x.stride(1), alpha.data_ptr(), B, Cc, T, y.data_ptr(), y.stride(0), y.stride(1),
+                                            current_stream_ptr(x.device)), "vrvq_snake_f32")
+        _lib.count_launch()
+    return y
+
+
 def importance_subnet(blocks, x: torch.Tensor) -> torch.Tensor:
-    """models/importance_subnet.py:38-44 on packed blocks: chain of snake_conv3 launches, sigmoid fused into the last."""
+    """models/importance_subnet.py:38-44 on packed blocks: chain of snake_conv3 launches, sigmoid fused into the last.
+    A run of tensor-core blocks evaluates each Snake once: the first one's input goes through vrvq_snake_f32, every later one gets its
+    activation from its predecessor's epilogue (`post_alpha`) -- inside a block the activation would be recomputed for each of the
+    Cout / 128 output tiles (8 times for 1024 -> 1024: 250 of 970 us at config-2 size)."""
+    pre = False
     for i, w in enumerate(blocks):
-        x = snake_conv3(w, x, sigmoid=(i == len(blocks) - 1))
+        last = i == len(blocks) - 1
+        tc = (not last) and _tc_block_ok(w, x)
+        if tc and not pre:
+            x = snake(x, w.alpha)
+            pre = True
+        nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+        post = None
+        if tc and nxt is not None and i + 1 < len(blocks) - 1 and nxt.packed_tc is not None:
+            post = nxt.alpha  # (the next block is a tensor-core block too: y has its batch pitch Cout * T, a multiple of 4 when T is -- checked there)
+        if tc:
+            y = snake_conv3(w, x, pre_activated=True, post_alpha=post)
+            if post is not None and not _tc_block_ok(nxt, y):  # cannot happen for contiguous outputs of these widths; keep the chain correct anyway
+                raise VrvqError("internal: post-activated output handed to a block that cannot take it")
+            x, pre = y, post is not None
+        else:
+            x = snake_conv3(w, x, sigmoid=last)
+            pre = False
     return x
