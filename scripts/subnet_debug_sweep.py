@@ -20,7 +20,10 @@ def timeit(fn, iters=10, warm=2):
 
 B, T = 16, 862
 rng = np.random.Generator(np.random.PCG64(1))
-x = torch.from_numpy(rng.normal(size=(B, 1024, T)).astype(np.float32)).cuda()
+x0 = torch.from_numpy(rng.normal(size=(B, 1024, T)).astype(np.float32)).cuda()
+x = ops._padded_rows(B, 1024, T, "cuda")  # as inside ops.importance_subnet: rows padded to 16 bytes, outputs through the TMA store
+x.copy_(x0)
+post = [torch.full((1024,), 0.9, device="cuda"), None]  # block 0 stores through block 1's Snake
 blocks = []
 for cout in (1024, 512):
     w = torch.from_numpy((rng.normal(size=(cout, 1024, 3)) / 55).astype(np.float32))
@@ -28,5 +31,10 @@ for cout in (1024, 512):
 modes = [int(a) for a in sys.argv[1:]] or [0]
 for mode in modes:
     os.environ["VRVQ_SUBNET_DEBUG"] = str(mode)
-    us = [timeit(lambda: ops.snake_conv3(b, x, pre_activated=True)) for b in blocks]
+    us = [timeit(lambda: ops.snake_conv3(b, x, pre_activated=True, post_alpha=pa, padded_out=True)) for b, pa in zip(blocks, post)]
     print(f"debug {mode:3d}: 1024->1024 {us[0]:8.1f} us   1024->512 {us[1]:8.1f} us", flush=True)
+    if os.environ.get("SWEEP_TRACE"):  # per-role cycle counters of block 0 (stderr), first block shape only
+        os.environ["VRVQ_SUBNET_TRACE"] = "1"
+        ops.snake_conv3(blocks[0], x, pre_activated=True, post_alpha=post[0], padded_out=True)
+        torch.cuda.synchronize()
+        del os.environ["VRVQ_SUBNET_TRACE"]

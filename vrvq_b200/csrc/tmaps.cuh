@@ -32,6 +32,17 @@ __device__ __forceinline__ void tma_load_3d(void *dst_smem, const CUtensorMap *m
                  : "memory");
 }
 
+// one TMA box from shared memory into a rank-3 tensor (SASS: UTMASTG), tracked by the thread's bulk async-group; elements outside the
+// tensor are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src_smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+                 "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // sources may be overwritten
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }            // writes are complete
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libvrvq.so does not link libcuda)
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -88,6 +99,21 @@ inline bool build_class_maps(const float *x, int B, int C, int T, long long stri
     }
     *lg_out = lg;
     return true;
+}
+
+// Tensor map for STORING boxes of box_w frames x box_c channels into y [B][C][T] (element strides): needs what the hardware needs --
+// a 16-byte aligned base and 16-byte multiples for both pitches; returns false otherwise (the caller stores per lane).
+inline bool build_store_map(float *y, int B, int C, int T, long long stride_c, long long stride_b, int box_w, int box_c, CUtensorMap *map) {
+    memset(map, 0, sizeof(*map));
+    if (stride_c <= 0 || stride_b < 0 || T < 1 || (reinterpret_cast<uintptr_t>(y) & 15) != 0 || stride_c % 4 != 0 || !(stride_b % 4 == 0 || B == 1)) return false;
+    encode_tiled_fn enc = get_encode_tiled();
+    if (enc == nullptr) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)stride_c * 4ull, B == 1 ? (cuuint64_t)stride_c * 4ull * (cuuint64_t)C : (cuuint64_t)stride_b * 4ull};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_c, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace vrvq

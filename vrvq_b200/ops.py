@@ -372,19 +372,25 @@ def _tc_block_ok(w: PackedConv3, x: torch.Tensor) -> bool:
     return w.packed_tc is not None and os.environ.get("VRVQ_SUBNET_IMPL", "") != "cuda" and (x.stride(0) % 4 == 0 or x.shape[0] == 1)
 
 
+def _padded_rows(B: int, Cc: int, T: int, device) -> torch.Tensor:
+    """[B, C, T] view of a buffer whose rows are padded to a multiple of 4 frames (16 bytes): the tensor-core block stores such an
+    output with one TMA store per tile and reads such an input through a single tensor map (csrc/tmaps.cuh)."""
+    return torch.empty((B, Cc, (T + 3) // 4 * 4), dtype=torch.float32, device=device)[:, :, :T]
+
+
 def snake_conv3(w: PackedConv3, x: torch.Tensor, sigmoid: bool = False, pre_activated: bool = False,
-                post_alpha: Optional[torch.Tensor] = None) -> torch.Tensor:
+                post_alpha: Optional[torch.Tensor] = None, padded_out: bool = False) -> torch.Tensor:
     """One block of the importance subnet, x [B,Cin,T] -> [B,Cout,T]: vrvq_snake_conv3_tc_f32 (tcgen05 3xTF32 implicit GEMM) for
     the wide blocks, vrvq_snake_conv3_f32 (CUDA cores) otherwise; VRVQ_SUBNET_IMPL=cuda forces the latter.
     `pre_activated` / `post_alpha` (tensor-core block only): the input already went through Snake / store the output through the
-    next block's Snake (see importance_subnet)."""
+    next block's Snake (see importance_subnet).  `padded_out`: the result is a view of a row-padded buffer (_padded_rows)."""
     require_cuda_f32(x, "x")
     if x.dim() != 3 or x.shape[1] != w.cin:
         raise VrvqError(f"x must be [B, {w.cin}, T], got {tuple(x.shape)}")
     if x.device != w.device:
         raise VrvqError(f"x is on {x.device} but the packed weights are on {w.device}")
     B, _, T = x.shape
-    y = torch.empty((B, w.cout, T), dtype=torch.float32, device=x.device)
+    y = _padded_rows(B, w.cout, T, x.device) if padded_out else torch.empty((B, w.cout, T), dtype=torch.float32, device=x.device)
     if B * T == 0:
         return y
     _check_view(x, "x")
@@ -405,12 +411,12 @@ def snake_conv3(w: PackedConv3, x: torch.Tensor, sigmoid: bool = False, pre_acti
     return y
 
 
-def snake(x: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
+def snake(x: torch.Tensor, alpha: torch.Tensor, padded_out: bool = False) -> torch.Tensor:
     """vrvq_snake_f32: x + sin(alpha x)^2 / (alpha + 1e-9) per channel (models/layers.py:25-31)."""
     require_cuda_f32(x, "x")
     _check_view(x, "x")
     B, Cc, T = x.shape
-    y = torch.empty_like(x, memory_format=torch.contiguous_format)
+    y = _padded_rows(B, Cc, T, x.device) if padded_out else torch.empty_like(x, memory_format=torch.contiguous_format)
     if y.numel():
         with torch.cuda.device(x.device):
             check(_lib.lib().vrvq_snake_f32(x.data_ptr(), x.stride(0), x.stride(1), alpha.data_ptr(), B, Cc, T, y.data_ptr(), y.stride(0), y.stride(1),
@@ -429,14 +435,14 @@ def importance_subnet(blocks, x: torch.Tensor) -> torch.Tensor:
         last = i == len(blocks) - 1
         tc = (not last) and _tc_block_ok(w, x)
         if tc and not pre:
-            x = snake(x, w.alpha)
+            x = snake(x, w.alpha, padded_out=True)
             pre = True
         nxt = blocks[i + 1] if i + 1 < len(blocks) else None
         post = None
         if tc and nxt is not None and i + 1 < len(blocks) - 1 and nxt.packed_tc is not None:
             post = nxt.alpha  # (the next block is a tensor-core block too: y has its batch pitch Cout * T, a multiple of 4 when T is -- checked there)
         if tc:
-            y = snake_conv3(w, x, pre_activated=True, post_alpha=post)
+            y = snake_conv3(w, x, pre_activated=True, post_alpha=post, padded_out=True)  # (intermediate activations: rows padded to 16 bytes)
             if post is not None and not _tc_block_ok(nxt, y):  # cannot happen for contiguous outputs of these widths; keep the chain correct anyway
                 raise VrvqError("internal: post-activated output handed to a block that cannot take it")
             x, pre = y, post is not None
