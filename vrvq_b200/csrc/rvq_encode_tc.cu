@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     __syncthreads();
     tmem_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem);  // the same value, provably warp-uniform: MMAs issued by a whole warp (elect_one) take
+                                                                   // their operands straight from uniform registers (no vote / elect / R2UR loop per MMA)
     const uint32_t smem_base = smem_u32(smem);
     if (P.stagger > 0) {
         const long long until = clock64() + (long long)P.stagger * (long long)(blockIdx.x & 7);
@@ -381,7 +383,7 @@ auto drain = [&](int g, uint32_t tq) {
             if (lane == 0) mbar_arrive(&bars[B_SET_EMPTY + set]);
             if (PROFILE && tid == 256 && it == 0) trace(7, 4 * g + 1);
         };
-        // Phase-L MMA issue, split over two issuing threads (lane 0 of warps 12 and 15): issuer X takes the chunks c % 2 == X and
+        // Phase-L MMA issue, split over two issuing warps (12 and 15; the loop runs warp-wide on uniform values, one elected lane issues): issuer X takes the chunks c % 2 == X and
         // accumulates all three 3xTF32 products of its chunks -- hi*W_hi + hi*W_lo + lo*W_hi, three N = 64 MMAs per k-step -- into its
         // own 64 columns of the current accumulator set (columns [64 X, 64 X + 64) of TM_SET + 128 set; the drain adds the two
         // halves).  A tcgen05.mma blocks its issuing thread while the tensor pipe is busy and a completed mbarrier wait costs
@@ -402,23 +404,25 @@ auto drain = [&](int g, uint32_t tq) {
                     TC_WAIT(fb, par);                                           // A operand (loaders)
                     TC_WAIT(&bars[B_WL_FULL + wsl], (n / WL_SLOTS) & 1u);      // B operand (W_in chunk)
                 }
-                if (PROFILE && it == 0 && X == 0) trace(4, c);
+                if (PROFILE && it == 0 && X == 0 && lane == 0) trace(4, c);
                 const uint32_t gg = gbase + (uint32_t)(c >> 2), set = gg & 1u;
                 if ((c & 3) == X && gg >= 2) TC_WAIT(&bars[B_SET_EMPTY + set], ((gg >> 1) - 1) & 1u);
                 tmem_fence_after_sync();
-                const uint32_t a_hi = tmem + TM_AL + 64u * sl, a_lo = a_hi + 32;  // A in tensor memory: 8 columns per k-step
+                const uint32_t a_hi = tmem_u + TM_AL + 64u * sl, a_lo = a_hi + 32;  // A in tensor memory: 8 columns per k-step
                 const uint64_t bh = desc128(smem_base + SM_LR + wsl * L_SLOT), bl = bh + (1024 >> 4);  // B rows 0-63 heads, 64-127 remainders
-                const uint32_t d = tmem + TM_SET + 128u * set + 64u * (uint32_t)X;
+                const uint32_t d = tmem_u + TM_SET + 128u * set + 64u * (uint32_t)X;
+                if (elect_one()) {  // (the whole warp runs this loop on warp-uniform values; one lane issues)
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    umma_tf32_ts(d, a_lo + 8 * ks, bh + ks * (4096 >> 4), ID_64, (c & 3) != X || ks != 0);  // smallest terms first
-                    umma_tf32_ts(d, a_hi + 8 * ks, bl + ks * (4096 >> 4), ID_64, true);
-                    umma_tf32_ts(d, a_hi + 8 * ks, bh + ks * (4096 >> 4), ID_64, true);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        umma_tf32_ts(d, a_lo + 8 * ks, bh + ks * (4096 >> 4), ID_64, (c & 3) != X || ks != 0);  // smallest terms first
+                        umma_tf32_ts(d, a_hi + 8 * ks, bl + ks * (4096 >> 4), ID_64, true);
+                        umma_tf32_ts(d, a_hi + 8 * ks, bh + ks * (4096 >> 4), ID_64, true);
+                    }
+                    umma_commit(&bars[B_L_EMPTY + sl]);
+                    umma_commit(&bars[B_WL_EMPTY + wsl]);
+                    if ((c & 3) == 2 + X) umma_commit(&bars[B_SET_FULL + set]);
                 }
-                umma_commit(&bars[B_L_EMPTY + sl]);
-                umma_commit(&bars[B_WL_EMPTY + wsl]);
-                if ((c & 3) == 2 + X) umma_commit(&bars[B_SET_FULL + set]);
-                if (PROFILE && it == 0 && X == 0) trace(5, c);
+                if (PROFILE && it == 0 && X == 0 && lane == 0) trace(5, c);
             }
         };
         // ---- search of one stage by one scan group (quantize.py:96-101): the tensor core scores all 1024 codes per frame (TF32,
@@ -1120,14 +1124,14 @@ auto drain = [&](int g, uint32_t tq) {
             // MMA issuer: lane 0 of warp 12.
             // =====================================================================================================
             constexpr uint32_t ID_128 = umma_idesc_tf32(128, 128), ID_64 = umma_idesc_tf32(128, 64), ID_32 = umma_idesc_tf32(128, 32);
-            if (!FC && lane == 0) issue_phase_l(0);
+            if (!FC) issue_phase_l(0);
             ph_mark(0);
             __syncwarp();
             tmem_fence_before_sync();
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
             ph_mark(1);
-            if (lane == 0) {
+            {  // the whole warp runs this on warp-uniform values; one elected lane issues the MMAs and commits (see tmem_u)
                 const uint64_t ones = desc128(smem_base + SM_ONES);
                 uint32_t step = wn;
                 auto take_w = [&]() -> uint64_t {
@@ -1136,7 +1140,7 @@ auto drain = [&](int g, uint32_t tq) {
                     return desc128(smem_base + SM_WO + slot * W_SLOT);
                 };
                 auto release_w = [&]() {
-                    umma_commit(&bars[B_W_EMPTY + step % W_SLOTS]);
+                    if (elect_one()) umma_commit(&bars[B_W_EMPTY + step % W_SLOTS]);
                     ++step;
                 };
                 auto wait_dbuf = [&]() -> uint32_t {
@@ -1158,37 +1162,39 @@ auto drain = [&](int g, uint32_t tq) {
                             const uint64_t wb = take_w();  // hi tile; lo at +4096 B, bias tile at +8192 B
                             const uint32_t buf = wait_dbuf();
                             tmem_fence_after_sync();
-                            const uint32_t d = tmem + TM_SET + 128u * buf;
-                            if (uniform) {
-                                const uint64_t sh = shifts & 0xffu;
-                                umma_tf32(d, al + sh, wb, ID_128, false);
-                                umma_tf32(d, ah + sh, wb + (4096 >> 4), ID_128, true);
-                                umma_tf32(d, ones, wb + (8192 >> 4), ID_128, true);
-                                umma_tf32(d, ah + sh, wb, ID_128, true);
-                            } else {
+                            const uint32_t d = tmem_u + TM_SET + 128u * buf;
+                            if (elect_one()) {
+                                if (uniform) {
+                                    const uint64_t sh = shifts & 0xffu;
+                                    umma_tf32(d, al + sh, wb, ID_128, false);
+                                    umma_tf32(d, ah + sh, wb + (4096 >> 4), ID_128, true);
+                                    umma_tf32(d, ones, wb + (8192 >> 4), ID_128, true);
+                                    umma_tf32(d, ah + sh, wb, ID_128, true);
+                                } else {
 #pragma unroll
-                                for (int pc = 0; pc < 4; ++pc) {  // class pc: B rows / D columns 32pc .. 32pc+31
-                                    const uint64_t sh = (shifts >> (8 * pc)) & 0xffu, wp = wb + 32 * pc;
-                                    umma_tf32(d + 32 * pc, al + sh, wp, ID_32, false);
-                                    umma_tf32(d + 32 * pc, ah + sh, wp + (4096 >> 4), ID_32, true);
-                                    umma_tf32(d + 32 * pc, ones, wp + (8192 >> 4), ID_32, true);
-                                    umma_tf32(d + 32 * pc, ah + sh, wp, ID_32, true);
+                                    for (int pc = 0; pc < 4; ++pc) {  // class pc: B rows / D columns 32pc .. 32pc+31
+                                        const uint64_t sh = (shifts >> (8 * pc)) & 0xffu, wp = wb + 32 * pc;
+                                        umma_tf32(d + 32 * pc, al + sh, wp, ID_32, false);
+                                        umma_tf32(d + 32 * pc, ah + sh, wp + (4096 >> 4), ID_32, true);
+                                        umma_tf32(d + 32 * pc, ones, wp + (8192 >> 4), ID_32, true);
+                                        umma_tf32(d + 32 * pc, ah + sh, wp, ID_32, true);
+                                    }
                                 }
                             }
                             release_w();
-                            umma_commit(&bars[B_D_FULL + buf]);
+                            if (elect_one()) umma_commit(&bars[B_D_FULL + buf]);
                             ++dn;
                         }
                         ph_mark(3);
                     }
                 }
-                umma_commit(&bars[B_MMA_DONE]);
+                if (elect_one()) umma_commit(&bars[B_MMA_DONE]);
                 if (GRP && p.z_q != nullptr && last_grp) {
                     // grouped final GEMM: A tiles from the staging ring (search warps), W_out / bias tiles from the final ring
                     uint32_t fstep = fn, am_ = astep;
                     for (int j = 0; j < NJ; ++j) {
                         const uint32_t buf = wait_dbuf();
-                        const uint32_t d = tmem + TM_SET + 128u * buf;
+                        const uint32_t d = tmem_u + TM_SET + 128u * buf;
                         for (int st = 0; st < G_NST; ++st, ++am_, ++fstep) {
                             const uint32_t sa = am_ & 1u, slot = fstep % F_SLOTS;
                             TC_WAIT(&bars[B_W_FULL + sa], (am_ >> 1) & 1u);
@@ -1196,6 +1202,7 @@ auto drain = [&](int g, uint32_t tq) {
                             fence_proxy_async();
                             tmem_fence_after_sync();
                             const uint32_t abase = smem_base + SM_AT + sa * G_ASLOT, wbase = smem_base + SM_WO + slot * F_SLOT;
+                            if (elect_one()) {
                             if (st < G_NST - 1) {
                                 for (int i = 0; i < G_FI && G_FI * st + i < n_run; ++i) {
                                     const uint64_t ah = desc128(abase + i * 8192) + 8, al = ah + (4096 >> 4);  // + 8 rows: skip the halo
@@ -1213,8 +1220,9 @@ auto drain = [&](int g, uint32_t tq) {
                             }
                             umma_commit(&bars[B_W_EMPTY + sa]);
                             umma_commit(&bars[B_F_EMPTY + slot]);
+                            }
                         }
-                        umma_commit(&bars[B_D_FULL + buf]);
+                        if (elect_one()) umma_commit(&bars[B_D_FULL + buf]);
                         ++dn;
                     }
                 }
@@ -1227,12 +1235,13 @@ auto drain = [&](int g, uint32_t tq) {
                     uint32_t fstep = fn;
                     for (int j = 0; j < NJ; ++j) {
                         const uint32_t buf = wait_dbuf();
-                        const uint32_t d = tmem + TM_SET + 128u * buf;
+                        const uint32_t d = tmem_u + TM_SET + 128u * buf;
                         for (int s0 = 0; s0 <= n_run; s0 += F_ITEMS) {  // one ring step = up to F_ITEMS chunks (stages s0.., then the bias)
                             const uint32_t slot = fstep % F_SLOTS;
                             TC_WAIT(&bars[B_F_FULL + slot], (fstep / F_SLOTS) & 1u);
                             tmem_fence_after_sync();
                             const int s1 = min(s0 + F_ITEMS, n_run + 1);
+                            if (elect_one()) {
                             for (int s = s0; s < s1; ++s) {
                                 const uint64_t wb = desc128(smem_base + SM_WO + slot * F_SLOT + (s - s0) * 8192);
                                 if (s < n_run) {
@@ -1246,9 +1255,10 @@ auto drain = [&](int g, uint32_t tq) {
                                 }
                             }
                             umma_commit(&bars[B_F_EMPTY + slot]);
+                            }
                             ++fstep;
                         }
-                        umma_commit(&bars[B_D_FULL + buf]);
+                        if (elect_one()) umma_commit(&bars[B_D_FULL + buf]);
                         ++dn;
                     }
                     ph_mark(5);
@@ -1259,7 +1269,7 @@ auto drain = [&](int g, uint32_t tq) {
             // =====================================================================================================
             // Second phase-L MMA issuer: lane 0 of warp 15 (odd chunks); idle afterwards.
             // =====================================================================================================
-            if (!FC && lane == 0) issue_phase_l(1);
+            if (!FC) issue_phase_l(1);
             __syncwarp();
             tmem_fence_before_sync();
             __syncthreads();  // L -> S
@@ -1302,7 +1312,7 @@ auto drain = [&](int g, uint32_t tq) {
             tmem_fence_before_sync();
             __syncthreads();  // L -> S
             tmem_fence_after_sync();
-            if (!FC && lane == 0) {
+            if (!FC) {  // (whole warp on warp-uniform values, one elected lane issues: see tmem_u)
                 constexpr uint32_t ID_S = umma_idesc_tf32(128, SCW);
                 // codebook tile: 1024 rows -> LBO = 16384 B, SBO = 128 B
                 constexpr uint64_t DESC_CB = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)(16384 >> 4) << 16);
@@ -1318,8 +1328,10 @@ auto drain = [&](int g, uint32_t tq) {
                         const uint32_t gc = gs * (uint32_t)NSC + (uint32_t)c, sbuf = gc % NSB, use = gc / NSB;
                         if (use >= 1) TC_WAIT(&bars[B_SB_EMPTY + sbuf], (use - 1) & 1u);
                         tmem_fence_after_sync();
-                        umma_tf32(tmem + TM_SC + (uint32_t)SCW * sbuf, ae, cb + (uint64_t)(c * (SCW * 16 >> 4)), ID_S, false);
-                        umma_commit(&bars[B_SB_FULL + sbuf]);
+                        if (elect_one()) {
+                            umma_tf32(tmem_u + TM_SC + (uint32_t)SCW * sbuf, ae, cb + (uint64_t)(c * (SCW * 16 >> 4)), ID_S, false);
+                            umma_commit(&bars[B_SB_FULL + sbuf]);
+                        }
                     }
                 }
             }
