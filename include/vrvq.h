@@ -232,6 +232,15 @@ int vrvq_snake_conv3_tc_f32(const float *x, int64_t x_stride_b, int64_t x_stride
 int vrvq_snake_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, const float *alpha, int B, int C, int T, float *y,
                    int64_t y_stride_b, int64_t y_stride_c, void *stream);
 
+/* The last three blocks of the subnet (C0 -> C1 -> C2 -> 1, models/importance_subnet.py:36-43 with the sigmoid of line 43) in one
+ * launch (csrc/subnet_tc.cu: subnet_tail_kernel); serves the shipped widths 128 -> 32 -> 8 -> 1 (vrvq_subnet_tail_usable; others: chain
+ * vrvq_snake_conv3_f32).  packed0..2 / alpha0..2 / bias0..2: the three blocks' vrvq_pack_conv3_weights output, Snake alphas and biases;
+ * pre_activated != 0: x already went through block 0's Snake (a tensor-core producer's post_alpha).  y [B][1][T], unit stride along T. */
+int vrvq_subnet_tail_usable(int C0, int C1, int C2);
+int vrvq_subnet_tail_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, int pre_activated, int C0, int C1, int C2, const float *alpha0,
+                         const float *packed0, const float *bias0, const float *alpha1, const float *packed1, const float *bias1,
+                         const float *alpha2, const float *packed2, const float *bias2, int B, int T, float *y, int64_t y_stride_b, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,9 +61,21 @@ def main():
         rows.append(dict(block=i, cin=w.cin, cout=w.cout, us=us, gflop=flops / 1e9, tflops=flops / us / 1e6,
                          frac_fp32_peak=flops / us / 1e6 / peak_tf))
         cur = ops.snake_conv3(w, cur, sigmoid=last)
+    # the launches of the actual chain (ops.importance_subnet): Snake pre-pass, tensor-core blocks on activated row-padded input, fused tail
+    chain_rows = []
+    if blocks[0].packed_tc is not None and len(blocks) == 6:
+        xs = ops.snake(x, blocks[0].alpha, padded_out=True)
+        chain_rows.append(dict(launch="snake_prepass", us=timeit(lambda: ops.snake(x, blocks[0].alpha, padded_out=True))))
+        cur = xs
+        for i in range(3):
+            pa = blocks[i + 1].alpha
+            f = lambda cur=cur, i=i, pa=pa: ops.snake_conv3(blocks[i], cur, pre_activated=True, post_alpha=pa, padded_out=True)
+            chain_rows.append(dict(launch=f"tc_block_{i}", cin=blocks[i].cin, cout=blocks[i].cout, us=timeit(f)))
+            cur = f()
+        chain_rows.append(dict(launch="fused_tail", us=timeit(lambda: ops.subnet_tail(blocks[3:], cur, pre_activated=True))))
     chain_us = timeit(lambda: m(x))
     total = sum(r["gflop"] for r in rows) * 1e9
-    res = dict(B=B, T=T, frames=B * T, sm_mhz=sm_mhz, fp32_peak_tflops=peak_tf, blocks=rows, chain_us=chain_us,
+    res = dict(B=B, T=T, frames=B * T, sm_mhz=sm_mhz, fp32_peak_tflops=peak_tf, blocks=rows, chain_launches=chain_rows, chain_us=chain_us,
                chain_tflops=total / chain_us / 1e6, chain_frac_fp32_peak=total / chain_us / 1e6 / peak_tf,
                Mframes_per_s=B * T / chain_us)
     with torch.no_grad():

@@ -106,7 +106,7 @@ def test_vbr_forward_uses_the_subnet_kernels():
     z = torch.from_numpy(gi.make_latents(8, B, D, T, 1.0)).cuda()
     n0 = _lib.launch_count
     r = m(z, n_quantizers=None, feat_enc=torch.from_numpy(feat).cuda(), level=0.5)
-    assert _lib.launch_count - n0 == 8, "Snake pre-pass of the tensor-core blocks + six subnet launches + one fused encode launch"
+    assert _lib.launch_count - n0 == 6, "Snake pre-pass + three tensor-core blocks + the fused tail + one fused encode launch"
     imp = r["imp_map"]
     assert imp.shape == (B, 1, T)
     assert np.abs(imp.cpu().numpy() - H.load_golden("subnet_d1024")["imp_map"]).max() <= IMP_ATOL
@@ -200,3 +200,63 @@ def test_tensor_core_block_on_views():
     view = big[:, 16:80, 57:457]
     assert not view.is_contiguous()
     assert torch.equal(ops.snake_conv3(pw, view), ops.snake_conv3(pw, torch.from_numpy(x).cuda()))
+
+
+# ---- the narrow tail 128 -> 32 -> 8 -> 1 + sigmoid in one launch (vrvq_subnet_tail_f32) ------------------------------------------
+def _tail_blocks(seed):
+    from vrvq_b200 import ops
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    raw, blocks = [], []
+    for cin, cout in ((128, 32), (32, 8), (8, 1)):
+        w = (rng.normal(size=(cout, cin, 3)) / np.sqrt(3 * cin) * 1.5).astype(np.float32)
+        alpha = rng.uniform(0.5, 1.5, cin).astype(np.float32)
+        bias = rng.normal(size=cout).astype(np.float32)
+        raw.append((w, alpha, bias))
+        blocks.append(ops.PackedConv3(torch.from_numpy(alpha), torch.from_numpy(w), torch.from_numpy(bias), "cuda"))
+    return raw, blocks
+
+
+@pytest.mark.parametrize("B,T", [(2, 87), (1, 1), (3, 60), (2, 61), (1, 59), (2, 121), (4, 301), (0, 5), (2, 0)])
+def test_fused_tail_matches_block_chain_and_binary64(B, T, monkeypatch):
+    """Tile edges (60 output frames per CTA), sequence ends (every level has its own zero padding) and empty inputs: against the chain
+    of generic block launches and against the binary64 evaluation."""
+    from vrvq_b200 import ops
+
+    raw, blocks = _tail_blocks(40 + B + T)
+    x = np.random.Generator(np.random.PCG64(B * 1000 + T)).normal(0, 1.5, (B, 128, T)).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    y = ops.subnet_tail(blocks, xd)
+    assert y.shape == (B, 1, T)
+    if B * T == 0:
+        return
+    chain = xd
+    for i, blk in enumerate(blocks):
+        chain = ops.snake_conv3(blk, chain, sigmoid=(i == 2))
+    o = x.astype(np.float64)
+    for w, alpha, bias in raw:
+        o = sp.conv3(sp.snake(o, alpha, np.float64), w.astype(np.float64), bias.astype(np.float64))
+    o = 1.0 / (1.0 + np.exp(-o))
+    assert np.abs(y.cpu().numpy() - o).max() <= IMP_ATOL
+    assert np.abs(y.cpu().numpy() - chain.cpu().numpy()).max() <= IMP_ATOL  # (two fp32 evaluations of the map)
+    # pre-activated input (what a tensor-core producer's post_alpha stores) and a frame-range view give the same map
+    y2 = ops.subnet_tail(blocks, ops.snake(xd, blocks[0].alpha), pre_activated=True)
+    assert torch.equal(y2, y)
+    big = torch.zeros((B, 128, T + 9), device="cuda")
+    big[:, :, 4:4 + T] = xd
+    assert torch.equal(ops.subnet_tail(blocks, big[:, :, 4:4 + T]), y)
+
+
+def test_chain_with_and_without_the_fused_launches_agree(monkeypatch):
+    """The shipped architecture with VRVQ_SUBNET_IMPL=cuda (six generic launches on the CUDA cores) against the default chain
+    (tensor-core blocks + fused tail): two fp32-grade evaluations of the same map."""
+    c = dict(gi.SUBNET_CASES["subnet_d1024"], B=3, T=301)
+    sd, x = case_inputs(c)
+    m = build(c, sd)
+    xd = torch.from_numpy(x).cuda()
+    y = m(xd)
+    monkeypatch.setenv("VRVQ_SUBNET_IMPL", "cuda")
+    y_cuda = m(xd)
+    monkeypatch.delenv("VRVQ_SUBNET_IMPL")
+    assert not torch.equal(y, y_cuda)
+    assert float((y - y_cuda).abs().max()) <= 2 * IMP_ATOL  # each is within IMP_ATOL of the reference's map (fixture tests)

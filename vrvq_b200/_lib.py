@@ -56,6 +56,7 @@ EXPORTS = [
     "vrvq_search_latents_f32", "vrvq_generate_mask_hard_f32", "vrvq_mask_sum_f32", "vrvq_remask_f32",
     "vrvq_pack_codes_u16", "vrvq_unpack_codes_u16", "vrvq_conv3_packed_floats", "vrvq_pack_conv3_weights", "vrvq_snake_conv3_f32",
     "vrvq_conv3_tc_packed_floats", "vrvq_pack_conv3_tc_weights", "vrvq_snake_conv3_tc_f32", "vrvq_snake_f32",
+    "vrvq_subnet_tail_usable", "vrvq_subnet_tail_f32",
 ]
 
 _lib = None
@@ -114,6 +115,9 @@ def lib():
                                           C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     L.vrvq_snake_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                  C.c_void_p]
+    L.vrvq_subnet_tail_usable.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.vrvq_subnet_tail_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_void_p,
+                                                                                                                  C.c_int64, C.c_void_p]
     if L.vrvq_abi_version() != ABI_VERSION:
         raise ImportError(f"libvrvq.so ABI {L.vrvq_abi_version()} != binding ABI {ABI_VERSION}; rebuild with python -m vrvq_b200.build")
     _lib = L

@@ -68,6 +68,10 @@ int launch_snake_conv3_tc(const float *x, long long x_sb, long long x_sc, const 
                           const float *post_alpha, int B, int Cin, int Cout, int T, float *y, long long y_sb, long long y_sc, cudaStream_t st);
 int launch_snake(const float *x, long long x_sb, long long x_sc, const float *alpha, int B, int C, int T, float *y, long long y_sb, long long y_sc,
                  cudaStream_t st);
+int subnet_tail_usable(int C0, int C1, int C2);
+int launch_subnet_tail(const float *x, long long x_sb, long long x_sc, int pre_activated, const float *alpha0, const float *w0, const float *bias0,
+                       const float *alpha1, const float *w1, const float *bias1, const float *alpha2, const float *w2, const float *bias2, int B, int T,
+                       float *y, long long y_sb, cudaStream_t st);
 int launch_search_latents(const float *blob, int D, int K, const float *lat, long long l_sb, long long l_sc, int B, int T, int n_run,
                           long long *codes, long long c_sb, long long c_sq, cudaStream_t st);
 
@@ -469,6 +473,25 @@ int vrvq_snake_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, const
     int rc = check_device();
     if (rc) return rc;
     return launch_snake(x, x_stride_b, x_stride_c, alpha, B, C, T, y, y_stride_b, y_stride_c, static_cast<cudaStream_t>(stream));
+}
+
+int vrvq_subnet_tail_usable(int C0, int C1, int C2) { return subnet_tail_usable(C0, C1, C2); }
+
+int vrvq_subnet_tail_f32(const float *x, int64_t x_stride_b, int64_t x_stride_c, int pre_activated, int C0, int C1, int C2, const float *alpha0,
+                         const float *packed0, const float *bias0, const float *alpha1, const float *packed1, const float *bias1,
+                         const float *alpha2, const float *packed2, const float *bias2, int B, int T, float *y, int64_t y_stride_b, void *stream) {
+    if (!subnet_tail_usable(C0, C1, C2)) {
+        set_error("vrvq_subnet_tail_f32: serves the widths %d -> %d -> %d -> 1 only (got %d -> %d -> %d)", 128, 32, 8, C0, C1, C2);
+        return VRVQ_EUNSUPPORTED;
+    }
+    if (B < 0 || T < 0 || !alpha0 || !packed0 || !bias0 || !alpha1 || !packed1 || !bias1 || !alpha2 || !packed2 || !bias2 || ((long long)B * T > 0 && (!x || !y))) {
+        set_error("vrvq_subnet_tail_f32: bad arguments");
+        return VRVQ_EINVAL;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    return launch_subnet_tail(x, x_stride_b, x_stride_c, pre_activated, alpha0, packed0, bias0, alpha1, packed1, bias1, alpha2, packed2, bias2, B, T, y,
+                              y_stride_b, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

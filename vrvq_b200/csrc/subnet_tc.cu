@@ -379,13 +379,130 @@ __global__ void __launch_bounds__(ST_NTH, 1) snake_conv3_tc_kernel(const SnTcPar
 
 // y[b][c][t] = snake(x[b][c][t], alpha[c]): the activation of the FIRST tensor-core block's input, computed once instead of once per
 // 128-channel output tile (8 times for 1024 -> 1024); the later blocks get theirs from the previous epilogue (post_alpha)
-__global__ void snake_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, const float *__restrict__ alpha, float *__restrict__ y,
-                             long long y_sb, long long y_sc, int C, int T) {
-    const int c = blockIdx.y, b = blockIdx.z;
+__global__ void __launch_bounds__(256) snake_kernel(const float *__restrict__ x, long long x_sb, long long x_sc, const float *__restrict__ alpha,
+                                                    float *__restrict__ y, long long y_sb, long long y_sc, int C, int T) {
+    // one CTA = 8 channel rows of one item: warp = row, 4 independent loads in flight per lane
+    const int c = 8 * blockIdx.x + (threadIdx.x >> 5), b = blockIdx.y, lane = threadIdx.x & 31;
+    if (c >= C) return;
     const float a = __ldg(alpha + c), inv_a = snake_inv(a);
     const float *xr = x + (long long)b * x_sb + (long long)c * x_sc;
     float *yr = y + (long long)b * y_sb + (long long)c * y_sc;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) yr[t] = snake_tc(xr[t], a, inv_a);
+    int t = lane;
+    for (; t + 96 < T; t += 128) {
+        const float v0 = __ldcs(xr + t), v1 = __ldcs(xr + t + 32), v2 = __ldcs(xr + t + 64), v3 = __ldcs(xr + t + 96);
+        yr[t] = snake_tc(v0, a, inv_a); yr[t + 32] = snake_tc(v1, a, inv_a); yr[t + 64] = snake_tc(v2, a, inv_a); yr[t + 96] = snake_tc(v3, a, inv_a);
+    }
+    for (; t < T; t += 32) yr[t] = snake_tc(__ldcs(xr + t), a, inv_a);
+}
+
+// ---- the narrow tail of the subnet in ONE launch ----------------------------------------------------------------------------------
+// models/importance_subnet.py's last three blocks (128 -> 32 -> 8 -> 1, then the sigmoid of line 43) are 13 kMAC per frame -- three
+// launches of the generic block kernel spent ~100 us at config-2 size on launch latency and half-empty grids.  Here one CTA of 256
+// threads takes 60 output frames through all three: it stages the 128-channel input for frames t0 - 3 .. t0 + 62 and block A's weights
+// with cp.async (everything in flight at once; Snake applied in place unless the producer already stored the input activated),
+// computes block A on 64 positions (warp = 8 of its 32 channels x 32 positions, lane = position), block B on 62, block C + sigmoid on
+// 60, each block reading its predecessor's Snake-activated output from shared memory.  Positions outside [0, T) are the convolutions'
+// zero padding at every level.  Weights: the generic kernel's packed layout [(ci * 3 + tap)][128 columns].
+constexpr int TL_C0 = 128, TL_C1 = 32, TL_C2 = 8, TL_F = 60, TL_NA = TL_F + 6, TL_AP = 68, TL_HP = 65, TL_NTH = 256;
+constexpr int TL_SM_A = 0, TL_SM_W3 = TL_SM_A + TL_C0 * TL_AP * 4, TL_SM_H3 = TL_SM_W3 + TL_C0 * 3 * TL_C1 * 4, TL_SM_W4 = TL_SM_H3 + TL_C1 * TL_HP * 4;
+constexpr int TL_SM_H4 = TL_SM_W4 + TL_C1 * 3 * TL_C2 * 4, TL_SM_W5 = TL_SM_H4 + TL_C2 * 64 * 4, TL_SMEM = TL_SM_W5 + TL_C2 * 3 * 4;
+static_assert(TL_SM_W3 % 16 == 0 && TL_SM_W4 % 16 == 0, "16-byte cp.async / vector loads");
+
+struct TailParams {
+    const float *x;
+    long long x_sb, x_sc;
+    const float *alpha0, *w0, *bias0, *alpha1, *w1, *bias1, *alpha2, *w2, *bias2;
+    float *y;
+    long long y_sb;
+    int B, T, pre_activated;
+};
+
+__global__ void __launch_bounds__(TL_NTH) subnet_tail_kernel(const TailParams P) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    float *A = reinterpret_cast<float *>(tsm + TL_SM_A), *W3 = reinterpret_cast<float *>(tsm + TL_SM_W3), *H3 = reinterpret_cast<float *>(tsm + TL_SM_H3);
+    float *W4 = reinterpret_cast<float *>(tsm + TL_SM_W4), *H4 = reinterpret_cast<float *>(tsm + TL_SM_H4), *W5 = reinterpret_cast<float *>(tsm + TL_SM_W5);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, cg = w & 3, pos = 32 * (w >> 2) + lane;
+    const int b = blockIdx.y, t0 = blockIdx.x * TL_F;
+    // weights: the first 32 / 8 / 1 columns of the packed rows
+    for (int i = tid; i < TL_C0 * 3 * TL_C1 / 4; i += TL_NTH) cp_async<16>(W3 + 4 * i, P.w0 + (size_t)(i >> 3) * VRVQ_CONV3_COUT_ALIGN + 4 * (i & 7));
+    for (int i = tid; i < TL_C1 * 3 * TL_C2 / 4; i += TL_NTH) cp_async<16>(W4 + 4 * i, P.w1 + (size_t)(i >> 1) * VRVQ_CONV3_COUT_ALIGN + 4 * (i & 1));
+    if (tid < TL_C2 * 3) W5[tid] = __ldg(P.w2 + (size_t)tid * VRVQ_CONV3_COUT_ALIGN);
+    // input: A[ci][q] = x[b][ci][t0 - 3 + q], q < 66; zeros outside [0, T) (cp.async with a source size of 0 writes zeros)
+    {
+        const float *xb = P.x + (long long)b * P.x_sb;
+        for (int i = tid; i < TL_C0 * TL_NA; i += TL_NTH) {
+            const int ci = i / TL_NA, q = i - ci * TL_NA, t = t0 - 3 + q;
+            const bool ok = t >= 0 && t < P.T;
+            const float *src = xb + (long long)ci * P.x_sc + (ok ? t : 0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(A + ci * TL_AP + q)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+        }
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    if (!P.pre_activated) {
+        for (int i = tid; i < TL_C0 * TL_NA; i += TL_NTH) {
+            const int ci = i / TL_NA, q = i - ci * TL_NA;
+            const float a = __ldg(P.alpha0 + ci);
+            A[ci * TL_AP + q] = snake_tc(A[ci * TL_AP + q], a, snake_inv(a));  // (snake(0) = 0: the padding stays zero)
+        }
+        __syncthreads();
+    }
+    // block A: position pos (frame t0 - 2 + pos), channels 8 cg .. 8 cg + 7
+    {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = __ldg(P.bias0 + 8 * cg + j);
+#pragma unroll 4
+        for (int ci = 0; ci < TL_C0; ++ci) {
+            const float *ar = A + ci * TL_AP + pos;
+            const float a3[3] = {ar[0], ar[1], ar[2]};
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(W3 + (ci * 3 + tap) * TL_C1 + 8 * cg);
+                const float4 w1 = *reinterpret_cast<const float4 *>(W3 + (ci * 3 + tap) * TL_C1 + 8 * cg + 4);
+                acc[0] = fmaf(w0.x, a3[tap], acc[0]); acc[1] = fmaf(w0.y, a3[tap], acc[1]); acc[2] = fmaf(w0.z, a3[tap], acc[2]); acc[3] = fmaf(w0.w, a3[tap], acc[3]);
+                acc[4] = fmaf(w1.x, a3[tap], acc[4]); acc[5] = fmaf(w1.y, a3[tap], acc[5]); acc[6] = fmaf(w1.z, a3[tap], acc[6]); acc[7] = fmaf(w1.w, a3[tap], acc[7]);
+            }
+        }
+        const int t = t0 - 2 + pos;
+        const bool ok = t >= 0 && t < P.T;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = __ldg(P.alpha1 + 8 * cg + j);
+            H3[(8 * cg + j) * TL_HP + pos] = ok ? snake_tc(acc[j], a, snake_inv(a)) : 0.0f;
+        }
+    }
+    __syncthreads();
+    // block B: position pos < 62 (frame t0 - 1 + pos), channels 2 cg, 2 cg + 1
+    if (pos < TL_F + 2) {
+        float acc0 = __ldg(P.bias1 + 2 * cg), acc1 = __ldg(P.bias1 + 2 * cg + 1);
+#pragma unroll 4
+        for (int ci = 0; ci < TL_C1; ++ci) {
+            const float *hr = H3 + ci * TL_HP + pos;
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) {
+                const float2 wv = *reinterpret_cast<const float2 *>(W4 + (ci * 3 + tap) * TL_C2 + 2 * cg);
+                acc0 = fmaf(wv.x, hr[tap], acc0);
+                acc1 = fmaf(wv.y, hr[tap], acc1);
+            }
+        }
+        const int t = t0 - 1 + pos;
+        const bool ok = t >= 0 && t < P.T;
+        const float a0 = __ldg(P.alpha2 + 2 * cg), a1 = __ldg(P.alpha2 + 2 * cg + 1);
+        H4[(2 * cg) * 64 + pos] = ok ? snake_tc(acc0, a0, snake_inv(a0)) : 0.0f;
+        H4[(2 * cg + 1) * 64 + pos] = ok ? snake_tc(acc1, a1, snake_inv(a1)) : 0.0f;
+    }
+    __syncthreads();
+    // block C + sigmoid: frame t0 + tid, tid < 60
+    if (tid < TL_F && t0 + tid < P.T) {
+        float acc = __ldg(P.bias2);
+#pragma unroll
+        for (int ci = 0; ci < TL_C2; ++ci)
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) acc = fmaf(W5[ci * 3 + tap], H4[ci * 64 + tid + tap], acc);
+        P.y[(long long)b * P.y_sb + t0 + tid] = 1.0f / (1.0f + expf(-acc));
+    }
 }
 
 }  // namespace
@@ -393,12 +510,29 @@ __global__ void snake_kernel(const float *__restrict__ x, long long x_sb, long l
 int launch_snake(const float *x, long long x_sb, long long x_sc, const float *alpha, int B, int C, int T, float *y, long long y_sb, long long y_sc,
                  cudaStream_t st) {
     if ((long long)B * C * T == 0) return VRVQ_OK;
-    if (B > 65535 || C > 65535) {
-        set_error("vrvq_snake_f32: B and C must be <= 65535");
+    if (B > 65535) {
+        set_error("vrvq_snake_f32: B must be <= 65535");
         return VRVQ_EUNSUPPORTED;
     }
-    snake_kernel<<<dim3((unsigned)((T + 255) / 256 < 8 ? (T + 255) / 256 : 8), (unsigned)C, (unsigned)B), 256, 0, st>>>(x, x_sb, x_sc, alpha, y, y_sb, y_sc, C, T);
+    snake_kernel<<<dim3((unsigned)((C + 7) / 8), (unsigned)B), 256, 0, st>>>(x, x_sb, x_sc, alpha, y, y_sb, y_sc, C, T);
     return check_cuda(cudaGetLastError(), "snake_kernel launch");
+}
+
+int subnet_tail_usable(int C0, int C1, int C2) { return C0 == TL_C0 && C1 == TL_C1 && C2 == TL_C2; }
+
+int launch_subnet_tail(const float *x, long long x_sb, long long x_sc, int pre_activated, const float *alpha0, const float *w0, const float *bias0,
+                       const float *alpha1, const float *w1, const float *bias1, const float *alpha2, const float *w2, const float *bias2, int B, int T,
+                       float *y, long long y_sb, cudaStream_t st) {
+    if ((long long)B * T == 0) return VRVQ_OK;
+    if (B > 65535) {
+        set_error("vrvq_subnet_tail_f32: B must be <= 65535");
+        return VRVQ_EUNSUPPORTED;
+    }
+    TailParams P{x, x_sb, x_sc, alpha0, w0, bias0, alpha1, w1, bias1, alpha2, w2, bias2, y, y_sb, B, T, pre_activated};
+    int rc = ensure_dynamic_smem<subnet_tail_kernel>(TL_SMEM, "cudaFuncSetAttribute(subnet_tail_kernel)");
+    if (rc) return rc;
+    subnet_tail_kernel<<<dim3((unsigned)((T + TL_F - 1) / TL_F), (unsigned)B), TL_NTH, TL_SMEM, st>>>(P);
+    return check_cuda(cudaGetLastError(), "subnet_tail_kernel launch");
 }
 
 // ---- host side -----------------------------------------------------------------------------------

@@ -425,13 +425,46 @@ def snake(x: torch.Tensor, alpha: torch.Tensor, padded_out: bool = False) -> tor
     return y
 
 
+def subnet_tail(blocks, x: torch.Tensor, pre_activated: bool = False) -> torch.Tensor:
+    """vrvq_subnet_tail_f32: the last three blocks (128 -> 32 -> 8 -> 1) and the sigmoid in one launch, x [B,128,T] -> [B,1,T]."""
+    require_cuda_f32(x, "x")
+    b0, b1, b2 = blocks
+    if x.dim() != 3 or x.shape[1] != b0.cin:
+        raise VrvqError(f"x must be [B, {b0.cin}, T], got {tuple(x.shape)}")
+    B, _, T = x.shape
+    y = torch.empty((B, 1, T), dtype=torch.float32, device=x.device)
+    if B * T == 0:
+        return y
+    _check_view(x, "x")
+    with torch.cuda.device(x.device):
+        check(_lib.lib().vrvq_subnet_tail_f32(x.data_ptr(), x.stride(0), x.stride(1), int(bool(pre_activated)), b0.cin, b1.cin, b2.cin, b0.alpha.data_ptr(),
+                                              b0.packed.data_ptr(), b0.bias.data_ptr(), b1.alpha.data_ptr(), b1.packed.data_ptr(), b1.bias.data_ptr(),
+                                              b2.alpha.data_ptr(), b2.packed.data_ptr(), b2.bias.data_ptr(), B, T, y.data_ptr(), y.stride(0),
+                                              current_stream_ptr(x.device)), "vrvq_subnet_tail_f32")
+    _lib.count_launch()
+    return y
+
+
+def _tail_ok(blocks) -> bool:
+    import os
+
+    if len(blocks) < 3 or os.environ.get("VRVQ_SUBNET_IMPL", "") == "cuda":
+        return False
+    b0, b1, b2 = blocks[-3:]
+    return b2.cout == 1 and b0.cout == b1.cin and b1.cout == b2.cin and bool(_lib.lib().vrvq_subnet_tail_usable(b0.cin, b1.cin, b2.cin))
+
+
 def importance_subnet(blocks, x: torch.Tensor) -> torch.Tensor:
-    """models/importance_subnet.py:38-44 on packed blocks: chain of snake_conv3 launches, sigmoid fused into the last.
-    A run of tensor-core blocks evaluates each Snake once: the first one's input goes through vrvq_snake_f32, every later one gets its
+    """models/importance_subnet.py:38-44 on packed blocks: tensor-core launches for the wide blocks (csrc/subnet_tc.cu), one launch for
+    the narrow tail 128 -> 32 -> 8 -> 1 with the sigmoid (vrvq_subnet_tail_f32); other shapes chain vrvq_snake_conv3_f32.
+    A run of tensor-core blocks evaluates each Snake once: the first one's input goes through vrvq_snake_f32, every later block gets its
     activation from its predecessor's epilogue (`post_alpha`) -- inside a block the activation would be recomputed for each of the
     Cout / 128 output tiles (8 times for 1024 -> 1024: 250 of 970 us at config-2 size)."""
+    blocks = list(blocks)
+    n_head = len(blocks) - 3 if _tail_ok(blocks) else len(blocks)
     pre = False
-    for i, w in enumerate(blocks):
+    for i in range(n_head):
+        w = blocks[i]
         last = i == len(blocks) - 1
         tc = (not last) and _tc_block_ok(w, x)
         if tc and not pre:
@@ -439,14 +472,16 @@ def importance_subnet(blocks, x: torch.Tensor) -> torch.Tensor:
             pre = True
         nxt = blocks[i + 1] if i + 1 < len(blocks) else None
         post = None
-        if tc and nxt is not None and i + 1 < len(blocks) - 1 and nxt.packed_tc is not None:
-            post = nxt.alpha  # (the next block is a tensor-core block too: y has its batch pitch Cout * T, a multiple of 4 when T is -- checked there)
+        if tc and nxt is not None and ((i + 1 < n_head and i + 1 < len(blocks) - 1 and nxt.packed_tc is not None) or i + 1 == n_head):
+            post = nxt.alpha  # the consumer takes activated input: a tensor-core block (its batch pitch Cout * padded T is a multiple of 4) or the tail
         if tc:
             y = snake_conv3(w, x, pre_activated=True, post_alpha=post, padded_out=True)  # (intermediate activations: rows padded to 16 bytes)
-            if post is not None and not _tc_block_ok(nxt, y):  # cannot happen for contiguous outputs of these widths; keep the chain correct anyway
+            if post is not None and i + 1 < n_head and not _tc_block_ok(nxt, y):  # cannot happen for outputs of these widths; keep the chain correct anyway
                 raise VrvqError("internal: post-activated output handed to a block that cannot take it")
             x, pre = y, post is not None
         else:
             x = snake_conv3(w, x, sigmoid=last)
             pre = False
+    if n_head < len(blocks):
+        x = subnet_tail(blocks[n_head:], x, pre_activated=pre)
     return x
