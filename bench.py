@@ -436,7 +436,7 @@ def run_ours(args):
             "e2e_subnet": {"value": world * frames * sub_steps / (sub_ms_max * 1e-3), "unit": "frames/s", "steps": sub_steps,
                            "ms_per_step": sub_ms_max / sub_steps,
                            "what": "VBRResidualVectorQuantize.forward(z, None, feat_enc, level) with z and feat_enc resident in HBM: the six "
-                                   "importance-subnet launches (fp32 CUDA cores, 9.85 MFLOP per frame) + the fused encode; `value` above takes "
+                                   "importance-subnet launches (blocks 0-2 on tcgen05 3xTF32, fused tail; 9.85 MFLOP per frame) + the fused encode; `value` above takes "
                                    "imp_map as an input (SURVEY.md 8(d))"},
             "host": host_info,
             "gpu_launches": launches * world, "clocks": clocks, "torch": torch.__version__,
