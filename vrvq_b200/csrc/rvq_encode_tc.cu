@@ -70,6 +70,7 @@ constexpr int SM_ZR = WL_SLOTS * L_SLOT, Z_CH = 32, Z_PITCH = 132, Z_SLOT = Z_CH
 constexpr int SM_AT = 0;           // phase S: per-stage A tiles, 8 x (hi 4 KB | lo 4 KB): [2 kg][128 frames][4]
 constexpr int SM_AM = 65536;       // phase S: mask tile (A operand of the bias rows of the final GEMM) [2 kg][128][4]
 constexpr int SM_WO = 69632;       // phase S: W_out ring, 4 slots x 12 KB (hi | lo | bias tile)
+constexpr int SM_RAW = SM_WO + 16384;  // without z_q_is (W_out ring idle; candidate lists in its first 16 KB): un-normalised codebook of the stage, 32 KB
 constexpr int SM_CB1 = 118784;     // search codebook buffer 1 (36864 B)
 constexpr int SM_CB0 = 155648;     // search codebook buffer 0 (outside the phase-L region: prefetched during phase L)
 constexpr int SM_ES = 192512;      // A operand of the search MMA: 2*e as a [2 kg][128 frames][4] tile
@@ -91,13 +92,14 @@ constexpr int F_SLOT = 40960, F_SLOTS = 3, F_ITEMS = 5;  // final-GEMM ring (<= 
 static_assert(SM_TOTAL <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 static_assert(SM_WO + W_SLOTS * W_SLOT == SM_CB1 && SM_CB1 + 36864 == SM_CB0 && SM_CB0 + 36864 == SM_ES, "shared memory map");
 static_assert(SM_WO + F_SLOTS * F_SLOT == SM_ES, "final ring covers [SM_WO, SM_ES)");
+static_assert(SM_RAW + 32768 <= SM_CB1 && !VRVQ_THIRD_SCAN_GROUP, "un-normalised codebook sits behind the candidate lists of two scan groups in the idle W_out ring");
 static_assert(SM_ZR + Z_SLOTS * Z_SLOT <= SM_CB0, "phase-L rings must not reach codebook buffer 0");
 static_assert(SM_ZR % 128 == 0 && Z_SLOT % 128 == 0, "TMA destinations are 128-byte aligned");
 
 enum {
     B_L_FULL = 0, B_L_EMPTY = 4, B_SET_FULL = 24, B_SET_EMPTY = 26, B_W_FULL = 28, B_W_EMPTY = 32,
     B_D_FULL = 36, B_D_EMPTY = 38, B_CB_FULL = 40, B_A_READY = 42, B_ZQ_READY = 50, B_MMA_DONE = 51, B_F_FULL = 52, B_F_EMPTY = 56,
-    B_E_READY = 60, B_L_FULL2 = 73, B_WL_FULL = 76, B_WL_EMPTY = 80, B_Z_FULL = 84, B_Z_EMPTY = 89, B_SB_FULL = 94, B_SB_EMPTY = 100, B_COUNT = 106
+    B_E_READY = 60, B_L_FULL2 = 73, B_WL_FULL = 76, B_WL_EMPTY = 80, B_Z_FULL = 84, B_Z_EMPTY = 89, B_SB_FULL = 94, B_SB_EMPTY = 100, B_RAW_FULL = 106, B_COUNT = 107
 };
 enum { ZMODE_LDG = 0, ZMODE_BULK = 1, ZMODE_TMA = 2 };  // how phase L fetches the latent
 
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         mbar_init(&bars[B_MMA_DONE], 1);
         for (int i = 0; i < F_SLOTS; ++i) { mbar_init(&bars[B_F_FULL + i], 1); mbar_init(&bars[B_F_EMPTY + i], 1); }
         mbar_init(&bars[B_E_READY], 4);
+        mbar_init(&bars[B_RAW_FULL], 1);  // un-normalised codebook of the stage (without z_q_is): the producer's expect_tx + 32 KB
         for (int i = 0; i < 6; ++i) { mbar_init(&bars[B_SB_FULL + i], 1); mbar_init(&bars[B_SB_EMPTY + i], 4); }
         // latent staging slot: filled by the producer's expect_tx + the TMA bytes, released by the 8 loader warps
         for (int i = 0; i < Z_SLOTS; ++i) { mbar_init(&bars[B_Z_FULL + i], 1); mbar_init(&bars[B_Z_EMPTY + i], 8); }
@@ -294,6 +297,11 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         if (PROFILE && P.trace && blockIdx.x == 0 && p.phase_cycles != nullptr) p.phase_cycles[1024 + 32 * ev + idx] = clock64();
     };
 
+    // VRVQ_DEBUG_PHASES=3, stage time line of block 0's first pass: phase_cycles[1024 + 32 * event + stage], events 8-15 thread 0 (frame
+    // thread, scan group 0), 16-20 thread 128 (scan group 1), 21-23 the search-MMA issuer (see the table printed by the launcher)
+    auto strace = [&](int ev, int stg, bool first_pass) {
+        if (PROFILE && P.trace && blockIdx.x == 0 && first_pass && p.phase_cycles != nullptr) p.phase_cycles[1024 + 32 * ev + stg] = clock64();
+    };
     // Full barrier of phase-L chunk n (slot n % 3, use n / 3).  Consecutive uses of a slot belong to different issuing threads
     // (3 is odd), and a parity wait can only tell the current phase from the previous one: an issuer that ran one use ahead of
     // the other would see "complete" for a slot that is still being filled.  So even and odd uses get their own barrier, each
@@ -440,6 +448,14 @@ auto drain = [&](int g, uint32_t tq) {
                     int bidx = 0x7fffffff;
                     float runmax = __int_as_float(0xff800000);
                     int cnt = 0;
+                    // (no wait for the codebook buffer here: the scores waited for below come from MMAs that the issuer released only after
+                    // it had seen B_CB_FULL of this stage, so the copy is complete and visible by then; a completed wait would still cost
+                    // its ~200 cycles on the path to the first scores)
+                    (void)cbuse;
+                    // codes whose normalised row is not a unit vector (blob section SPC; none in a trained or random model): the
+                    // score filter cannot rank them, so they are always re-scored exactly -- or, if there are many, everything is
+                    const int *spc = reinterpret_cast<const int *>(P.tc + TL.off_spc()) + (s0 + s) * 16;
+                    const int nsp = __ldg(spc);
                     constexpr int NPIECE = (NSC + NSG - 1) / NSG * (SCW / 64);  // this group's score chunks (SCW codes each), in 64-code pieces
                     for (int pc = 0; pc < NPIECE; ++pc) {
                         const int ck = NSG * (pc / (SCW / 64)) + h, sub = pc % (SCW / 64);
@@ -449,6 +465,7 @@ auto drain = [&](int g, uint32_t tq) {
                         if (sub == 0) {
                             TC_WAIT(&bars[B_SB_FULL + sbuf], (gc / NSB) & 1u);
                             tmem_fence_after_sync();
+                            if (PROFILE && pc == 0 && (tid & 127) == 0) strace(tid == 0 ? 9 : 18, s, it == 0);
                         }
                         ph_mark(8);
                         uint32_t va[32], vb[32];
@@ -495,7 +512,7 @@ auto drain = [&](int g, uint32_t tq) {
                         }
                         ph_mark(10);
                     }
-                    TC_WAIT(&bars[B_CB_FULL + (s & 1)], cbuse & 1u);  // (long complete: the score MMAs read the same buffer)
+                    if (PROFILE && (tid & 127) == 0) strace(tid == 0 ? 10 : 19, s, it == 0);
                     // 2e / e2 of the frame (written by its frame thread before it released the stage to the search-MMA issuer: the
                     // scores waited for above are causally after those writes)
                     const float4 ea = *reinterpret_cast<const float4 *>(&es[f * 4]), eb = *reinterpret_cast<const float4 *>(&es[512 + f * 4]);
@@ -517,10 +534,6 @@ auto drain = [&](int g, uint32_t tq) {
                             c0 = (hit && nc == 0) ? gidx : c0;
                             nc += hit ? 1 : 0;
                         }
-                        // codes whose normalised row is not a unit vector (blob section SPC; none in a trained or random model): the
-                        // score filter cannot rank them, so they are always re-scored exactly -- or, if there are many, everything is
-                        const int *spc = reinterpret_cast<const int *>(P.tc + TL.off_spc()) + (s0 + s) * 16;
-                        const int nsp = __ldg(spc);
                         const int mode = (cnt > 16 || nsp > 15) ? 2 : nc > 3 ? 1 : 0;
                         const int total = mode == 2 ? ((NSC - h + NSG - 1) / NSG) * (SCW / 8) : mode == 1 ? cnt : nc;
                         for (int wi = 0; wi < total; ++wi) {
@@ -560,6 +573,7 @@ auto drain = [&](int g, uint32_t tq) {
                         }
                     }
                     ph_mark(11);
+                    if (PROFILE && (tid & 127) == 0) strace(tid == 0 ? 11 : 20, s, it == 0);
                     bd_out = bd;
                     bi_out = bidx;
         };
@@ -836,10 +850,7 @@ auto drain = [&](int g, uint32_t tq) {
             // bias, latents, normalise (quantize.py:66,92 in torch's op order) of stage s: frame threads.  Runs one stage ahead of the
             // searches: right after stage s - 1 has corrected the running sum of stage s (below), so the score MMAs of stage s
             // start while the corrections of the later stages are still being applied.
-            auto prep = [&](int s) {
-                uint32_t r8[8];
-                tmem_ld8(tq + TM_RUN + 8 * s, r8);
-                tmem_wait_ld(r8);
+            auto prep_from = [&](int s, const uint32_t (&r8)[8]) {  // r8: the (corrected) running sum W_in[s] z of the frame
                 float ss = 0.0f;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -864,10 +875,16 @@ auto drain = [&](int g, uint32_t tq) {
                     for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)((s0 + s) * 8 + k) * p.lat_sc + fr] = zev[k];
                 }
             };
-            // correction of a later stage of the pass by the straight-through vector of stage s: z_e[s2] -= G[s2][s] q + g[s2][s]
-            auto correct = [&](int s, int s2, const float (&qv)[8]) {
-                const float *G = ggs + TcLayout::pair_index(GRP ? 8 : Nq, s, s2) * 72;
+            auto prep = [&](int s) {
                 uint32_t r8[8];
+                tmem_ld8(tq + TM_RUN + 8 * s, r8);
+                tmem_wait_ld(r8);
+                prep_from(s, r8);
+            };
+            // correction of a later stage of the pass by the straight-through vector of stage s: z_e[s2] -= G[s2][s] q + g[s2][s];
+            // corrected(): the new running sum in registers (not stored)
+            auto corrected = [&](int s, int s2, const float (&qv)[8], uint32_t (&r8)[8]) {
+                const float *G = ggs + TcLayout::pair_index(GRP ? 8 : Nq, s, s2) * 72;
                 tmem_ld8(tq + TM_RUN + 8 * s2, r8);
                 float a[8];
 #pragma unroll
@@ -883,25 +900,58 @@ auto drain = [&](int g, uint32_t tq) {
                 tmem_wait_ld(r8);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) r8[c] = __float_as_uint(__fsub_rn(__uint_as_float(r8[c]), a[c]));
+            };
+            auto correct = [&](int s, int s2, const float (&qv)[8]) {
+                uint32_t r8[8];
+                corrected(s, s2, qv, r8);
                 tmem_st8(tq + TM_RUN + 8 * s2, r8);
             };
             // (the pipelined order pays where the stores are the critical path: config 2 with z_q_is 148.0 -> 145.8 us; without z_q_is
             // the frame threads are the critical path and it costs 2 %: 934 -> 955 us on the config-4 shape, so that variant keeps the
             // classic order: prep, barrier, scan, merge, all corrections)
-            if (PIPE && w < 4) prep(0);
+            // Without z_q_is (SPLIT) the frame threads are the critical path, so after the merge they only correct and normalise the NEXT
+            // stage (its score MMAs start right away) and hand the straight-through vector to warps 4-7 through shared memory, which
+            // apply the corrections of the later stages while the tensor core scores (they have nothing else to do until the first
+            // scores arrive).  Running sum x is touched by warps 4-7 in the stages <= x - 2 and by the frame threads in stage x - 1:
+            // ordered by the barrier after the scans (tcgen05 fences on both sides).
+            constexpr bool SPLIT = !ZQIS && !VRVQ_THIRD_SCAN_GROUP;
+            float4 *qsh = reinterpret_cast<float4 *>(smem + SM_SB + 4096);  // [2][128]: q of the stage just merged (SPLIT)
+            if ((PIPE || SPLIT) && w < 4) prep(0);
+            if constexpr (SPLIT) named_bar_sync(1, NSCAN);  // 2e / e2 of the first stage visible to every scan group
             for (int s = 0; s < nl; ++s) {  // s: stage within this pass, sg = s0 + s: stage of the model
                 const int sg = s0 + s;
-                if constexpr (!PIPE) {
+                if constexpr (!PIPE && !SPLIT) {
                     if (w < 4) prep(s);
                     named_bar_sync(1, NSCAN);  // 2e / e2 of the stage visible to every scan group
                 }
                 ph_mark(3);
+                if (PROFILE && tid == 0) strace(8, s, it == 0);
                 float bd_pub;
                 int bi_pub;
                 scan_stage(s, w >> 2, f, tq, bd_pub, bi_pub);
                 publish_best(s, w >> 2, f, bd_pub, bi_pub);
+                if constexpr (!ZQIS) {  // un-normalised codebook of the stage in shared memory (in flight since the previous merge); a
+                                        // completed wait still costs ~200 cycles: here, where the frame warps usually wait for warps 4-7
+                    if (w < 4) TC_WAIT(&bars[B_RAW_FULL], (gstage + (uint32_t)s) & 1u);
+                }
+                if constexpr (SPLIT) tmem_fence_before_sync();
                 named_bar_sync(1, NSCAN);
+                if constexpr (SPLIT) tmem_fence_after_sync();
                 ph_mark(4);
+                if (PROFILE && tid == 0) strace(12, s, it == 0);
+                if constexpr (SPLIT) {
+                    if (w >= 4) {
+                        named_bar_sync(2, NSCAN);  // q of stage s is in shared memory (2e / e2 of stage s + 1 reach these warps through the score barriers)
+                        if (PROFILE && tid == 128) strace(16, s, it == 0);
+                        if (s + 2 < nl) {
+                            const float4 qa = qsh[f], qb = qsh[128 + f];
+                            const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                            for (int s2 = s + 2; s2 < nl; ++s2) correct(s, s2, qv);
+                            tmem_wait_st();
+                        }
+                        if (PROFILE && tid == 128) strace(17, s, it == 0);
+                    }
+                }
                 if (w < 4) {
                     // ---- merge of the groups' results (first index on ties), gather, loss, straight-through (quantize.py:69-75,81-85,102) ----
                     const float *sbd = reinterpret_cast<const float *>(smem + SM_SB);
@@ -924,6 +974,10 @@ auto drain = [&](int g, uint32_t tq) {
                         const float4 *rowp = reinterpret_cast<const float4 *>(smem + SM_SB + 4096) + (bh * 128 + f) * 2;
                         ra = rowp[0];
                         rb = rowp[1];
+                    } else if constexpr (!ZQIS) {  // (an L2 round trip per stage on the critical path otherwise)
+                        const float4 *rawp = reinterpret_cast<const float4 *>(smem + SM_RAW) + (size_t)bi * 2;
+                        ra = rawp[0];
+                        rb = rawp[1];
                     } else {
                         const float4 *rawp = reinterpret_cast<const float4 *>(stages + (size_t)sg * L.stage_floats() + L.off_raw() + (size_t)bi * 8);
                         ra = __ldg(rawp);
@@ -938,12 +992,24 @@ auto drain = [&](int g, uint32_t tq) {
                         ls = (k == 0) ? sq : __fadd_rn(ls, sq);
                         qv[k] = __fadd_rn(zev[k], __fsub_rn(cr[k], zev[k]));
                     }
+                    if (PROFILE && tid == 0) strace(13, s, it == 0);
+                    if constexpr (SPLIT) {  // warps 4-7 start on the corrections of the stages after the next one
+                        qsh[f] = make_float4(qv[0], qv[1], qv[2], qv[3]);
+                        qsh[128 + f] = make_float4(qv[4], qv[5], qv[6], qv[7]);
+                        named_bar_arrive(2, NSCAN);
+                    }
                     // the next stage first: correct its running sum, normalise, hand 2e to the search-MMA issuer
+                    if (SPLIT && s + 1 < nl) {  // (nobody reads that running sum again: it goes from registers straight into the normalise)
+                        uint32_t r8[8];
+                        corrected(s, s + 1, qv, r8);
+                        prep_from(s + 1, r8);  // (overwrites zev: everything of stage s that needs z_e is done)
+                    }
                     if (PIPE && s + 1 < nl) {
                         correct(s, s + 1, qv);
                         tmem_wait_st();
-                        prep(s + 1);  // (overwrites zev: everything of stage s that needs z_e is done)
+                        prep(s + 1);
                     }
+                    if (PROFILE && tid == 0) strace(14, s, it == 0);
                     if (own) {
                         const float loss = __fdiv_rn(ls, 8.0f);
                         p.codes[(long long)b * p.codes_sb + (long long)sg * p.codes_sq + fr] = (long long)bi;
@@ -966,10 +1032,13 @@ auto drain = [&](int g, uint32_t tq) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars[B_A_READY + s]);
                     // corrections of the stages after the next one (in the shadow of the next stage's score MMAs)
-                    for (int s2 = s + (PIPE ? 2 : 1); s2 < nl; ++s2) correct(s, s2, qv);
-                    tmem_wait_st();
+                    if constexpr (!SPLIT) {
+                        for (int s2 = s + (PIPE ? 2 : 1); s2 < nl; ++s2) correct(s, s2, qv);
+                        tmem_wait_st();
+                    }
                 }
                 ph_mark(5);
+                if (PROFILE && tid == 0) strace(15, s, it == 0);
             }
             if (!GRP && w < 4) {
                 // ---- mask the A tiles for the final z_q GEMM (quantize.py:194 / :421) once every per-stage MMA has read them ----
@@ -1319,19 +1388,27 @@ auto drain = [&](int g, uint32_t tq) {
                 const uint64_t ae = desc128(smem_base + SM_ES);
                 for (int s = 0; s < nl; ++s) {
                     const uint32_t gs = gstage + (uint32_t)s;
-                    TC_WAIT(&bars[B_E_READY], gs & 1u);
+                    // (the codebook and the first score buffer are free long before the stage's 2e tile is: those waits -- ~170 cycles
+                    // each even when complete -- come first, so that only the fence stands between E_READY and the first MMA)
                     const uint32_t cbuse = (s & 1) ? (cbu1 + (uint32_t)(s >> 1)) : (cbu0 + (uint32_t)(s >> 1));
                     TC_WAIT(&bars[B_CB_FULL + (s & 1)], cbuse & 1u);
+                    {
+                        const uint32_t gc0 = gs * (uint32_t)NSC, use0 = gc0 / NSB;
+                        if (use0 >= 1) TC_WAIT(&bars[B_SB_EMPTY + gc0 % NSB], (use0 - 1) & 1u);
+                    }
+                    TC_WAIT(&bars[B_E_READY], gs & 1u);
+                    if (PROFILE && lane == 0) strace(21, s, it == 0);
                     fence_proxy_async();
                     const uint64_t cb = DESC_CB | (uint64_t)((smem_base + ((s & 1) ? SM_CB1 : SM_CB0)) >> 4);
                     for (int c = 0; c < NSC; ++c) {
                         const uint32_t gc = gs * (uint32_t)NSC + (uint32_t)c, sbuf = gc % NSB, use = gc / NSB;
-                        if (use >= 1) TC_WAIT(&bars[B_SB_EMPTY + sbuf], (use - 1) & 1u);
+                        if (c > 0 && use >= 1) TC_WAIT(&bars[B_SB_EMPTY + sbuf], (use - 1) & 1u);
                         tmem_fence_after_sync();
                         if (elect_one()) {
                             umma_tf32(tmem_u + TM_SC + (uint32_t)SCW * sbuf, ae, cb + (uint64_t)(c * (SCW * 16 >> 4)), ID_S, false);
                             umma_commit(&bars[B_SB_FULL + sbuf]);
                         }
+                        if (PROFILE && lane == 0 && (c == 0 || c == NSC - 1)) strace(c == 0 ? 22 : 23, s, it == 0);
                     }
                 }
             }
@@ -1364,6 +1441,10 @@ auto drain = [&](int g, uint32_t tq) {
                     mbar_arrive_expect_tx(&bars[B_CB_FULL + 1], 36864);
                     bulk_g2s(smem + SM_CB1, P.tc + TL.off_cbk() + (size_t)(s0 + 1) * 9216, 36864, &bars[B_CB_FULL + 1]);
                 }
+                if (!FC && !ZQIS) {  // un-normalised codebook of the pass's first stage (inside the phase-L region too)
+                    mbar_arrive_expect_tx(&bars[B_RAW_FULL], 32768);
+                    bulk_g2s(smem + SM_RAW, stages + (size_t)s0 * L.stage_floats() + L.off_raw(), 32768, &bars[B_RAW_FULL]);
+                }
                 // W_out ring of the per-stage out_proj: chunk (s, j), row-major; refills of the search codebooks interleaved
                 const float *wout = P.tc + TL.off_wout();
                 const float *bout = P.tc + TL.off_bout();
@@ -1387,6 +1468,10 @@ auto drain = [&](int g, uint32_t tq) {
                             mbar_arrive_expect_tx(&bars[B_CB_FULL + (cs & 1)], 36864);
                             bulk_g2s(smem + ((cs & 1) ? SM_CB1 : SM_CB0), P.tc + TL.off_cbk() + (size_t)(s0 + cs + 2) * 9216, 36864,
                                      &bars[B_CB_FULL + (cs & 1)]);
+                        }
+                        if (!ZQIS && !FC && cs + 1 < nl) {  // ... and with the un-normalised rows of stage cs (gathered in its merge)
+                            mbar_arrive_expect_tx(&bars[B_RAW_FULL], 32768);
+                            bulk_g2s(smem + SM_RAW, stages + (size_t)(s0 + cs + 1) * L.stage_floats() + L.off_raw(), 32768, &bars[B_RAW_FULL]);
                         }
                         ++cs;
                         progressed = true;
@@ -1622,6 +1707,21 @@ int encode_tc(const vrvq_encode_args *a, const EncodeParams &e, void *stream) {
                 fprintf(stderr, "  %2d:", c);
                 for (int e = 0; e < 8; ++e) { const long long v = h[1024 + 32 * e + c]; fprintf(stderr, " %7lld", v ? v - t0 : -1); }
                 fprintf(stderr, "\n");
+            }
+            {
+                static const char *sev[16] = {"top", "g0_scores", "g0_scanned", "g0_rescored", "g0_postbar", "g0_q", "g0_prepped", "g0_end",
+                                              "g1_q_seen", "g1_corrected", "g1_scores", "g1_scanned", "g1_rescored", "iss_e_ready", "iss_first", "iss_last"};
+                long long s0t = 0;
+                for (int e = 8; e < 24; ++e)
+                    for (int c = 0; c < 8; ++c) { const long long v = h[1024 + 32 * e + c]; if (v != 0 && (s0t == 0 || v < s0t)) s0t = v; }
+                fprintf(stderr, "[vrvq tc trace] block 0, first pass, stage time line (cycles since its first event); stage:");
+                for (int e = 0; e < 16; ++e) fprintf(stderr, " %s", sev[e]);
+                fprintf(stderr, "\n");
+                for (int c = 0; c < 8; ++c) {
+                    fprintf(stderr, "  %2d:", c);
+                    for (int e = 8; e < 24; ++e) { const long long v = h[1024 + 32 * e + c]; fprintf(stderr, " %7lld", v ? v - s0t : -1); }
+                    fprintf(stderr, "\n");
+                }
             }
             free(h);
             cudaFree(P.e.phase_cycles);
