@@ -49,6 +49,15 @@
 #endif
 #ifndef VRVQ_ROW_PREFETCH
 #define VRVQ_ROW_PREFETCH 0
+#ifndef VRVQ_SCAN_PROBE
+#define VRVQ_SCAN_PROBE 0     // probe the full barrier of the scan group's next score chunk one chunk ahead (test_wait): no gain, measured
+#endif
+#ifndef VRVQ_SCAN_PREFETCH_GRP
+#define VRVQ_SCAN_PREFETCH_GRP 0
+#endif
+#ifndef VRVQ_SCAN_PREFETCH
+#define VRVQ_SCAN_PREFETCH 1  // without z_q_is: issue the tcgen05.ld of the next 64-code piece before the candidate appends of the current one
+#endif
 #endif
 
 namespace vrvq {
@@ -456,24 +465,51 @@ auto drain = [&](int g, uint32_t tq) {
                     // score filter cannot rank them, so they are always re-scored exactly -- or, if there are many, everything is
                     const int *spc = reinterpret_cast<const int *>(P.tc + TL.off_spc()) + (s0 + s) * 16;
                     const int nsp = __ldg(spc);
-                    constexpr int NPIECE = (NSC + NSG - 1) / NSG * (SCW / 64);  // this group's score chunks (SCW codes each), in 64-code pieces
+                    constexpr int PPC = SCW / 64;                                // 64-code pieces per score chunk
+                    constexpr int NPIECE = (NSC + NSG - 1) / NSG * PPC;          // this group's score chunks (SCW codes each), in pieces
+                    // Software pipeline (without z_q_is, where the scans are the critical path: config-4 shape 760 -> 745 us; with z_q_is it
+                    // costs 1.5 %): the tcgen05.ld of piece pc + 1 are issued as soon as the group maxima of piece pc are in registers, so
+                    // their ~200 cycles pass under the candidate appends.  (Probing the full barrier of the next chunk one chunk ahead with a
+                    // non-blocking test_wait, VRVQ_SCAN_PROBE, changed nothing.)
+                    constexpr bool PREFETCH = VRVQ_SCAN_PREFETCH && !ZQIS && (!GRP || VRVQ_SCAN_PREFETCH_GRP);  // (the grouped instantiation spills with it: config 3 1165 -> 1216 us)
+                    uint32_t va[32], vb[32];
+                    bool nxt_ok = false;
+                    auto piece_addr = [&](int pc_, uint32_t &sbuf_, uint32_t &par_, bool &in_range) -> uint32_t {
+                        const int ck_ = NSG * (pc_ / PPC) + h, sub_ = pc_ % PPC;
+                        in_range = pc_ < NPIECE && !(NSC % NSG != 0 && ck_ >= NSC);
+                        const uint32_t gc_ = (gstage + (uint32_t)s) * (uint32_t)NSC + (uint32_t)ck_;
+                        sbuf_ = gc_ % NSB;
+                        par_ = (gc_ / NSB) & 1u;
+                        return tq + TM_SC + (uint32_t)SCW * sbuf_ + 64u * (uint32_t)sub_;
+                    };
+                    // acquire the chunk that piece pc_ starts (pc_ % PPC == 0), probe the one after it, then issue the piece's loads
+                    auto start_piece = [&](int pc_) {
+                        uint32_t sbuf_, par_;
+                        bool ok_;
+                        const uint32_t tsc_ = piece_addr(pc_, sbuf_, par_, ok_);
+                        if (!ok_) return;
+                        if (pc_ % PPC == 0) {
+                            if (!nxt_ok) TC_WAIT(&bars[B_SB_FULL + sbuf_], par_);
+                            tmem_fence_after_sync();
+                            uint32_t sbuf2, par2;
+                            bool ok2;
+                            piece_addr(pc_ + PPC, sbuf2, par2, ok2);
+                            if (VRVQ_SCAN_PROBE) nxt_ok = ok2 && mbar_test_wait(&bars[B_SB_FULL + sbuf2], par2);
+                        }
+                        tmem_ld32(tsc_, va);
+                        tmem_ld32(tsc_ + 32, vb);
+                    };
+                    start_piece(0);
+                    if (PROFILE && (tid & 127) == 0) strace(tid == 0 ? 9 : 18, s, it == 0);
                     for (int pc = 0; pc < NPIECE; ++pc) {
-                        const int ck = NSG * (pc / (SCW / 64)) + h, sub = pc % (SCW / 64);
+                        const int ck = NSG * (pc / PPC) + h, sub = pc % PPC;
                         if (NSC % NSG != 0 && ck >= NSC) break;
                         const uint32_t gc = (gstage + (uint32_t)s) * (uint32_t)NSC + (uint32_t)ck, sbuf = gc % NSB;
-                        const uint32_t tsc = tq + TM_SC + (uint32_t)SCW * sbuf + 64u * (uint32_t)sub;
-                        if (sub == 0) {
-                            TC_WAIT(&bars[B_SB_FULL + sbuf], (gc / NSB) & 1u);
-                            tmem_fence_after_sync();
-                            if (PROFILE && pc == 0 && (tid & 127) == 0) strace(tid == 0 ? 9 : 18, s, it == 0);
-                        }
                         ph_mark(8);
-                        uint32_t va[32], vb[32];
-                        tmem_ld32(tsc, va);
-                        tmem_ld32(tsc + 32, vb);
+                        if (!PREFETCH && pc > 0) start_piece(pc);
                         tmem_wait_ld32(va);
                         tmem_wait_ld32(vb);
-                        if (sub == SCW / 64 - 1) {
+                        if (sub == PPC - 1) {
                             tmem_fence_before_sync();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&bars[B_SB_EMPTY + sbuf]);
@@ -496,7 +532,9 @@ auto drain = [&](int g, uint32_t tq) {
                         asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(g[0]), "f"(g[1]), "f"(g[2]));
                         asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(cm), "f"(g[3]), "f"(g[4]));
                         asm("max.f32 %0, %1, %2, %3;" : "=f"(cm) : "f"(cm), "f"(g[5]), "f"(g[6]));
-                        runmax = fmaxf(runmax, fmaxf(cm, g[7]));
+                        cm = fmaxf(cm, g[7]);
+                        if (PREFETCH) start_piece(pc + 1);  // (va / vb are dead from here on: g[] holds all that the appends need)
+                        runmax = fmaxf(runmax, cm);
                         const float thr = runmax - SEARCH_MARGIN;
                         const uint32_t gid0 = (uint32_t)(ck * (SCW / 8) + sub * 8);  // group id = code / 8
                         // branch-free append of every group whose maximum is within the margin: entry = (max & ~0xff) | group id
@@ -847,6 +885,7 @@ auto drain = [&](int g, uint32_t tq) {
             } else {
             // ---- phase S ----
             float zev[8];  // frame threads: z_e of the current stage
+            float4 *zsh = reinterpret_cast<float4 *>(smem + SM_SB + 8192);  // [2][128]: its home during the scan (without z_q_is)
             // bias, latents, normalise (quantize.py:66,92 in torch's op order) of stage s: frame threads.  Runs one stage ahead of the
             // searches: right after stage s - 1 has corrected the running sum of stage s (below), so the score MMAs of stage s
             // start while the corrections of the later stages are still being applied.
@@ -868,6 +907,10 @@ auto drain = [&](int g, uint32_t tq) {
                     es[(k >> 2) * 512 + f * 4 + (k & 3)] = __fmul_rn(2.0f, ec);
                 }
                 e2s[f] = e2;
+                if constexpr (!ZQIS) {  // z_e waits for the merge in shared memory: 8 registers fewer across the scan
+                    zsh[f] = make_float4(zev[0], zev[1], zev[2], zev[3]);
+                    zsh[128 + f] = make_float4(zev[4], zev[5], zev[6], zev[7]);
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[B_E_READY]);  // the search-MMA issuer may start on this stage
                 if (p.latents != nullptr && own) {
@@ -957,6 +1000,11 @@ auto drain = [&](int g, uint32_t tq) {
                     const float *sbd = reinterpret_cast<const float *>(smem + SM_SB);
                     const int *sbi = reinterpret_cast<const int *>(smem + SM_SB + 2048);
                     float best = sbd[f];
+                    if constexpr (!ZQIS) {
+                        const float4 za = zsh[f], zb = zsh[128 + f];
+                        zev[0] = za.x; zev[1] = za.y; zev[2] = za.z; zev[3] = za.w;
+                        zev[4] = zb.x; zev[5] = zb.y; zev[6] = zb.z; zev[7] = zb.w;
+                    }
                     int bi = sbi[f], bh = 0;
 #pragma unroll
                     for (int h2 = 1; h2 < NSG; ++h2) {
