@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
     };
 
     double loss_acc = 0.0;               // frame threads
-    unsigned long long kept_acc = 0ull;  // lane k of warps 0-3 counts stage k
+    unsigned long long kept_acc = 0ull;  // lane k of warps 8-11 counts stage k
     uint32_t wn = 0, fn = 0, dn = 0;     // W_out ring / final ring step counters, out_proj unit counter
     uint32_t cbu0 = 0, cbu1 = 0;         // uses of the two codebook buffers
 
@@ -646,26 +646,6 @@ auto drain = [&](int g, uint32_t tq) {
             const bool inb = fr >= 0 && (f < 8 || f - 8 < fv);  // rows that hold a real frame (halo rows of the first tile do not)
             const uint32_t tq = tmem + ((uint32_t)(32 * (w & 3)) << 16);  // this warp's lane quarter
             if constexpr (!FC) {
-            if (w < 4 && first_grp) {
-                // ---- keep counts, mask, kept-frame counts (quantize.py:389, utils.py:59-60) ----
-                int nk = 0;
-                if (own) {
-                    if (p.imp != nullptr) {
-                        const float lv = p.level_dev ? p.level_dev[(long long)b * p.level_stride] : p.level_host;
-                        const float x = __fmul_rn(__fmul_rn(p.imp[(long long)b * p.imp_sb + fr], lv), (float)Nq);
-                        for (int k = 0; k < n_run; ++k) nk += (__fsub_rn(x, (float)k) >= 0.0f) ? 1 : 0;
-                    } else {
-                        nk = n_run;
-                    }
-                }
-                nkeep[f] = nk;
-                for (int k = 0; k < n_run; ++k) {
-                    const bool on = nk > k;
-                    const unsigned bal = __ballot_sync(0xffffffffu, on);
-                    if (lane == k) kept_acc += (unsigned long long)__popc(bal);
-                    if (p.mask != nullptr && own) p.mask[(long long)b * p.mask_sb + (long long)k * p.mask_sq + fr] = on ? 1.0f : 0.0f;
-                }
-            }
             ph_mark(0);
             // ---- phase L: load, split, stage (256 threads: frame f, half q of each 32-channel chunk) ----
             if (P.zmode != ZMODE_LDG) {
@@ -1162,6 +1142,31 @@ auto drain = [&](int g, uint32_t tq) {
             // =====================================================================================================
             // Epilogue warps: TMEM -> global.  Lane quarter q4 = w - 8, frame f = 32*q4 + lane.
             // =====================================================================================================
+            if constexpr (!FC) {
+                if (first_grp) {
+                    // ---- keep counts, mask, kept-frame counts (quantize.py:389, utils.py:59-60): by these warps, which only have a drain
+                    // every fourth chunk to do in phase L -- on the loader warps it delayed the first chunk of every tile by ~4k cycles ----
+                    const int f = tid & 127, fr = t0 - 8 + f;  // tile row, its frame
+                    const bool own = f >= 8 && f - 8 < fv;
+                    int nk = 0;
+                    if (own) {
+                        if (p.imp != nullptr) {
+                            const float lv = p.level_dev ? p.level_dev[(long long)b * p.level_stride] : p.level_host;
+                            const float x = __fmul_rn(__fmul_rn(p.imp[(long long)b * p.imp_sb + fr], lv), (float)Nq);
+                            for (int k = 0; k < n_run; ++k) nk += (__fsub_rn(x, (float)k) >= 0.0f) ? 1 : 0;
+                        } else {
+                            nk = n_run;
+                        }
+                    }
+                    nkeep[f] = nk;  // (read by the frame threads after the L -> S barrier)
+                    for (int k = 0; k < n_run; ++k) {
+                        const bool on = nk > k;
+                        const unsigned bal = __ballot_sync(0xffffffffu, on);
+                        if (lane == k) kept_acc += (unsigned long long)__popc(bal);
+                        if (p.mask != nullptr && own) p.mask[(long long)b * p.mask_sb + (long long)k * p.mask_sq + fr] = on ? 1.0f : 0.0f;
+                    }
+                }
+            }
             if constexpr (!FC)
                 for (int g = 0; g < NCT / 4; ++g) drain(g, tmem + ((uint32_t)(32 * (w - 8)) << 16));
             tmem_fence_before_sync();
@@ -1593,8 +1598,8 @@ auto drain = [&](int g, uint32_t tq) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
         if (lane == 0 && p.loss_sum != nullptr && loss_acc != 0.0) atomicAdd(p.loss_sum, loss_acc);
-        if (lane < n_run && p.kept != nullptr && kept_acc != 0ull) atomicAdd(&p.kept[lane], kept_acc);
     }
+    if (w >= 8 && w < 12 && lane < n_run && p.kept != nullptr && kept_acc != 0ull) atomicAdd(&p.kept[lane], kept_acc);
     if (w == 12) tmem_dealloc(tmem, TM_COLS);
 }
 
