@@ -73,6 +73,18 @@ class DAC_VRVQ(nn.Module):
             return self.quantizer(z=z, n_quantizers=n_quantizers)
         return self.quantizer(z=z, n_quantizers=n_quantizers, feat_enc=feat, level=level)
 
+    def compress(self, audio_path_or_signal, win_duration: float = 1.0, verbose: bool = False, normalize_db: float = -16,
+                 n_quantizers: int = None):
+        """models/dac_base.py:129-169: the reference's chunked `compress` raises NotImplementedError on its first line ("TODO: Implement
+        this function"; everything below it is unreachable and needs audiotools).  Same signature, same behaviour.  The working
+        container path of this package is encode() -> wire.pack_codes -> wire.DACFile (vrvq_b200/wire.py)."""
+        raise NotImplementedError
+
+    def decompress(self, obj, verbose: bool = False):
+        """models/dac_base.py:242-261: raises NotImplementedError in the reference as well; wire.unpack_codes + quantizer.from_codes
+        (+ from_codes_masked for VBR) is the decode-side path built here."""
+        raise NotImplementedError
+
     def decode(self, z):
         raise NotImplementedError("the DAC decoder is outside the accelerated encode path (DESIGN.md, out of scope)")
 
