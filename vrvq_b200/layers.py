@@ -101,8 +101,10 @@ class Encoder(nn.Module):
 class ImportanceSubnet(nn.Module):
     """Importance map producer (models/importance_subnet.py:6-45): 6 x (Snake, k=3 conv) + sigmoid -> [B,1,T].
 
-    Eval forward on a CUDA fp32 tensor runs the fused Snake+conv kernels of csrc/subnet.cu (SURVEY.md section 8(f) row 3,
-    six launches, no PyTorch op in between); there is no fallback on that path -- a missing libvrvq.so raises.
+    Eval forward on a CUDA fp32 tensor runs this package's kernels (no PyTorch op in between, five
+    launches for the shipped 1024-wide net): a Snake pre-pass, the three wide blocks as tcgen05 3xTF32 implicit GEMMs
+    and the tail 128 -> 32 -> 8 -> 1 + sigmoid in one launch (all csrc/subnet_tc.cu); the generic fp32 block of csrc/subnet.cu
+    serves every other shape.  There is no fallback on that path -- a missing libvrvq.so raises.
     The differentiable PyTorch formulation (`forward_torch`) serves training, which is outside this package's scope."""
 
     def __init__(self, d_input, d_feat, intermediate_channels=(512, 128, 32, 8), out_channels=1, detach_input=False):
