@@ -24,14 +24,16 @@ def run_cases(seed, n_cases, verbose=True):
   worst = 0.0
   for it in range(n_cases):
       D = random.choice([1024, 1024, 512, 256])
-      Nq = random.choice([8, 8, 8, 5, 3, 1])
+      Nq = random.choice([8, 8, 8, 5, 3, 1, 9, 12, 28])  # > 8: the grouped instantiation (no z_q_is)
       n_run = Nq if random.random() < 0.7 else random.randint(1, Nq)
       B = random.choice([1, 2, 3, 7, 16, 33])
       T = random.choice([1, 7, 8, 9, 95, 96, 97, 120, 121, 431, 862, 1000, 2049])
       if B * T * D > 40e6:
           B = max(1, int(40e6 // (T * D)))
       vbr = random.random() < 0.6 and n_run == Nq
-      zqis = random.random() < 0.5
+      zqis = random.random() < 0.5 and Nq <= 8
+      if Nq > 8 and B * T > 20000:
+          B = max(1, 20000 // T)
       pw = get_w(D, Nq)
       z = torch.randn(B, D, T, device="cuda")
       imp = torch.rand(B, 1, T, device="cuda") if vbr else None
