@@ -108,7 +108,7 @@ static_assert(SM_ZR % 128 == 0 && Z_SLOT % 128 == 0, "TMA destinations are 128-b
 enum {
     B_L_FULL = 0, B_L_EMPTY = 4, B_SET_FULL = 24, B_SET_EMPTY = 26, B_W_FULL = 28, B_W_EMPTY = 32,
     B_D_FULL = 36, B_D_EMPTY = 38, B_CB_FULL = 40, B_A_READY = 42, B_ZQ_READY = 50, B_MMA_DONE = 51, B_F_FULL = 52, B_F_EMPTY = 56,
-    B_E_READY = 60, B_L_FULL2 = 73, B_WL_FULL = 76, B_WL_EMPTY = 80, B_Z_FULL = 84, B_Z_EMPTY = 89, B_SB_FULL = 94, B_SB_EMPTY = 100, B_RAW_FULL = 106, B_COUNT = 107
+    B_E_READY = 60, B_L_FULL2 = 73, B_WL_FULL = 76, B_WL_EMPTY = 80, B_Z_FULL = 84, B_Z_EMPTY = 89, B_SB_FULL = 94, B_SB_EMPTY = 100, B_RAW_FULL = 106, B_D4_FULL = 107, B_D4_EMPTY = 111, B_COUNT = 115
 };
 enum { ZMODE_LDG = 0, ZMODE_BULK = 1, ZMODE_TMA = 2 };  // how phase L fetches the latent
 
@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         mbar_init(&bars[B_MMA_DONE], 1);
         for (int i = 0; i < F_SLOTS; ++i) { mbar_init(&bars[B_F_FULL + i], 1); mbar_init(&bars[B_F_EMPTY + i], 1); }
         mbar_init(&bars[B_E_READY], 4);
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars[B_D4_FULL + i], 1); mbar_init(&bars[B_D4_EMPTY + i], 4); }  // grouped final GEMM: four accumulators
         mbar_init(&bars[B_RAW_FULL], 1);  // un-normalised codebook of the stage (without z_q_is): the producer's expect_tx + 32 KB
         for (int i = 0; i < 6; ++i) { mbar_init(&bars[B_SB_FULL + i], 1); mbar_init(&bars[B_SB_EMPTY + i], 4); }
         // latent staging slot: filled by the producer's expect_tx + the TMA bytes, released by the 8 loader warps
@@ -355,6 +356,11 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         };
         const int n_stage_steps = ZQIS ? n_run * NJ : 0;
         const int G_NST = (n_run + G_FI - 1) / G_FI + 1;  // grouped final GEMM: ring steps per 128-channel chunk (stages in fours, then the bias)
+        // grouped final GEMM: the A tiles (regenerated from the codes) do not depend on the channel chunk, so they are staged once per
+        // QD = 4 chunks, whose products accumulate in four TMEM buffers (columns 0-511: nothing else is live by then) -- staging them
+        // per chunk (8 x 8 steps of L2 gathers per tile) made the final phase 107k cycles per tile for 44k of tensor work
+        constexpr int QD = NJ < 4 ? NJ : 4;
+        const int n_astage_steps = (p.z_q == nullptr || !last_grp || !GRP) ? 0 : (NJ / QD) * G_NST;
         const int n_final_steps = (p.z_q == nullptr || !last_grp) ? 0 : GRP ? NJ * G_NST : NJ * ((n_run + F_ITEMS) / F_ITEMS);  // !GRP: ceil((n_run + 1) / F_ITEMS) per chunk
         if constexpr (GRP) {
             // this group's correction matrices (pairs j < s inside the group, local pair order) and biases (cross-group terms folded in)
@@ -1095,7 +1101,7 @@ auto drain = [&](int g, uint32_t tq) {
                     const int hsel = w >> 2;
                     named_bar_sync(1, NSCAN);  // the code of the last stage (written by the frame threads in its merge) is visible to warps 4-7
                     uint32_t m = astep;
-                    for (int j = 0; j < NJ; ++j)
+                    for (int jh = 0; jh < NJ / QD; ++jh)
                         for (int st = 0; st < G_NST; ++st, ++m) {
                             const uint32_t sa = m & 1u, use = m >> 1;
                             if (use >= 1) TC_WAIT(&bars[B_W_EMPTY + sa], (use - 1) & 1u);
@@ -1190,11 +1196,12 @@ auto drain = [&](int g, uint32_t tq) {
             // t0 - 8 + delta_p + r.  The tile owns, per class, the frames [t0 - 8 + delta_p, t0 + adv - 8 + delta_p) (the last tile of
             // an item up to T), so consecutive tiles cover every row exactly once and every 32-lane store starts on a sector.
             auto unit = [&](float *row0, long long rstride, uint32_t shifts) {  // row0 = (row 128j, frame 0) of the output
-                const uint32_t buf = dn & 1u;
-                TC_WAIT(&bars[B_D_FULL + buf], (dn >> 1) & 1u);
+                // (grouped: QD accumulators at columns 128 k, filled together -- see the issuer)
+                const uint32_t buf = GRP ? dn % QD : (dn & 1u);
+                TC_WAIT(&bars[(GRP ? B_D4_FULL : B_D_FULL) + buf], (GRP ? dn / QD : (dn >> 1)) & 1u);
                 tmem_fence_after_sync();
                 ph_mark(1);
-                const uint32_t tcol = tq + TM_SET + 128u * buf;
+                const uint32_t tcol = tq + (GRP ? 0u : TM_SET) + 128u * buf;
                 const uint32_t stepb = (uint32_t)(16 * rstride);  // bytes between channels 4 apart (row pitch < 2^28 floats: checked on the host)
                 uint32_t va[32], vb[32];
                 auto put = [&](const uint32_t (&v)[32], int piece) {
@@ -1225,7 +1232,7 @@ auto drain = [&](int g, uint32_t tq) {
                 tmem_wait_ld32(vb);
                 tmem_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[B_D_EMPTY + buf]);  // the MMA thread may refill this buffer
+                if (lane == 0) mbar_arrive(&bars[(GRP ? B_D4_EMPTY : B_D_EMPTY) + buf]);  // the MMA thread may refill this buffer
                 put(vb, 3);
                 ++dn;
                 ph_mark(2);
@@ -1312,40 +1319,49 @@ auto drain = [&](int g, uint32_t tq) {
                 }
                 if (elect_one()) umma_commit(&bars[B_MMA_DONE]);
                 if (GRP && p.z_q != nullptr && last_grp) {
-                    // grouped final GEMM: A tiles from the staging ring (search warps), W_out / bias tiles from the final ring
+                    // grouped final GEMM: A tiles from the staging ring (search warps; one staging step serves QD channel chunks), W_out /
+                    // bias tiles from the final ring (one ring step per (staging step, chunk)), QD accumulators at TMEM columns 128 k
                     uint32_t fstep = fn, am_ = astep;
-                    for (int j = 0; j < NJ; ++j) {
-                        const uint32_t buf = wait_dbuf();
-                        const uint32_t d = tmem_u + TM_SET + 128u * buf;
-                        for (int st = 0; st < G_NST; ++st, ++am_, ++fstep) {
-                            const uint32_t sa = am_ & 1u, slot = fstep % F_SLOTS;
+                    for (int jh = 0; jh < NJ / QD; ++jh) {
+                        for (int k = 0; k < QD; ++k) {  // the accumulators of the previous QD chunks are in the epilogue's registers
+                            const uint32_t u = dn + (uint32_t)k, use = u / QD;
+                            if (use >= 1) TC_WAIT(&bars[B_D4_EMPTY + u % QD], (use - 1) & 1u);
+                        }
+                        tmem_fence_after_sync();
+                        for (int st = 0; st < G_NST; ++st, ++am_) {
+                            const uint32_t sa = am_ & 1u;
                             TC_WAIT(&bars[B_W_FULL + sa], (am_ >> 1) & 1u);
-                            TC_WAIT(&bars[B_F_FULL + slot], (fstep / F_SLOTS) & 1u);
                             fence_proxy_async();
-                            tmem_fence_after_sync();
-                            const uint32_t abase = smem_base + SM_AT + sa * G_ASLOT, wbase = smem_base + SM_WO + slot * F_SLOT;
-                            if (elect_one()) {
-                            if (st < G_NST - 1) {
-                                for (int i = 0; i < G_FI && G_FI * st + i < n_run; ++i) {
-                                    const uint64_t ah = desc128(abase + i * 8192) + 8, al = ah + (4096 >> 4);  // + 8 rows: skip the halo
-                                    const uint64_t wb = desc128(wbase + i * 8192);
-                                    umma_tf32(d, al, wb, ID_128, st > 0 || i > 0);
-                                    umma_tf32(d, ah, wb + (4096 >> 4), ID_128, true);
-                                    umma_tf32(d, ah, wb, ID_128, true);
+                            const uint32_t abase = smem_base + SM_AT + sa * G_ASLOT;
+                            for (int k = 0; k < QD; ++k, ++fstep) {
+                                const uint32_t slot = fstep % F_SLOTS;
+                                TC_WAIT(&bars[B_F_FULL + slot], (fstep / F_SLOTS) & 1u);
+                                tmem_fence_after_sync();
+                                const uint32_t wbase = smem_base + SM_WO + slot * F_SLOT;
+                                const uint32_t d = tmem_u + 128u * ((dn + (uint32_t)k) % QD);
+                                if (elect_one()) {
+                                    if (st < G_NST - 1) {
+                                        for (int i = 0; i < G_FI && G_FI * st + i < n_run; ++i) {
+                                            const uint64_t ah = desc128(abase + i * 8192) + 8, al = ah + (4096 >> 4);  // + 8 rows: skip the halo
+                                            const uint64_t wb = desc128(wbase + i * 8192);
+                                            umma_tf32(d, al, wb, ID_128, st > 0 || i > 0);
+                                            umma_tf32(d, ah, wb + (4096 >> 4), ID_128, true);
+                                            umma_tf32(d, ah, wb, ID_128, true);
+                                        }
+                                    } else {
+                                        for (int i = 0; i < n_grp; ++i) {  // + sum_s mask_s b_out[s], eight stages per mask tile
+                                            const uint64_t am = desc128(abase + i * 4096) + 8, wb = desc128(wbase + i * 8192);
+                                            umma_tf32(d, am, wb + (4096 >> 4), ID_128, true);
+                                            umma_tf32(d, am, wb, ID_128, true);
+                                        }
+                                    }
+                                    umma_commit(&bars[B_F_EMPTY + slot]);
+                                    if (k == QD - 1) umma_commit(&bars[B_W_EMPTY + sa]);
+                                    if (st == G_NST - 1) umma_commit(&bars[B_D4_FULL + (dn + (uint32_t)k) % QD]);
                                 }
-                            } else {
-                                for (int i = 0; i < n_grp; ++i) {  // + sum_s mask_s b_out[s], eight stages per mask tile
-                                    const uint64_t am = desc128(abase + i * 4096) + 8, wb = desc128(wbase + i * 8192);
-                                    umma_tf32(d, am, wb + (4096 >> 4), ID_128, true);
-                                    umma_tf32(d, am, wb, ID_128, true);
-                                }
-                            }
-                            umma_commit(&bars[B_W_EMPTY + sa]);
-                            umma_commit(&bars[B_F_EMPTY + slot]);
                             }
                         }
-                        if (elect_one()) umma_commit(&bars[B_D_FULL + buf]);
-                        ++dn;
+                        dn += QD;
                     }
                 }
                 if (!GRP && p.z_q != nullptr) {
@@ -1537,8 +1553,8 @@ auto drain = [&](int g, uint32_t tq) {
                 if (GRP && n_final_steps > 0) {  // grouped: four stages per step (W_out hi | lo tiles), last step = the groups' bias tiles
                     TC_WAIT(&bars[B_MMA_DONE], tpar);
                     uint32_t m = fn;
-                    for (int j = 0; j < NJ; ++j)
-                        for (int st = 0; st < G_NST; ++st, ++m) {
+                    for (int jq = 0; jq < (NJ / QD) * G_NST * QD; ++jq, ++m) {  // order of the issuer: (chunk quad, staging step, chunk of the quad)
+                            const int st = (jq / QD) % G_NST, j = (jq / (QD * G_NST)) * QD + jq % QD;
                             const uint32_t slot = m % F_SLOTS, use = m / F_SLOTS;
                             if (use >= 1) TC_WAIT(&bars[B_F_EMPTY + slot], (use - 1) & 1u);
                             const int cnt = st < G_NST - 1 ? min(G_FI, n_run - G_FI * st) : n_grp;
@@ -1570,7 +1586,7 @@ auto drain = [&](int g, uint32_t tq) {
         }
         wn += (uint32_t)n_stage_steps;
         fn += (uint32_t)n_final_steps;
-        if (GRP) astep += (uint32_t)n_final_steps;
+        if (GRP) astep += (uint32_t)n_astage_steps;
         gstage += (uint32_t)nl;
         cbu0 += (uint32_t)((nl + 1) >> 1);  // buffer 0 serves the even stages, buffer 1 the odd ones
         cbu1 += (uint32_t)(nl >> 1);
