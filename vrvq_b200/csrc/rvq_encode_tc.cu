@@ -5,7 +5,7 @@
 // pre-normalisation latents of ALL stages are one skinny GEMM of the input plus 8x8 corrections:
 //     z_e[s] = W_in[s] (z - sum_{j<s} (W_out[j] q_j + b_out[j])) + b_in[s]
 //            = (W_in[s] z + b_in[s]) - sum_{j<s} (G[s][j] q_j + g[s][j]),   G[s][j] = W_in[s] W_out[j],  g = W_in[s] b_out[j]
-// so the residual never exists.  One CTA owns a tile of up to 120 consecutive frames of one batch item plus the 8 frames
+// so the residual never exists.  One CTA owns a tile of up to 120 consecutive frames of one batch item (128 without z_q_is, which needs no halo) plus the 8 frames
 // before it (halo); tile row r = TMEM lane r = MMA row r <-> frame t0 - 8 + r.
 //   phase L  warps 0-7 load the tile (lane = frame), split every value into a TF32 head and an exact fp32 remainder and write
 //            both straight into tensor memory as the A operand; tcgen05.mma kind::tf32 (A in TMEM, W_in chunks in shared
@@ -206,7 +206,10 @@ __device__ __forceinline__ uint32_t base_mod8(const float *ptr, long long off) {
 template <int D, bool ZQIS, bool PROFILE, bool FC, bool GRP = false>
 __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P, const __grid_constant__ ZMaps zmaps) {
     static_assert(!GRP || (!ZQIS && !FC && !PROFILE), "the grouped instantiation has no z_q_is, from_codes or profiling variant");
-    constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;  // 32-channel chunks, accumulator drained every 4 chunks
+    constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;
+    // rows of a tile in front of its own frames: the 8-frame halo exists for the shifted, sector-aligned stores of z_q_is; without them a
+    // tile is 128 own frames (config-4 shard: 41 instead of 44 tiles per item = 9 waves instead of 10)
+    constexpr int HALO = ZQIS ? 8 : 0;  // 32-channel chunks, accumulator drained every 4 chunks
     // search-score chunks: 64 codes per MMA into 3 x 64 TMEM columns; without z_q_is the out_proj ring is idle during the
     // searches, so the scores take 3 x 128 columns from TM_SET on and half as many (170-cycle) barrier hand-overs
     // (third scan group: 64-code chunks in six buffers, so that each of the three groups has two of its own in flight)
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         const int fv = min(P.adv, p.T - t0);  // frames this tile owns: tile rows 8 .. 8+fv-1 (rows 0-7: halo = the previous 8 frames)
         const bool last_tile = (tile % P.tiles_per_b) == P.tiles_per_b - 1;
         // latent staging geometry of this tile (ZMODE_BULK / ZMODE_TMA): smem column of frame fr in a staged row = fr - tstart + shift(row)
-        const int tstart = P.zmode == ZMODE_TMA ? t0 - 8 : max(t0 - 8, 0);
+        const int tstart = P.zmode == ZMODE_TMA ? t0 - HALO : max(t0 - HALO, 0);
         const uint32_t tpar = (uint32_t)it & 1u;  // phase parity of the once-per-pass barriers
         // A_READY[s] completes one phase per pass that HAS a stage s (the last group of a tile may be shorter): its phase index
         auto apar = [&](int s) -> uint32_t {
@@ -647,9 +650,9 @@ auto drain = [&](int g, uint32_t tq) {
             // Search group.  Frame threads (warps 0-3): f = tid = TMEM lane.
             // =====================================================================================================
             const int f = tid & 127;            // tile row = TMEM lane
-            const int fr = t0 - 8 + f;          // its frame
-            const bool own = f >= 8 && f - 8 < fv;              // frames whose per-frame outputs this tile writes
-            const bool inb = fr >= 0 && (f < 8 || f - 8 < fv);  // rows that hold a real frame (halo rows of the first tile do not)
+            const int fr = t0 - HALO + f;       // its frame
+            const bool own = f >= HALO && f - HALO < fv;        // frames whose per-frame outputs this tile writes
+            const bool inb = fr >= 0 && (f < HALO || f - HALO < fv);  // rows that hold a real frame (halo rows of the first tile do not)
             const uint32_t tq = tmem + ((uint32_t)(32 * (w & 3)) << 16);  // this warp's lane quarter
             if constexpr (!FC) {
             ph_mark(0);
@@ -814,7 +817,7 @@ auto drain = [&](int g, uint32_t tq) {
 
             if constexpr (FC) {
                 if (w < 4) {
-                    const bool rowok = fr >= 0 && fr < p.T && f < 8 + fv;  // the row holds a real frame (own or halo)
+                    const bool rowok = fr >= 0 && fr < p.T && f < HALO + fv;  // the row holds a real frame (own or halo)
                     for (int s = 0; s < n_run; ++s) {
                         long long code = rowok ? P.codes_in[(long long)b * P.cin_sb + (long long)s * P.cin_sq + fr] : 0;
                         if (code < 0 || code >= TCK) {  // F.embedding raises on such an index (quantize.py:82): report it
@@ -1152,8 +1155,8 @@ auto drain = [&](int g, uint32_t tq) {
                 if (first_grp) {
                     // ---- keep counts, mask, kept-frame counts (quantize.py:389, utils.py:59-60): by these warps, which only have a drain
                     // every fourth chunk to do in phase L -- on the loader warps it delayed the first chunk of every tile by ~4k cycles ----
-                    const int f = tid & 127, fr = t0 - 8 + f;  // tile row, its frame
-                    const bool own = f >= 8 && f - 8 < fv;
+                    const int f = tid & 127, fr = t0 - HALO + f;  // tile row, its frame
+                    const bool own = f >= HALO && f - HALO < fv;
                     int nk = 0;
                     if (own) {
                         if (p.imp != nullptr) {
@@ -1206,7 +1209,7 @@ auto drain = [&](int g, uint32_t tq) {
                 uint32_t va[32], vb[32];
                 auto put = [&](const uint32_t (&v)[32], int piece) {
                     const int dl = (int)((shifts >> (8 * piece)) & 0xffu);
-                    const int frame = t0 - 8 + dl + r;
+                    const int frame = t0 - HALO + dl + r;
                     const bool ok = frame >= 0 && (last_tile ? frame < p.T : r < P.adv);
                     if (ok) {
                         const unsigned long long o = reinterpret_cast<unsigned long long>(row0 + (long long)piece * rstride + frame);
@@ -1246,7 +1249,7 @@ auto drain = [&](int g, uint32_t tq) {
             }
             if (p.z_q != nullptr && last_grp) {  // the final GEMM uses delta = 8 for every class: lane r <-> frame t0 + r
                 float *outp = p.z_q + (long long)b * p.zq_sb;
-                for (int j = 0; j < NJ; ++j) unit(outp + (long long)(128 * j) * p.zq_sd, p.zq_sd, 0x08080808u);
+                for (int j = 0; j < NJ; ++j) unit(outp + (long long)(128 * j) * p.zq_sd, p.zq_sd, (uint32_t)HALO * 0x01010101u);
             }
         } else if (w == 12) {
             // =====================================================================================================
@@ -1342,7 +1345,7 @@ auto drain = [&](int g, uint32_t tq) {
                                 if (elect_one()) {
                                     if (st < G_NST - 1) {
                                         for (int i = 0; i < G_FI && G_FI * st + i < n_run; ++i) {
-                                            const uint64_t ah = desc128(abase + i * 8192) + 8, al = ah + (4096 >> 4);  // + 8 rows: skip the halo
+                                            const uint64_t ah = desc128(abase + i * 8192) + HALO, al = ah + (4096 >> 4);  // + HALO rows: skip the halo
                                             const uint64_t wb = desc128(wbase + i * 8192);
                                             umma_tf32(d, al, wb, ID_128, st > 0 || i > 0);
                                             umma_tf32(d, ah, wb + (4096 >> 4), ID_128, true);
@@ -1350,7 +1353,7 @@ auto drain = [&](int g, uint32_t tq) {
                                         }
                                     } else {
                                         for (int i = 0; i < n_grp; ++i) {  // + sum_s mask_s b_out[s], eight stages per mask tile
-                                            const uint64_t am = desc128(abase + i * 4096) + 8, wb = desc128(wbase + i * 8192);
+                                            const uint64_t am = desc128(abase + i * 4096) + HALO, wb = desc128(wbase + i * 8192);
                                             umma_tf32(d, am, wb + (4096 >> 4), ID_128, true);
                                             umma_tf32(d, am, wb, ID_128, true);
                                         }
@@ -1369,7 +1372,7 @@ auto drain = [&](int g, uint32_t tq) {
                     fence_proxy_async();
                     tmem_fence_after_sync();
                     ph_mark(4);
-                    const uint64_t am = desc128(smem_base + SM_AM) + 8;
+                    const uint64_t am = desc128(smem_base + SM_AM) + HALO;
                     uint32_t fstep = fn;
                     for (int j = 0; j < NJ; ++j) {
                         const uint32_t buf = wait_dbuf();
@@ -1383,7 +1386,7 @@ auto drain = [&](int g, uint32_t tq) {
                             for (int s = s0; s < s1; ++s) {
                                 const uint64_t wb = desc128(smem_base + SM_WO + slot * F_SLOT + (s - s0) * 8192);
                                 if (s < n_run) {
-                                    const uint64_t ah = desc128(smem_base + SM_AT + s * 8192) + 8, al = ah + (4096 >> 4);  // + 8 rows: skip the halo
+                                    const uint64_t ah = desc128(smem_base + SM_AT + s * 8192) + HALO, al = ah + (4096 >> 4);  // + HALO rows: skip the halo
                                     umma_tf32(d, al, wb, ID_128, s > 0);
                                     umma_tf32(d, ah, wb + (4096 >> 4), ID_128, true);
                                     umma_tf32(d, ah, wb, ID_128, true);
@@ -1625,13 +1628,14 @@ static int pick_tiling(int B, int T, int sms, bool zqis, int *adv, int *tiles_pe
     // With z_q_is a tile's time is its stores, proportional to its frames (+ a fixed part: pipeline fill, first search); without,
     // it is the in_proj stream and the serial stage chain, the same for any number of frames (measured: 85.9 us per wave at 104,
     // 112 and 120 frames on the config-4 shape), so the fewest waves win and the frame count only breaks ties.
-    const int nt_min = (T + 119) / 120;
+    const int amax = zqis ? 120 : 128;  // own frames per tile: 128 rows minus the 8-row halo that only the z_q_is stores need
+    const int nt_min = (T + amax - 1) / amax;
     const long fixed = zqis ? 24 : 1000;
     long best_cost = -1;
-    int best_nt = nt_min, best_adv = 120;
+    int best_nt = nt_min, best_adv = amax;
     for (int nt = nt_min; nt <= nt_min * 4 + 4; ++nt) {
         int a = ((T + nt - 1) / nt + 7) / 8 * 8;
-        if (a > 120) continue;
+        if (a > amax) continue;
         if (a < 8) a = 8;
         const int nt_eff = (T + a - 1) / a;
         const long tiles = (long)B * nt_eff;
@@ -1685,7 +1689,7 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
     pick_tiling(a->B, a->T, sms, a->z_q_is != nullptr, &P.adv, &P.tiles_per_b);
     if (const char *dbg = getenv("VRVQ_DEBUG_TILE_FRAMES")) {  // profiling knob
         const int v = atoi(dbg);
-        if (v >= 8 && v <= 120 && v % 8 == 0) { P.adv = v; P.tiles_per_b = (a->T + v - 1) / v; }
+        if (v >= 8 && v <= (a->z_q_is != nullptr ? 120 : 128) && v % 8 == 0) { P.adv = v; P.tiles_per_b = (a->T + v - 1) / v; }
     }
     P.n_tiles = P.tiles_per_b * a->B;
     P.zmode = pick_zmode(a, zmap, P);
