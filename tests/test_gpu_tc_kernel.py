@@ -45,7 +45,7 @@ def test_tc_kernel_is_the_default_path():
     cc = run_impl("cuda", lambda: ops.encode_launch_info(pw, 16, 862, 8, "cuda", z_q_is=True))
     assert tc["kernel"] == "tc" and tc["block"] == 512 and cc["kernel"] == "cuda", (tc, cc)
     assert tc["grid"] == 144  # with z_q_is a tile's time is its stores: 9 tiles of 96 frames per item, one wave on 148 SMs
-    # without z_q_is a tile costs the same whatever its length: the fewest waves win (config-4 shard: 10 waves of 120-frame tiles)
+    # without z_q_is a tile costs the same whatever its length: the fewest waves win (config-4 shard: 9 waves of 128-frame tiles)
     nz = run_impl(None, lambda: ops.encode_launch_info(pw, 32, 5168, 8, "cuda"))
     assert nz["kernel"] == "tc" and nz["grid"] == 148
     small = run_impl(None, lambda: ops.encode_launch_info(pw, 1, 87, 8, "cuda"))
@@ -306,3 +306,35 @@ def test_codebook_rows_that_do_not_normalise_to_unit_vectors():
         differ = (npy(out.codes) != o["codes"])
         assert np.isin(npy(out.codes)[differ], (7, 900)).all() or excused == 0
         H.assert_close_frames(npy(out.z_q), o["z_q"], skip=skip, what=f"z_q ({impl})")
+
+
+@pytest.mark.parametrize("Nq,n_run,vbr", [(8, 8, True), (8, 2, False), (8, 1, False), (9, 9, True), (17, 10, False)])
+@pytest.mark.parametrize("T", [127, 128, 129, 257, 384])
+def test_tiles_without_z_q_is_have_no_halo(Nq, n_run, vbr, T):
+    """Without z_q_is a tile is 128 own frames (no 8-row halo: it only serves the shifted z_q_is stores), the frame threads hand the
+    corrections of the later stages to warps 4-7 and the un-normalised codebook is staged in shared memory: tile boundaries at
+    multiples of 128 frames, one / two stages (nothing for warps 4-7 to correct), VBR masks, and the grouped instantiation."""
+    from vrvq_b200 import ops
+
+    D, B = 1024, 2
+    sd = gi.torch_state_dict(gi.make_state_dict(400 + Nq, Nq, D))
+    w = c_oracle.OracleWeights.from_state_dict(sd)
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    z_np = gi.make_latents(500 + T, B, D, T, 1.0)
+    imp_np = gi.make_imp_map(600 + T, B, T) if vbr else None
+    z = torch.from_numpy(z_np).cuda()
+    imp = torch.from_numpy(imp_np).cuda() if vbr else None
+    level = 0.7 if vbr else None
+    # (a call this small would be cut into shorter tiles to use more SMs: the profiling knob pins the 128-frame tiles of large calls)
+    os.environ["VRVQ_DEBUG_TILE_FRAMES"] = "128"
+    try:
+        a = run_impl("tc", lambda: ops.rvq_encode(pw, z, n_run, imp, level, want_z_q_is=False, want_loss_pf=True))
+        info = run_impl("tc", lambda: ops.encode_launch_info(pw, B, T, Nq, "cuda"))
+    finally:
+        os.environ.pop("VRVQ_DEBUG_TILE_FRAMES", None)
+    assert info["kernel"] == "tc" and info["grid"] == B * ((T + 127) // 128), info  # ceil(T / 128) tiles per item
+    o = c_oracle.encode(w, z_np, n_run if not vbr else None, imp_np, level, want_z_q_is=False)
+    excused, skip = H.assert_codes_match(w, o, npy(a.codes))
+    assert np.array_equal(npy(a.mask), o["mask"]) and np.array_equal(npy(a.kept), o["kept"])
+    H.assert_close_frames(npy(a.z_q), o["z_q"], skip=skip, what="z_q vs oracle")
+    H.assert_close_frames(npy(a.latents), o["latents"], skip=skip, what="latents vs oracle")
