@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         // QD = 4 chunks, whose products accumulate in four TMEM buffers (columns 0-511: nothing else is live by then) -- staging them
         // per chunk (8 x 8 steps of L2 gathers per tile) made the final phase 107k cycles per tile for 44k of tensor work
         constexpr int QD = NJ < 4 ? NJ : 4;
+        constexpr bool D4 = !ZQIS;  // the final GEMM's accumulators: QD buffers from column 0 (no per-stage units share the tensor memory)
         const int n_astage_steps = (p.z_q == nullptr || !last_grp || !GRP) ? 0 : (NJ / QD) * G_NST;
         const int n_final_steps = (p.z_q == nullptr || !last_grp) ? 0 : GRP ? NJ * G_NST : NJ * ((n_run + F_ITEMS) / F_ITEMS);  // !GRP: ceil((n_run + 1) / F_ITEMS) per chunk
         if constexpr (GRP) {
@@ -1199,12 +1200,13 @@ auto drain = [&](int g, uint32_t tq) {
             // t0 - 8 + delta_p + r.  The tile owns, per class, the frames [t0 - 8 + delta_p, t0 + adv - 8 + delta_p) (the last tile of
             // an item up to T), so consecutive tiles cover every row exactly once and every 32-lane store starts on a sector.
             auto unit = [&](float *row0, long long rstride, uint32_t shifts) {  // row0 = (row 128j, frame 0) of the output
-                // (grouped: QD accumulators at columns 128 k, filled together -- see the issuer)
-                const uint32_t buf = GRP ? dn % QD : (dn & 1u);
-                TC_WAIT(&bars[(GRP ? B_D4_FULL : B_D_FULL) + buf], (GRP ? dn / QD : (dn >> 1)) & 1u);
+                // (without z_q_is: QD accumulators at columns 128 k -- all of the tensor memory is free by the final GEMM; grouped: filled
+                // together, see the issuer; otherwise one after the other, so that the MMAs run up to QD units ahead of the stores)
+                const uint32_t buf = D4 ? dn % QD : (dn & 1u);
+                TC_WAIT(&bars[(D4 ? B_D4_FULL : B_D_FULL) + buf], (D4 ? dn / QD : (dn >> 1)) & 1u);
                 tmem_fence_after_sync();
                 ph_mark(1);
-                const uint32_t tcol = tq + (GRP ? 0u : TM_SET) + 128u * buf;
+                const uint32_t tcol = tq + (D4 ? 0u : TM_SET) + 128u * buf;
                 const uint32_t stepb = (uint32_t)(16 * rstride);  // bytes between channels 4 apart (row pitch < 2^28 floats: checked on the host)
                 uint32_t va[32], vb[32];
                 auto put = [&](const uint32_t (&v)[32], int piece) {
@@ -1235,7 +1237,7 @@ auto drain = [&](int g, uint32_t tq) {
                 tmem_wait_ld32(vb);
                 tmem_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[(GRP ? B_D4_EMPTY : B_D_EMPTY) + buf]);  // the MMA thread may refill this buffer
+                if (lane == 0) mbar_arrive(&bars[(D4 ? B_D4_EMPTY : B_D_EMPTY) + buf]);  // the MMA thread may refill this buffer
                 put(vb, 3);
                 ++dn;
                 ph_mark(2);
@@ -1375,8 +1377,14 @@ auto drain = [&](int g, uint32_t tq) {
                     const uint64_t am = desc128(smem_base + SM_AM) + HALO;
                     uint32_t fstep = fn;
                     for (int j = 0; j < NJ; ++j) {
-                        const uint32_t buf = wait_dbuf();
-                        const uint32_t d = tmem_u + TM_SET + 128u * buf;
+                        uint32_t buf;
+                        if constexpr (D4) {
+                            buf = dn % QD;
+                            if (dn / QD >= 1) TC_WAIT(&bars[B_D4_EMPTY + buf], (dn / QD - 1) & 1u);
+                        } else {
+                            buf = wait_dbuf();
+                        }
+                        const uint32_t d = tmem_u + (D4 ? 0u : TM_SET) + 128u * buf;
                         for (int s0 = 0; s0 <= n_run; s0 += F_ITEMS) {  // one ring step = up to F_ITEMS chunks (stages s0.., then the bias)
                             const uint32_t slot = fstep % F_SLOTS;
                             TC_WAIT(&bars[B_F_FULL + slot], (fstep / F_SLOTS) & 1u);
@@ -1399,7 +1407,7 @@ auto drain = [&](int g, uint32_t tq) {
                             }
                             ++fstep;
                         }
-                        if (elect_one()) umma_commit(&bars[B_D_FULL + buf]);
+                        if (elect_one()) umma_commit(&bars[(D4 ? B_D4_FULL : B_D_FULL) + buf]);
                         ++dn;
                     }
                     ph_mark(5);
