@@ -196,7 +196,7 @@ class VBRResidualVectorQuantize(ResidualVectorQuantize):
         if n_quantizers is None:  # ---- VBR mode
             assert level is not None, "level must be specified in VBR mode"
             if imp_map is None:
-                imp_map = self.imp_subnet(feat_enc)  # csrc/subnet.cu: six fused Snake+conv launches (quantize.py:372)
+                imp_map = self.imp_subnet(feat_enc)  # csrc/subnet_tc.cu: Snake pre-pass, three tcgen05 blocks, fused tail (quantize.py:372)
             imp_in, lvl = imp_map.contiguous(), level
             if isinstance(level, torch.Tensor):
                 # the reference broadcasts `imp_map [B,1,T] * level` (quantize.py:389): a scalar tensor or [B,1,1] is a
