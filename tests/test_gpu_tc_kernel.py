@@ -332,9 +332,49 @@ def test_tiles_without_z_q_is_have_no_halo(Nq, n_run, vbr, T):
         info = run_impl("tc", lambda: ops.encode_launch_info(pw, B, T, Nq, "cuda"))
     finally:
         os.environ.pop("VRVQ_DEBUG_TILE_FRAMES", None)
-    assert info["kernel"] == "tc" and info["grid"] == B * ((T + 127) // 128), info  # ceil(T / 128) tiles per item
+    flat = os.environ.get("VRVQ_FLAT_TILES") == "1" and T >= 128  # (forced flat tiling: tiles of the flattened frame sequence)
+    assert info["kernel"] == "tc" and info["grid"] == ((B * T + 127) // 128 if flat else B * ((T + 127) // 128)), info  # ceil(T / 128) tiles per item
     o = c_oracle.encode(w, z_np, n_run if not vbr else None, imp_np, level, want_z_q_is=False)
     excused, skip = H.assert_codes_match(w, o, npy(a.codes))
     assert np.array_equal(npy(a.mask), o["mask"]) and np.array_equal(npy(a.kept), o["kept"])
     H.assert_close_frames(npy(a.z_q), o["z_q"], skip=skip, what="z_q vs oracle")
     H.assert_close_frames(npy(a.latents), o["latents"], skip=skip, what="latents vs oracle")
+
+
+@pytest.mark.parametrize("Nq,n_run,vbr", [(8, 8, True), (8, 3, False), (9, 9, True), (28, 28, True)])
+@pytest.mark.parametrize("B,T", [(3, 129), (5, 200), (4, 333), (2, 128)])
+def test_flat_tiles_spanning_two_items(Nq, n_run, vbr, B, T):
+    """Flat tiling (taken by itself when it saves a wave, e.g. config 3: 431 instead of 448 tiles; forced here): a tile is 128
+    consecutive frames of the flattened (item, frame) sequence and may span two items -- two TMA boxes per chunk, per-row item for
+    the importance map, the per-item level, codes, latents, mask and z_q."""
+    from vrvq_b200 import ops
+
+    D = 1024
+    sd = gi.torch_state_dict(gi.make_state_dict(700 + Nq, Nq, D))
+    w = c_oracle.OracleWeights.from_state_dict(sd)
+    pw = ops.PackedWeights.from_state_dict(sd, "cuda")
+    z_np = gi.make_latents(800 + T, B, D, T, 1.0)
+    imp_np = gi.make_imp_map(900 + T, B, T) if vbr else None
+    z = torch.from_numpy(z_np).cuda()
+    imp = torch.from_numpy(imp_np).cuda() if vbr else None
+    level = 0.8 if vbr else None
+    os.environ["VRVQ_FLAT_TILES"] = "1"
+    try:
+        a = run_impl("tc", lambda: ops.rvq_encode(pw, z, n_run, imp, level, want_z_q_is=False, want_loss_pf=True))
+        info = run_impl("tc", lambda: ops.encode_launch_info(pw, B, T, Nq, "cuda"))
+        # a frame-range view of a wider tensor (rows 8-byte aligned only): same result bit for bit
+        zw = torch.zeros(B, D, T + 6, device="cuda")
+        zw[:, :, 2:T + 2] = z
+        v = run_impl("tc", lambda: ops.rvq_encode(pw, zw[:, :, 2:T + 2], n_run, imp, level, want_z_q_is=False))
+    finally:
+        os.environ.pop("VRVQ_FLAT_TILES", None)
+    b = run_impl("tc", lambda: ops.rvq_encode(pw, z, n_run, imp, level, want_z_q_is=False, want_loss_pf=True))  # per-item tiles
+    assert info["grid"] == (B * T + 127) // 128, info
+    o = c_oracle.encode(w, z_np, n_run if not vbr else None, imp_np, level, want_z_q_is=False)
+    excused, skip = H.assert_codes_match(w, o, npy(a.codes))
+    assert np.array_equal(npy(a.mask), o["mask"]) and np.array_equal(npy(a.kept), o["kept"])
+    H.assert_close_frames(npy(a.z_q), o["z_q"], skip=skip, what="z_q vs oracle")
+    H.assert_close_frames(npy(a.latents), o["latents"], skip=skip, what="latents vs oracle")
+    # frames are independent and every lane's arithmetic order is fixed: the tiling cannot change a bit
+    assert torch.equal(a.codes, b.codes) and torch.equal(a.z_q, b.z_q) and torch.equal(a.latents, b.latents) and torch.equal(a.loss_pf, b.loss_pf)
+    assert torch.equal(a.codes, v.codes) and torch.equal(a.z_q, v.z_q)

@@ -75,7 +75,7 @@ constexpr int L_SLOTS = 3;         // the matching A operand (the split latent c
 // boxes through the channel-class tensor maps (pick_zmode); or, for A/B runs, one cp.async.bulk per channel row from the 16-byte
 // aligned address at or below the row's first frame -- so the 256 loader threads read the latent with conflict-free LDS
 // (lane = frame) instead of issuing 128 misaligned LDGs per chunk and waiting on HBM.
-constexpr int SM_ZR = WL_SLOTS * L_SLOT, Z_CH = 32, Z_PITCH = 132, Z_SLOT = Z_CH * Z_PITCH * 4, Z_SLOTS = 5;
+constexpr int SM_ZR = WL_SLOTS * L_SLOT, Z_CH = 32, Z_PITCH = 136, Z_SLOT = Z_CH * Z_PITCH * 4, Z_SLOTS = 5;
 constexpr int SM_AT = 0;           // phase S: per-stage A tiles, 8 x (hi 4 KB | lo 4 KB): [2 kg][128 frames][4]
 constexpr int SM_AM = 65536;       // phase S: mask tile (A operand of the bias rows of the final GEMM) [2 kg][128][4]
 constexpr int SM_WO = 69632;       // phase S: W_out ring, 4 slots x 12 KB (hi | lo | bias tile)
@@ -156,6 +156,8 @@ struct TcParams {
     const float *tc;  // TC section of the blob
     int adv;          // frames per tile (multiple of 8, <= 120)
     int tiles_per_b, n_tiles;
+    int flat;         // without z_q_is, T >= 128, TMA latent path: tiles are 128 consecutive frames of the FLATTENED (item, frame) sequence
+                      // and may span two items (config 3: 431 tiles = 3 waves of 148 instead of 64 x 7 = 448 = 4 waves)
     int zmode;        // ZMODE_*
     int znc_log2;     // ZMODE_TMA: log2 of the number of channel classes (1, 2 or 4 tensor maps; see pick_zmode)
     int zshift[4];    // ZMODE_TMA: x offset of frame 0 in the rows of class k
@@ -203,9 +205,10 @@ __device__ __forceinline__ uint32_t base_mod8(const float *ptr, long long off) {
 // -G[s][j] = -W_in[s] W_out[j] -- so the cross-group corrections are extra K of the same GEMM (the straight-through vector q_j is
 // taken as the code's row there: it differs from it by <= 1 ulp, below the rounding of z_e itself); codes stay in shared memory,
 // and the final z_q GEMM over K = 8 n_run regenerates its A tiles from them, four stages per ring step.
-template <int D, bool ZQIS, bool PROFILE, bool FC, bool GRP = false>
+template <int D, bool ZQIS, bool PROFILE, bool FC, bool GRP = false, bool FLAT = false>
 __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams P, const __grid_constant__ ZMaps zmaps) {
     static_assert(!GRP || (!ZQIS && !FC && !PROFILE), "the grouped instantiation has no z_q_is, from_codes or profiling variant");
+    static_assert(!FLAT || (!ZQIS && !FC && !PROFILE), "flat tiling (tiles that may span two items) exists for the encode without z_q_is only");
     constexpr int NCH = D / 32, NG = NCH / 4, NJ = D / 128;
     // rows of a tile in front of its own frames: the 8-frame halo exists for the shifted, sector-aligned stores of z_q_is; without them a
     // tile is 128 own frames (config-4 shard: 41 instead of 44 tiles per item = 9 waves instead of 10)
@@ -346,12 +349,20 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         const bool first_grp = grp == 0, last_grp = grp == n_grp - 1;
         const int NV = GRP ? TcLayout::vp(grp) : 0, NCT = NCH + NV;  // virtual chunks (cross-group corrections); chunks of this pass
         const int tile = (int)blockIdx.x + tile_i * (int)gridDim.x;
-        const int b = tile / P.tiles_per_b;
-        const int t0 = (tile % P.tiles_per_b) * P.adv;
-        const int fv = min(P.adv, p.T - t0);  // frames this tile owns: tile rows 8 .. 8+fv-1 (rows 0-7: halo = the previous 8 frames)
+        // Flat tiling (P.flat; never with z_q_is or from_codes): row r of the tile is flat frame 128 tile + r of the (item, frame) sequence;
+        // rows [0, ra) belong to item b (frames t0 ..), rows [ra, ra + nb2) to item b + 1 (frames 0 ..) -- T >= 128, so at most two items.
+        constexpr bool flat = FLAT;  // (its own instantiation: the extra per-row bookkeeping costs the other shapes 4-8 % through register pressure)
+        const long long g0 = 128ll * (long long)tile;
+        const int b = flat ? (int)(g0 / p.T) : tile / P.tiles_per_b;
+        const int t0 = flat ? (int)(g0 - (long long)b * p.T) : (tile % P.tiles_per_b) * P.adv;
+        const int ra = flat ? min(128, p.T - t0) : 128;
+        const int nb2 = (flat && b + 1 < p.B) ? 128 - ra : 0;
+        const int fv = flat ? ra : min(P.adv, p.T - t0);  // frames of item b this tile owns: tile rows HALO .. HALO+fv-1 (rows 0-7 with z_q_is: halo = the previous 8 frames)
         const bool last_tile = (tile % P.tiles_per_b) == P.tiles_per_b - 1;
+        const uint32_t zper = nb2 > 0 ? 2u : 1u;  // latent ring slots per chunk: a second box for the rows of item b + 1
         // latent staging geometry of this tile (ZMODE_BULK / ZMODE_TMA): smem column of frame fr in a staged row = fr - tstart + shift(row)
-        const int tstart = P.zmode == ZMODE_TMA ? t0 - HALO : max(t0 - HALO, 0);
+        // (flat: t0 is any frame of the item, and a TMA box must start at a multiple of 4 elements)
+        const int tstart = P.zmode == ZMODE_TMA ? (flat ? (t0 & ~3) : t0 - HALO) : max(t0 - HALO, 0);
         const uint32_t tpar = (uint32_t)it & 1u;  // phase parity of the once-per-pass barriers
         // A_READY[s] completes one phase per pass that HAS a stage s (the last group of a tile may be shorter): its phase index
         auto apar = [&](int s) -> uint32_t {
@@ -651,9 +662,11 @@ auto drain = [&](int g, uint32_t tq) {
             // Search group.  Frame threads (warps 0-3): f = tid = TMEM lane.
             // =====================================================================================================
             const int f = tid & 127;            // tile row = TMEM lane
-            const int fr = t0 - HALO + f;       // its frame
-            const bool own = f >= HALO && f - HALO < fv;        // frames whose per-frame outputs this tile writes
-            const bool inb = fr >= 0 && (f < HALO || f - HALO < fv);  // rows that hold a real frame (halo rows of the first tile do not)
+            const bool row2 = flat && f >= ra;  // (flat tiling) the row belongs to item b + 1
+            const int bq = b + (row2 ? 1 : 0);  // its item
+            const int fr = row2 ? f - ra : t0 - HALO + f;  // its frame
+            const bool own = flat ? (row2 ? f - ra < nb2 : true) : (f >= HALO && f - HALO < fv);  // frames whose per-frame outputs this tile writes
+            const bool inb = flat ? own : (fr >= 0 && (f < HALO || f - HALO < fv));  // rows that hold a real frame (halo rows of the first tile do not)
             const uint32_t tq = tmem + ((uint32_t)(32 * (w & 3)) << 16);  // this warp's lane quarter
             if constexpr (!FC) {
             ph_mark(0);
@@ -662,7 +675,7 @@ auto drain = [&](int g, uint32_t tq) {
                 // staged path: the chunk's rows are in shared memory (TMA); lane = frame, so every LDS is conflict-free
                 const int q = tid >> 7;
                 const bool valid = inb;
-                const int col = min(max(fr - tstart, 0), 127);
+                const int col = row2 ? f - ra : min(max(fr - tstart, 0), flat ? 131 : 127);  // (flat: the second item's box starts at its frame 0)
                 // row shift: (alignment of the row's first frame) mod 4 floats; rows 4 apart share it (32 and 16 rows apart too)
                 uint32_t shw[4];
                 if (P.zmode == ZMODE_TMA) {
@@ -681,10 +694,12 @@ auto drain = [&](int g, uint32_t tq) {
                 auto stage = [&](auto nc_tag) {
                     constexpr int NC = decltype(nc_tag)::value;
                     for (int c = 0; c < NCH; ++c) {
-                        const uint32_t zn = zbase + (uint32_t)c, zsl = zn % Z_SLOTS;
+                        const uint32_t zn = zbase + (uint32_t)c * zper, zsl = zn % Z_SLOTS;
+                        const uint32_t zn2 = zn + 1u, zsl2 = zn2 % Z_SLOTS;  // (flat tiling, tile spans two items: the box of item b + 1)
                         TC_WAIT(&bars[B_Z_FULL + zsl], (zn / Z_SLOTS) & 1u);
+                        if (zper == 2u) TC_WAIT(&bars[B_Z_FULL + zsl2], (zn2 / Z_SLOTS) & 1u);
                         if (PROFILE && tid == 0 && it == 0) trace(0, c);
-                        const float *zr = reinterpret_cast<const float *>(smem + SM_ZR + zsl * Z_SLOT) + ((16 * q) / NC) * Z_PITCH + col;
+                        const float *zr = reinterpret_cast<const float *>(smem + SM_ZR + (row2 ? zsl2 : zsl) * Z_SLOT) + ((16 * q) / NC) * Z_PITCH + col;
                         float h[16], l[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -693,7 +708,10 @@ auto drain = [&](int g, uint32_t tq) {
                             l[i] = __fsub_rn(x, h[i]);
                         }
                         __syncwarp();  // the slot is in registers: hand it back to the producer
-                        if (lane == 0) mbar_arrive(&bars[B_Z_EMPTY + zsl]);
+                        if (lane == 0) {
+                            mbar_arrive(&bars[B_Z_EMPTY + zsl]);
+                            if (zper == 2u) mbar_arrive(&bars[B_Z_EMPTY + zsl2]);
+                        }
                         if (PROFILE && tid == 0 && it == 0) trace(1, c);
                         const uint32_t n = lbase + (uint32_t)c, sl = n % L_SLOTS, use = n / L_SLOTS;
                         if (use >= 1) {
@@ -905,7 +923,7 @@ auto drain = [&](int g, uint32_t tq) {
                 if (lane == 0) mbar_arrive(&bars[B_E_READY]);  // the search-MMA issuer may start on this stage
                 if (p.latents != nullptr && own) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) p.latents[(long long)b * p.lat_sb + (long long)((s0 + s) * 8 + k) * p.lat_sc + fr] = zev[k];
+                    for (int k = 0; k < 8; ++k) p.latents[(long long)bq * p.lat_sb + (long long)((s0 + s) * 8 + k) * p.lat_sc + fr] = zev[k];
                 }
             };
             auto prep = [&](int s) {
@@ -1050,8 +1068,8 @@ auto drain = [&](int g, uint32_t tq) {
                     if (PROFILE && tid == 0) strace(14, s, it == 0);
                     if (own) {
                         const float loss = __fdiv_rn(ls, 8.0f);
-                        p.codes[(long long)b * p.codes_sb + (long long)sg * p.codes_sq + fr] = (long long)bi;
-                        if (p.loss_pf != nullptr) p.loss_pf[(long long)b * p.loss_sb + (long long)sg * p.loss_sq + fr] = loss;
+                        p.codes[(long long)bq * p.codes_sb + (long long)sg * p.codes_sq + fr] = (long long)bi;
+                        if (p.loss_pf != nullptr) p.loss_pf[(long long)bq * p.loss_sb + (long long)sg * p.loss_sq + fr] = loss;
                         if (nkeep[f] > sg) loss_acc += (double)loss;
                     }
                     if constexpr (GRP) code_slot(sg)[f] = (unsigned short)bi;  // for the later groups' virtual chunks and the final GEMM
@@ -1156,13 +1174,15 @@ auto drain = [&](int g, uint32_t tq) {
                 if (first_grp) {
                     // ---- keep counts, mask, kept-frame counts (quantize.py:389, utils.py:59-60): by these warps, which only have a drain
                     // every fourth chunk to do in phase L -- on the loader warps it delayed the first chunk of every tile by ~4k cycles ----
-                    const int f = tid & 127, fr = t0 - HALO + f;  // tile row, its frame
-                    const bool own = f >= HALO && f - HALO < fv;
+                    const int f = tid & 127;  // tile row
+                    const bool row2 = flat && f >= ra;
+                    const int bq = b + (row2 ? 1 : 0), fr = row2 ? f - ra : t0 - HALO + f;  // its item, its frame
+                    const bool own = flat ? (row2 ? f - ra < nb2 : true) : (f >= HALO && f - HALO < fv);
                     int nk = 0;
                     if (own) {
                         if (p.imp != nullptr) {
-                            const float lv = p.level_dev ? p.level_dev[(long long)b * p.level_stride] : p.level_host;
-                            const float x = __fmul_rn(__fmul_rn(p.imp[(long long)b * p.imp_sb + fr], lv), (float)Nq);
+                            const float lv = p.level_dev ? p.level_dev[(long long)bq * p.level_stride] : p.level_host;
+                            const float x = __fmul_rn(__fmul_rn(p.imp[(long long)bq * p.imp_sb + fr], lv), (float)Nq);
                             for (int k = 0; k < n_run; ++k) nk += (__fsub_rn(x, (float)k) >= 0.0f) ? 1 : 0;
                         } else {
                             nk = n_run;
@@ -1173,7 +1193,7 @@ auto drain = [&](int g, uint32_t tq) {
                         const bool on = nk > k;
                         const unsigned bal = __ballot_sync(0xffffffffu, on);
                         if (lane == k) kept_acc += (unsigned long long)__popc(bal);
-                        if (p.mask != nullptr && own) p.mask[(long long)b * p.mask_sb + (long long)k * p.mask_sq + fr] = on ? 1.0f : 0.0f;
+                        if (p.mask != nullptr && own) p.mask[(long long)bq * p.mask_sb + (long long)k * p.mask_sq + fr] = on ? 1.0f : 0.0f;
                     }
                 }
             }
@@ -1211,10 +1231,11 @@ auto drain = [&](int g, uint32_t tq) {
                 uint32_t va[32], vb[32];
                 auto put = [&](const uint32_t (&v)[32], int piece) {
                     const int dl = (int)((shifts >> (8 * piece)) & 0xffu);
-                    const int frame = t0 - HALO + dl + r;
-                    const bool ok = frame >= 0 && (last_tile ? frame < p.T : r < P.adv);
+                    const bool r2 = flat && r >= ra;  // (flat tiling: the lane's row belongs to item b + 1; only z_q is stored then)
+                    const int frame = r2 ? r - ra : t0 - HALO + dl + r;
+                    const bool ok = flat ? (r2 ? r - ra < nb2 : true) : (frame >= 0 && (last_tile ? frame < p.T : r < P.adv));
                     if (ok) {
-                        const unsigned long long o = reinterpret_cast<unsigned long long>(row0 + (long long)piece * rstride + frame);
+                        const unsigned long long o = reinterpret_cast<unsigned long long>(row0 + (r2 ? p.zq_sb : 0ll) + (long long)piece * rstride + frame);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             // one independent IMAD.WIDE per address (a running 64-bit pointer costs a 4-instruction dependent chain per store)
@@ -1431,16 +1452,17 @@ auto drain = [&](int g, uint32_t tq) {
             if (!FC && P.zmode != ZMODE_LDG) {
                 // ---- phase L: producer of the latent staging ring (this warp has nothing else to do before the searches) ----
                 const int fvz = t0 + fv - tstart;  // frames to stage per row (<= 128)
-                for (int zc = 0; zc < NCH; ++zc) {
-                    const uint32_t m = zbase + (uint32_t)zc, slot = m % Z_SLOTS, use = m / Z_SLOTS;
+                for (int zq = 0; zq < NCH * (int)zper; ++zq) {
+                    const int zc = zq / (int)zper, second = zq % (int)zper;  // (flat tiling, tile spans two items: second box = item b + 1 from its frame 0)
+                    const uint32_t m = zbase + (uint32_t)zq, slot = m % Z_SLOTS, use = m / Z_SLOTS;
                     if (use >= 1) TC_WAIT(&bars[B_Z_EMPTY + slot], (use - 1) & 1u);
                     unsigned char *dst = smem + SM_ZR + slot * Z_SLOT;
                     if (P.zmode == ZMODE_TMA) {
-                        if (lane == 0) {  // nc boxes [1 item][64 / nc channels of one class][132 frames]; x outside the map arrives as zeros
+                        if (lane == 0) {  // nc boxes [1 item][64 / nc channels of one class][136 frames]; x outside the map arrives as zeros
                             const int lg = P.znc_log2, rows = Z_CH >> lg;
                             mbar_arrive_expect_tx(&bars[B_Z_FULL + slot], Z_SLOT);
                             for (int k = 0; k < (1 << lg); ++k)
-                                tma_load_3d(dst + k * rows * (Z_PITCH * 4), &zmaps.m[k], tstart, rows * zc, b, &bars[B_Z_FULL + slot]);
+                                tma_load_3d(dst + k * rows * (Z_PITCH * 4), &zmaps.m[k], second ? 0 : tstart, rows * zc, b + second, &bars[B_Z_FULL + slot]);
                         }
                     } else {
                         // one bulk copy per channel row, from the 16-byte aligned address at or below its first frame to the
@@ -1603,7 +1625,7 @@ auto drain = [&](int g, uint32_t tq) {
         cbu1 += (uint32_t)(nl >> 1);
         lbase += (uint32_t)NCT;
         gbase += (uint32_t)(NCT / 4);
-        zbase += (uint32_t)NCH;
+        zbase += (uint32_t)NCH * zper;
         tmem_fence_before_sync();
         __syncthreads();  // end of tile: every MMA of the tile has completed (the epilogue waited for the last one)
         tmem_fence_after_sync();
@@ -1701,18 +1723,38 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
     }
     P.n_tiles = P.tiles_per_b * a->B;
     P.zmode = pick_zmode(a, zmap, P);
+    // Flat tiling: without z_q_is a tile costs the same whatever it holds, so only the number of waves counts, and items whose length is not
+    // a multiple of 128 waste the rest of their last tile (config 3: 64 x 7 = 448 tiles = 3.03 waves of 148).  Tiles of 128 consecutive frames
+    // of the flattened (item, frame) sequence -- a tile may then span two items, hence T >= 128 -- need ceil(B T / 128) (431 = 3 waves).
+    // Taken when it saves a wave; the latent of a spanning tile comes through two TMA boxes, so only on the TMA path.
+    P.flat = 0;
+    const char *dbgp = getenv("VRVQ_DEBUG_PHASES");
+    if (a->z_q_is == nullptr && a->T >= 128 && P.zmode == ZMODE_TMA && !(dbgp != nullptr && dbgp[0] != '2')) {
+        const long long flat_tiles = ((long long)a->B * a->T + 127) / 128;
+        const long long waves_now = ((long long)P.n_tiles + sms - 1) / sms, waves_flat = (flat_tiles + sms - 1) / sms;
+        const char *env = getenv("VRVQ_FLAT_TILES");
+        if (env ? env[0] == '1' : (waves_flat < waves_now && P.n_tiles > sms)) {
+            P.flat = 1;
+            P.adv = 128;
+            P.tiles_per_b = (a->T + 127) / 128;
+            P.n_tiles = (int)flat_tiles;
+        }
+    }
     P.single_issuer = getenv("VRVQ_DEBUG_SINGLE_ISSUER") != nullptr;
     P.stagger = getenv("VRVQ_DEBUG_STAGGER") ? atoi(getenv("VRVQ_DEBUG_STAGGER")) : 0;
     *grid = P.n_tiles < sms ? P.n_tiles : sms;
     return VRVQ_OK;
 }
 
-template <int D, bool ZQIS, bool PROFILE, bool FC = false, bool GRP = false>
+template <int D, bool ZQIS, bool PROFILE, bool FC = false, bool GRP = false, bool FLAT = false>
 static int launch_tc_one(const TcParams &P, const ZMaps &zmap, int grid, cudaStream_t st) {
     constexpr int SMEM = GRP ? SM_TOTAL_G : SM_TOTAL;
-    int rc = ensure_dynamic_smem<rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC, GRP>>(SMEM, "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
+    if constexpr (!FLAT && !ZQIS && !FC && !PROFILE) {  // flat tiling is its own instantiation
+        if (P.flat) return launch_tc_one<D, ZQIS, PROFILE, FC, GRP, true>(P, zmap, grid, st);
+    }
+    int rc = ensure_dynamic_smem<rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC, GRP, FLAT>>(SMEM, "cudaFuncSetAttribute(rvq_encode_tc_kernel)");
     if (rc) return rc;
-    rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC, GRP><<<grid, TC_NTH, SMEM, st>>>(P, zmap);
+    rvq_encode_tc_kernel<D, ZQIS, PROFILE, FC, GRP, FLAT><<<grid, TC_NTH, SMEM, st>>>(P, zmap);
     return check_cuda(cudaGetLastError(), "rvq_encode_tc_kernel launch");
 }
 template <int D, bool ZQIS>
