@@ -378,6 +378,9 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         const int fv = flat ? ra : min(P.adv, p.T - t0);  // frames of item b this tile owns: tile rows HALO .. HALO+fv-1 (rows 0-7 with z_q_is: halo = the previous 8 frames)
         const bool last_tile = (tile % P.tiles_per_b) == P.tiles_per_b - 1;
         const uint32_t zper = nb2 > 0 ? 2u : 1u;  // latent ring slots per chunk: a second box for the rows of item b + 1
+        // ... which starts at a NEGATIVE x, so that only the nb2 (+ class shift) frames it needs lie inside the tensor (what is outside arrives
+        // as zeros without being fetched, like the frames past T of the first box): frame fr of item b + 1 sits in column x2off + fr + shift
+        const int x2off = Z_PITCH - ((nb2 + 6) & ~3);
         // latent staging geometry of this tile (ZMODE_BULK / ZMODE_TMA): smem column of frame fr in a staged row = fr - tstart + shift(row)
         // (flat: t0 is any frame of the item, and a TMA box must start at a multiple of 4 elements)
         const int tstart = P.zmode == ZMODE_TMA ? (flat ? (t0 & ~3) : t0 - HALO) : max(t0 - HALO, 0);
@@ -693,7 +696,7 @@ auto drain = [&](int g, uint32_t tq) {
                 // staged path: the chunk's rows are in shared memory (TMA); lane = frame, so every LDS is conflict-free
                 const int q = tid >> 7;
                 const bool valid = inb;
-                const int col = row2 ? f - ra : min(max(fr - tstart, 0), flat ? 131 : 127);  // (flat: the second item's box starts at its frame 0)
+                const int col = row2 ? x2off + f - ra : min(max(fr - tstart, 0), flat ? 131 : 127);
                 // row shift: (alignment of the row's first frame) mod 4 floats; rows 4 apart share it (32 and 16 rows apart too)
                 uint32_t shw[4];
                 if (P.zmode == ZMODE_TMA) {
@@ -1480,7 +1483,7 @@ auto drain = [&](int g, uint32_t tq) {
                             const int lg = P.znc_log2, rows = Z_CH >> lg;
                             mbar_arrive_expect_tx(&bars[B_Z_FULL + slot], Z_SLOT);
                             for (int k = 0; k < (1 << lg); ++k)
-                                tma_load_3d(dst + k * rows * (Z_PITCH * 4), &zmaps.m[k], second ? 0 : tstart, rows * zc, b + second, &bars[B_Z_FULL + slot]);
+                                tma_load_3d(dst + k * rows * (Z_PITCH * 4), &zmaps.m[k], second ? -x2off : tstart, rows * zc, b + second, &bars[B_Z_FULL + slot]);
                         }
                     } else {
                         // one bulk copy per channel row, from the 16-byte aligned address at or below its first frame to the
