@@ -1754,7 +1754,9 @@ static int make_params(const vrvq_encode_args *a, const EncodeParams &e, TcParam
         const long long flat_tiles = ((long long)a->B * a->T + 127) / 128;
         const long long waves_now = ((long long)P.n_tiles + sms - 1) / sms, waves_flat = (flat_tiles + sms - 1) / sms;
         const char *env = getenv("VRVQ_FLAT_TILES");
-        if (env ? env[0] == '1' : (waves_flat < waves_now && P.n_tiles > sms)) {
+        // (a pass of the flat instantiation costs ~10 % more -- per-row items, the permuted order, two boxes for the spanning tiles -- so it
+        // has to save more than that: config 3 4 -> 3 waves; not all of config 4 on one GPU, 71 -> 70 waves: 5230 vs 5817 us)
+        if (env ? env[0] == '1' : (waves_flat * 112 < waves_now * 100 && P.n_tiles > sms)) {
             P.flat = 1;
             P.adv = 128;
             P.tiles_per_b = (a->T + 127) / 128;
