@@ -377,7 +377,12 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         const int nb2 = (flat && b + 1 < p.B) ? 128 - ra : 0;
         const int fv = flat ? ra : min(P.adv, p.T - t0);  // frames of item b this tile owns: tile rows HALO .. HALO+fv-1 (rows 0-7 with z_q_is: halo = the previous 8 frames)
         const bool last_tile = (tile % P.tiles_per_b) == P.tiles_per_b - 1;
-        const uint32_t zper = nb2 > 0 ? 2u : 1u;  // latent ring slots per chunk: a second box for the rows of item b + 1
+        // The rest of the pass is instantiated twice in the flat kernel: for tiles inside one item (everything per-item stays warp-uniform, the
+        // code of the per-item tiling) and for the ~B spanning tiles (SPAN: per-row item, two latent boxes per chunk) -- with the per-row
+        // bookkeeping compiled into every pass the flat kernel cost 8-10 % per tile.
+        auto pass_body = [&](auto span_c) {
+        constexpr bool SPAN = FLAT && decltype(span_c)::value;
+        constexpr uint32_t zper = SPAN ? 2u : 1u;  // latent ring slots per chunk: a second box for the rows of item b + 1
         // ... which starts at a NEGATIVE x, so that only the nb2 (+ class shift) frames it needs lie inside the tensor (what is outside arrives
         // as zeros without being fetched, like the frames past T of the first box): frame fr of item b + 1 sits in column x2off + fr + shift
         const int x2off = Z_PITCH - ((nb2 + 6) & ~3);
@@ -683,10 +688,10 @@ auto drain = [&](int g, uint32_t tq) {
             // Search group.  Frame threads (warps 0-3): f = tid = TMEM lane.
             // =====================================================================================================
             const int f = tid & 127;            // tile row = TMEM lane
-            const bool row2 = flat && f >= ra;  // (flat tiling) the row belongs to item b + 1
+            const bool row2 = SPAN && f >= ra;  // (spanning tile) the row belongs to item b + 1
             const int bq = b + (row2 ? 1 : 0);  // its item
             const int fr = row2 ? f - ra : t0 - HALO + f;  // its frame
-            const bool own = flat ? (row2 ? f - ra < nb2 : true) : (f >= HALO && f - HALO < fv);  // frames whose per-frame outputs this tile writes
+            const bool own = flat ? (f < ra || (SPAN && f - ra < nb2)) : (f >= HALO && f - HALO < fv);  // frames whose per-frame outputs this tile writes
             const bool inb = flat ? own : (fr >= 0 && (f < HALO || f - HALO < fv));  // rows that hold a real frame (halo rows of the first tile do not)
             const uint32_t tq = tmem + ((uint32_t)(32 * (w & 3)) << 16);  // this warp's lane quarter
             if constexpr (!FC) {
@@ -1196,9 +1201,9 @@ auto drain = [&](int g, uint32_t tq) {
                     // ---- keep counts, mask, kept-frame counts (quantize.py:389, utils.py:59-60): by these warps, which only have a drain
                     // every fourth chunk to do in phase L -- on the loader warps it delayed the first chunk of every tile by ~4k cycles ----
                     const int f = tid & 127;  // tile row
-                    const bool row2 = flat && f >= ra;
+                    const bool row2 = SPAN && f >= ra;
                     const int bq = b + (row2 ? 1 : 0), fr = row2 ? f - ra : t0 - HALO + f;  // its item, its frame
-                    const bool own = flat ? (row2 ? f - ra < nb2 : true) : (f >= HALO && f - HALO < fv);
+                    const bool own = flat ? (f < ra || (SPAN && f - ra < nb2)) : (f >= HALO && f - HALO < fv);
                     int nk = 0;
                     if (own) {
                         if (p.imp != nullptr) {
@@ -1252,9 +1257,9 @@ auto drain = [&](int g, uint32_t tq) {
                 uint32_t va[32], vb[32];
                 auto put = [&](const uint32_t (&v)[32], int piece) {
                     const int dl = (int)((shifts >> (8 * piece)) & 0xffu);
-                    const bool r2 = flat && r >= ra;  // (flat tiling: the lane's row belongs to item b + 1; only z_q is stored then)
+                    const bool r2 = SPAN && r >= ra;  // (spanning tile: the lane's row belongs to item b + 1; only z_q is stored then)
                     const int frame = r2 ? r - ra : t0 - HALO + dl + r;
-                    const bool ok = flat ? (r2 ? r - ra < nb2 : true) : (frame >= 0 && (last_tile ? frame < p.T : r < P.adv));
+                    const bool ok = flat ? (r < ra || (SPAN && r - ra < nb2)) : (frame >= 0 && (last_tile ? frame < p.T : r < P.adv));
                     if (ok) {
                         const unsigned long long o = reinterpret_cast<unsigned long long>(row0 + (r2 ? p.zq_sb : 0ll) + (long long)piece * rstride + frame);
 #pragma unroll
@@ -1658,6 +1663,9 @@ auto drain = [&](int g, uint32_t tq) {
             lite_t0 = t;
             lite_l = 0;
         }
+        };  // pass_body
+        if (FLAT && nb2 > 0) pass_body(std::true_type{});
+        else pass_body(std::false_type{});
     }
     if (PROFILE && ph_on && !P.trace)
         for (int k = 0; k < 16; ++k) p.phase_cycles[((size_t)blockIdx.x * 4 + ph_role) * 16 + k] = ph_acc[k];
