@@ -121,6 +121,10 @@ int vrvq_rvq_encode_f32(const vrvq_encode_args *args, void *stream);
 
 /* Number of CTAs / dynamic shared memory bytes the encode launch would use (bench/roofline reporting). */
 int vrvq_rvq_encode_launch_info(const vrvq_encode_args *args, int *grid, int *block, int *smem_bytes);
+/* Diagnostic: the tile visited at position q of the order in which the kernel's CTAs walk the "flat" tiling of calls without z_q_is
+ * (tiles of 128 consecutive frames of the flattened (item, frame) sequence; the B - 1 tiles that span two items come first).  A
+ * permutation of [0, ceil(B T / 128)); VRVQ_EINVAL outside (T < 128, q out of range).  No reference counterpart: scheduling detail. */
+int vrvq_flat_tile_order(int B, int T, int q);
 
 /* Which kernel vrvq_rvq_encode_f32 would launch for these arguments: "tc" = rvq_encode_tc_kernel (tcgen05 tensor cores),
  * "cuda" = rvq_encode_kernel (CUDA cores); NULL (and an error message) for invalid arguments.  Static strings. */

@@ -249,3 +249,17 @@ def test_blob_without_tensor_core_section_for_large_nq():
     pw = ops.PackedWeights.from_state_dict(sd, "cpu")
     hdr = pw.host_blob[:16].view(np.int32)
     assert int(hdr[6]) == 0 and int(hdr[7]) == 0, "Nq > 32 has no tensor-core kernel: no TC section"
+
+
+def test_flat_tile_order_is_a_permutation_with_the_spanning_tiles_first():
+    """csrc/common.cuh:flat_tile_at (the order in which the flat-tiling kernel's CTAs walk their tiles) through its diagnostic entry:
+    a permutation of [0, ceil(B T / 128)) whose first B - 1 positions are the tiles that hold an item boundary."""
+    L = _lib.lib()
+    L.vrvq_flat_tile_order.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.vrvq_flat_tile_order.restype = C.c_int
+    for B, T in [(64, 862), (3, 129), (5, 200), (4, 333), (2, 128), (32, 5168), (7, 128), (9, 255), (6, 256), (1, 500), (256, 5168), (17, 131)]:
+        n = (B * T + 127) // 128
+        order = [L.vrvq_flat_tile_order(B, T, q) for q in range(n)]
+        assert sorted(order) == list(range(n)), (B, T)
+        assert order[:B - 1] == [(j * T) // 128 for j in range(1, B)], (B, T)
+    assert L.vrvq_flat_tile_order(4, 127, 0) == -1 and L.vrvq_flat_tile_order(4, 200, 7) == -1 and L.vrvq_flat_tile_order(4, 200, -1) == -1

@@ -56,7 +56,7 @@ EXPORTS = [
     "vrvq_search_latents_f32", "vrvq_generate_mask_hard_f32", "vrvq_mask_sum_f32", "vrvq_remask_f32",
     "vrvq_pack_codes_u16", "vrvq_unpack_codes_u16", "vrvq_conv3_packed_floats", "vrvq_pack_conv3_weights", "vrvq_snake_conv3_f32",
     "vrvq_conv3_tc_packed_floats", "vrvq_pack_conv3_tc_weights", "vrvq_snake_conv3_tc_f32", "vrvq_snake_f32",
-    "vrvq_subnet_tail_usable", "vrvq_subnet_tail_f32",
+    "vrvq_subnet_tail_usable", "vrvq_subnet_tail_f32", "vrvq_flat_tile_order",
 ]
 
 _lib = None

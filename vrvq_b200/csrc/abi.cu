@@ -222,6 +222,10 @@ using namespace vrvq;
 extern "C" {
 
 int vrvq_abi_version(void) { return VRVQ_ABI_VERSION; }
+int vrvq_flat_tile_order(int B, int T, int q) {
+    if (B < 1 || T < 128 || q < 0 || (long long)q >= ((long long)B * T + 127) / 128) return VRVQ_EINVAL;
+    return vrvq::flat_tile_at(q, B, T);
+}
 
 const char *vrvq_last_error(void) { return g_err; }
 

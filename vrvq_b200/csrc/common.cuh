@@ -177,6 +177,23 @@ struct TcLayout {
     __host__ __device__ constexpr int total() const { return off_cbk() + Nq * 9216; }
     __host__ __device__ static constexpr int pair_index(int nq, int j, int s) { return j * nq - j * (j + 1) / 2 + (s - j - 1); }
 };
+// Flat tiling of the encode without z_q_is (rvq_encode_tc.cu, FLAT): tiles are 128 consecutive frames of the flattened (item, frame)
+// sequence; the one holding flat frame j T (j = 1 .. B-1) spans two items and costs ~20 % more, so CTAs walk a permuted order: position
+// q < B-1 is the q-th spanning tile (they go first, one per CTA), position q >= B-1 the (q - (B-1))-th of the others -- the least fixpoint of
+// t = m + #{j : floor(j T / 128) <= t}.  A permutation of [0, ceil(B T / 128)) for T >= 128 (tests/test_abi_cpu.py through vrvq_flat_tile_order).
+__host__ __device__ inline int flat_tile_at(int q, int B, int T) {
+    const int S = B - 1;
+    if (q < S) return (int)(((long long)(q + 1) * T) / 128);
+    const int m = q - S;
+    int t = m;
+    for (int guard = 0; guard < 64; ++guard) {
+        const long long cl = (128ll * (t + 1) - 1) / T;
+        const int c = cl < S ? (int)cl : S;
+        if (m + c == t) break;
+        t = m + c;
+    }
+    return t;
+}
 constexpr int TC_MAX_NQ = 32;       // stages per model on the tensor-core path (4 groups of 8)
 constexpr int TC_MAX_NQ_ZQIS = 8;   // with the per-stage outputs z_q_is: one group (the per-stage out_proj ring shares the TMEM)
 __host__ __device__ constexpr bool tc_shape_ok(int D, int K, int Nq) { return K == 1024 && (D == 1024 || D == 512 || D == 256) && Nq >= 1 && Nq <= TC_MAX_NQ; }

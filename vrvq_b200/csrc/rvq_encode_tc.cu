@@ -349,24 +349,7 @@ __global__ void __launch_bounds__(TC_NTH, 1) rvq_encode_tc_kernel(const TcParams
         const bool first_grp = grp == 0, last_grp = grp == n_grp - 1;
         const int NV = GRP ? TcLayout::vp(grp) : 0, NCT = NCH + NV;  // virtual chunks (cross-group corrections); chunks of this pass
         int tile = (int)blockIdx.x + tile_i * (int)gridDim.x;
-        if constexpr (FLAT) {
-            // Tiles that span two items (the one holding flat frame j T, j = 1 .. B-1) cost ~20 % more -- two TMA boxes per chunk -- and with
-            // the plain round-robin some CTA gets two or three of them.  Permuted order: position q < B-1 is the q-th spanning tile (they go
-            // first, one per CTA), position q >= B-1 the (q - (B-1))-th of the others: least fixpoint of t = m + #{j : floor(j T / 128) <= t}.
-            const int q = tile, S = p.B - 1;
-            if (q < S) {
-                tile = (int)(((long long)(q + 1) * p.T) / 128);
-            } else {
-                const int m = q - S;
-                int t = m;
-                for (int guard = 0; guard < 64; ++guard) {
-                    const int c = min(S, (int)((128ll * (t + 1) - 1) / p.T));
-                    if (m + c == t) break;
-                    t = m + c;
-                }
-                tile = t;
-            }
-        }
+        if constexpr (FLAT) tile = flat_tile_at(tile, p.B, p.T);  // permuted order: the spanning tiles first, one per CTA (common.cuh)
         // Flat tiling (P.flat; never with z_q_is or from_codes): row r of the tile is flat frame 128 tile + r of the (item, frame) sequence;
         // rows [0, ra) belong to item b (frames t0 ..), rows [ra, ra + nb2) to item b + 1 (frames 0 ..) -- T >= 128, so at most two items.
         constexpr bool flat = FLAT;  // (its own instantiation: the extra per-row bookkeeping costs the other shapes 4-8 % through register pressure)
